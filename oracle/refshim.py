@@ -1,0 +1,144 @@
+"""TEST INFRASTRUCTURE ONLY -- load-time Python-3 shim of the reference decoder.
+
+The reference (jacke121/p265, /root/reference) is Python 2 and "all rights reserved"
+(LICENSE:1), so nothing of it is committed here.  `build()` mechanically transforms
+the reference's own files into the git-ignored directory `baseline/_ref/p265ref/`
+(which still travels to the GPU box with gpurun) and `load()` imports them.
+
+Transform, nothing else is touched:
+  1. `print X[,]`            -> `print(X[, end=' '])`
+  2. every `/` operator token -> `//` except on lines containing `float(`
+     (sps.py:151,155, bsb.py:155 really want true division)
+  3. dec.py: `import decoder.X as X` -> `import X` (so `log` is one module)
+  4. stub `matplotlib`, `matplotlib.pyplot`, `matplotlib.patches` (imported at
+     image.py:1-2, tree.py:2-3, slice.py:1; never used while decoding)
+
+Only tests/, bench.py's cpu_baseline / --impl reference leg and
+__graft_entry__ may import this module; the product package never does.
+"""
+from __future__ import annotations
+
+import io
+import os
+import re
+import sys
+import tokenize
+import types
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_ROOT = os.environ.get("P265_REFERENCE_ROOT", "/root/reference")
+SHIM_DIR = os.path.join(REPO, "baseline", "_ref", "p265ref")
+
+_PRINT_RE = re.compile(r"^(\s*)print\s+(?!\()(.*?)(,?)\s*$")
+_PRINT_PAREN_RE = re.compile(r"^(\s*)print\s+(\(.*\))\s*$")
+
+
+def _fix_print(line: str) -> str:
+    body = line.rstrip("\n")
+    m = _PRINT_RE.match(body)
+    if m:
+        indent, expr, comma = m.groups()
+        end = ", end=' '" if comma else ""
+        return "%sprint(%s%s)\n" % (indent, expr, end)
+    return line
+
+
+def _fix_division(src: str) -> str:
+    """Replace the `/` OP token by `//` (py2 int division) except on float( lines."""
+    lines = src.splitlines(keepends=True)
+    edits = []  # (row, col)
+    for tok in tokenize.generate_tokens(io.StringIO(src).readline):
+        if tok.type == tokenize.OP and tok.string == "/":
+            row, col = tok.start
+            if "float(" in lines[row - 1]:
+                continue
+            edits.append((row, col))
+    for row, col in sorted(edits, reverse=True):
+        ln = lines[row - 1]
+        lines[row - 1] = ln[:col] + "//" + ln[col + 1:]
+    return "".join(lines)
+
+
+def transform_source(src: str, name: str) -> str:
+    src = src.replace("\t", "        ")
+    src = "".join(_fix_print(l) for l in src.splitlines(keepends=True))
+    src = _fix_division(src)
+    if name == "dec.py":
+        src = re.sub(r"^import decoder\.(\w+) as \1$", r"import \1", src, flags=re.M)
+    return src
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, "decoder", "transform.py"))
+
+
+def shim_available() -> bool:
+    return os.path.isfile(os.path.join(SHIM_DIR, "transform.py"))
+
+
+def build(force: bool = False) -> str:
+    """Generate baseline/_ref/p265ref/ from REF_ROOT.  Returns the shim dir."""
+    if shim_available() and not force:
+        return SHIM_DIR
+    if not reference_available():
+        raise FileNotFoundError("reference tree not found at %s" % REF_ROOT)
+    os.makedirs(SHIM_DIR, exist_ok=True)
+    dec_dir = os.path.join(REF_ROOT, "decoder")
+    files = [(os.path.join(dec_dir, f), f) for f in sorted(os.listdir(dec_dir))
+             if f.endswith(".py") and f != "__init__.py"]
+    files.append((os.path.join(REF_ROOT, "dec.py"), "dec.py"))
+    files.append((os.path.join(REF_ROOT, "tools", "gen_logs.py"), "gen_logs.py"))
+    for path, name in files:
+        with open(path, "r") as fh:
+            src = fh.read()
+        out = transform_source(src, name)
+        with open(os.path.join(SHIM_DIR, name), "w") as fh:
+            fh.write(out)
+    # the bitstream fixture travels too (28 KB) so the GPU box can decode it
+    with open(os.path.join(REF_ROOT, "sanity.bin"), "rb") as fi, \
+            open(os.path.join(SHIM_DIR, "sanity.bin"), "wb") as fo:
+        fo.write(fi.read())
+    return SHIM_DIR
+
+
+def _stub_matplotlib() -> None:
+    if "matplotlib" in sys.modules:
+        return
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches"):
+        sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["matplotlib"].patches = sys.modules["matplotlib.patches"]
+
+
+def load(workdir: str | None = None):
+    """Import the shimmed reference; returns a namespace of its modules.
+
+    The reference's log.py opens logs/*.log relative to the cwd at import time
+    (log.py:33-83), so the first call chdir()s into `workdir` (a scratch dir with a
+    logs/ sub-directory) for the import.
+    """
+    if not shim_available():
+        build()
+    _stub_matplotlib()
+    if SHIM_DIR not in sys.path:
+        sys.path.insert(0, SHIM_DIR)
+    import tempfile
+    if "log" not in sys.modules or not hasattr(sys.modules["log"], "syntax"):
+        wd = workdir or tempfile.mkdtemp(prefix="p265ref_")
+        os.makedirs(os.path.join(wd, "logs"), exist_ok=True)
+        cwd = os.getcwd()
+        os.chdir(wd)
+        try:
+            import log  # noqa: F401
+        finally:
+            os.chdir(cwd)
+    import importlib
+    ns = types.SimpleNamespace()
+    for name in ("utils", "scaling", "transform", "reconstruction", "sao", "tu", "cu",
+                 "ctu", "nalu", "context", "log", "dec", "sld", "scan", "image", "intra"):
+        setattr(ns, name, importlib.import_module(name))
+    return ns
+
+
+if __name__ == "__main__":
+    print(build(force=True))

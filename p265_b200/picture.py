@@ -1,0 +1,140 @@
+"""Packed per-picture formats at the host <-> C-ABI boundary.
+
+Names follow the decoder's domain: a *TB* (transform block) is one component's block
+of one leaf transform unit; a *TU descriptor* is its 16-byte record; the *coefficient
+arena* holds every coded TB's TransCoeffLevel values, TB after TB, row-major [y][x]
+int16 (the reference stores them [x][y] int64 per leaf, tu.py:87-90,331).
+
+Everything here is plain numpy; nothing computes residuals or SAO on the CPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+#: mirrors `p265_tu_desc` in include/p265_b200.h (16 bytes, little endian)
+TU_DESC = np.dtype([("x", "<u2"), ("y", "<u2"),        # component-plane sample coords
+                    ("log2n", "u1"), ("c_idx", "u1"),
+                    ("qp", "u1"),                        # qP incl. QpBdOffset (scaling.py:13-18)
+                    ("flags", "u1"),
+                    ("coeff_off", "<u4"),                # arena offset in units of 16 coeffs
+                    ("pic", "<u2"), ("rsvd", "<u2")])
+assert TU_DESC.itemsize == 16
+
+TU_DST = 1        # trType = 1: 4x4 luma intra (8.6.4.2; transform.py:97)
+TU_SKIP = 2       # transform_skip_flag (tu.py:142-143)
+TU_BYPASS = 4     # cu_transquant_bypass_flag (cu.py:102-105)
+TU_INTRA = 8      # CuPredMode == MODE_INTRA -> matrixId (scaling.py:33-42)
+
+#: mirrors `p265_sao_ctb` (24 bytes)
+SAO_CTB = np.dtype([("type", "u1", 3), ("band_pos", "u1", 3), ("eo_class", "u1", 3),
+                    ("offset_val", "i1", (3, 4)), ("pad", "u1"), ("avail", "<u2")])
+assert SAO_CTB.itemsize == 24
+
+#: all eight neighbouring CTBs usable (bit (dy+1)*3+(dx+1), centre bit unused)
+AVAIL_ALL = 0x1FF
+
+SF_BYTES = 4064
+_SF_OFFSETS = (0, 96, 480, 2016)
+
+
+def align_up(v: int, a: int) -> int:
+    return (v + a - 1) // a * a
+
+
+@dataclass
+class PicGeom:
+    """Plane geometry of a batch of 4:2:0 (or 4:0:0-like luma-only) pictures.
+
+    Mirrors `p265_pic_geom`.  Planes of one picture are laid out Y, Cb, Cr inside one
+    buffer; pictures follow each other `pic_stride` elements apart."""
+    width: int                      # luma samples
+    height: int
+    n_pics: int = 1
+    bit_depth_y: int = 8
+    bit_depth_c: int = 8
+    stride_align: int = 64          # elements; 128 B rows for int16 / uint16 planes
+    width_c: int = field(init=False)
+    height_c: int = field(init=False)
+    stride_y: int = field(init=False)
+    stride_c: int = field(init=False)
+    plane_off: tuple = field(init=False)
+    pic_stride: int = field(init=False)
+
+    def __post_init__(self):
+        if self.width <= 0 or self.height <= 0 or self.width % 2 or self.height % 2:
+            raise ValueError("picture size must be positive and even (4:2:0)")
+        self.width_c, self.height_c = self.width // 2, self.height // 2
+        self.stride_y = align_up(self.width, self.stride_align)
+        self.stride_c = align_up(self.width_c, self.stride_align)
+        y = self.stride_y * self.height
+        c = self.stride_c * self.height_c
+        self.plane_off = (0, y, y + c)
+        self.pic_stride = align_up(y + 2 * c, 64)
+
+    # ---- helpers -------------------------------------------------------------
+    def plane_shape(self, c_idx: int):
+        return (self.height, self.width) if c_idx == 0 else (self.height_c, self.width_c)
+
+    def stride(self, c_idx: int) -> int:
+        return self.stride_y if c_idx == 0 else self.stride_c
+
+    def total_elems(self) -> int:
+        return self.pic_stride * self.n_pics
+
+    def plane_view(self, buf: np.ndarray, pic: int, c_idx: int) -> np.ndarray:
+        """(H, W) strided view of plane `c_idx` of picture `pic` inside flat `buf`."""
+        h, w = self.plane_shape(c_idx)
+        s = self.stride(c_idx)
+        off = pic * self.pic_stride + self.plane_off[c_idx]
+        return buf[off:off + h * s].reshape(h, s)[:, :w]
+
+    def pixels(self) -> int:
+        return self.width * self.height * self.n_pics
+
+
+@dataclass
+class ResidualBatch:
+    """Everything one residual launch needs: descriptors binned by size (32,16,8,4),
+    the coefficient arena and, optionally, the 4064-byte ScalingFactor table."""
+    geom: PicGeom
+    tus: np.ndarray                         # TU_DESC, sorted by log2n descending
+    coeffs: np.ndarray                      # int16 arena
+    scaling_factor: np.ndarray | None = None    # uint8[4064] or None (flat 16)
+    covers_all: bool = False                # TBs tile every plane completely
+
+    def bin_counts(self):
+        l2 = self.tus["log2n"]
+        return tuple(int((l2 == k).sum()) for k in (5, 4, 3, 2))
+
+    def samples(self) -> int:
+        return int((1 << (2 * self.tus["log2n"].astype(np.int64))).sum())
+
+
+def sort_by_size(tus: np.ndarray) -> np.ndarray:
+    """Stable sort, largest TBs first -- the order `p265_residual_*` requires."""
+    order = np.argsort(-tus["log2n"].astype(np.int16), kind="stable")
+    return np.ascontiguousarray(tus[order])
+
+
+def sf_offset(size_id: int, matrix_id: int) -> int:
+    n = 4 << size_id
+    return _SF_OFFSETS[size_id] + matrix_id * n * n
+
+
+def pack_scaling_factor(sf: dict) -> np.ndarray:
+    """{(sizeId, matrixId): (N, N) [x][y] array} -> device table uint8[4064], each
+    matrix row-major [y][x].  `sf` uses the reference's indexing
+    sps.scaling_factor[size_id][matrix_id][x][y] (scaling.py:44)."""
+    out = np.full(SF_BYTES, 16, dtype=np.uint8)
+    for (s, m), f in sf.items():
+        n = 4 << s
+        f = np.asarray(f)
+        if f.shape != (n, n):
+            raise ValueError("ScalingFactor[%d][%d] must be %dx%d" % (s, m, n, n))
+        if f.min() < 1 or f.max() > 255:
+            raise ValueError("ScalingFactor entries must be in 1..255")
+        off = sf_offset(s, m)
+        out[off:off + n * n] = f.T.reshape(-1)
+    return out
