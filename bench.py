@@ -1,0 +1,462 @@
+#!/usr/bin/env python
+"""Benchmark of the residual + SAO path at 4K 10-bit (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--pics P] [--impl reference]
+
+A *step* is one pass of the hot path over one batch of P synthetic 4K 10-bit 4:2:0
+pictures: one residual launch (config 3: TB mix skewed to 32x32, default scaling
+lists, transform-skip, bypass) + one SAO launch (config 4: band + all four edge
+classes, per-CTB parameters).  Metric: Mpixel/s, pixel = luma sample position of the
+3840x2160 picture.
+
+  value     device-resident inputs/outputs, CUDA events on the launching stream, max
+            over ranks (N > 1: one process per GPU, pictures/streams partitioned by
+            rank, no data-path collective -> weak scaling)
+  e2e       same step through the public host API (Engine.residual / Engine.sao ->
+            C-ABI p265_residual_batch / p265_sao_batch) from pinned host buffers,
+            H2D and D2H copies inside the timed region
+  roofline  dominant kernel vs measured HBM bandwidth (MEASURED_PEAKS.json), dense
+            algorithmic bytes: residual 4 B/sample + 16 B/TB, SAO
+            4 B/sample at 10 bits
+  cpu_baseline  the reference's own pure-Python scaling.py + transform.py (through the
+            py3 shim, 1 core) on a stratified TB sample, + the oracle's SAO (the
+            reference has none); N=1 only
+
+`--impl reference` times that CPU path with all host cores.  Nothing here reads
+/root/reference at run time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+PIC_W, PIC_H = 3840, 2160
+METRIC = "Mpixel/s residual+SAO at 4K 10-bit"
+
+
+# ------------------------------------------------------------------------ helpers
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0.0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for n, v in zip(names, s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def pinned(n_bytes):
+    import torch
+    return torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
+
+
+# ------------------------------------------------------------------ workload
+def make_workload(n_pics: int, seed_base: int):
+    from p265_b200 import synth
+    res = synth.residual_batch("4k10", n_pics=n_pics, seed=seed_base, n_unique=min(2, n_pics))
+    geom, rec, params = synth.sao_batch(PIC_W, PIC_H, 10, n_pics=n_pics, seed=seed_base + 1000,
+                                        n_unique=min(2, n_pics))
+    return res, geom, rec, params
+
+
+def alg_bytes(res, sao_geom):
+    """Dense algorithmic bytes per launch."""
+    samples = res.samples()
+    r = 4 * samples + 16 * len(res.tus)
+    s_samples = sao_geom.n_pics * (sao_geom.width * sao_geom.height * 3 // 2)
+    return r, 4 * s_samples, samples, s_samples
+
+
+def alg_int_ops(res):
+    """Dense even/odd butterfly op count: per sample 20/23/28.5/39.25."""
+    ops = {2: 20.0, 3: 23.0, 4: 28.5, 5: 39.25}
+    l2 = res.tus["log2n"]
+    return float(sum(ops[k] * int((l2 == k).sum()) * (1 << (2 * k)) for k in (2, 3, 4, 5)))
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from p265_b200.engine import Engine
+    from p265_b200.picture import SAO_CTB, TU_DESC
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    # stream s -> GPU s mod G; each rank owns the streams 26510 + rank
+    res, sgeom, rec, params = make_workload(args.pics, 26510 + rank)
+    stream = torch.cuda.Stream(device=dev)
+    eng = Engine(local, stream.cuda_stream)
+
+    def to_dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+
+    d_tus, d_co = to_dev(res.tus), to_dev(res.coeffs)
+    d_sf = to_dev(res.scaling_factor) if res.scaling_factor is not None else None
+    d_res = torch.empty(res.geom.total_elems() * 2, dtype=torch.uint8, device=dev)
+    d_rec, d_par = to_dev(rec), to_dev(params)
+    d_sao = torch.empty_like(d_rec)
+    bins = res.bin_counts()
+    torch.cuda.synchronize()
+
+    def residual():
+        eng.residual_dev(d_tus.data_ptr(), bins, d_co.data_ptr(), d_sf.data_ptr() if d_sf is not None else None,
+                         res.geom, d_res.data_ptr(), zero_fill=not res.covers_all)
+
+    def sao():
+        eng.sao_dev(d_rec.data_ptr(), d_sao.data_ptr(), sgeom, 6, d_par.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1)
+
+    def step():
+        residual()
+        sao()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = eng.launch_count
+    ms_total = timed(step, args.steps)
+    launches = eng.launch_count - l0
+    barrier()
+    # per-kernel durations for the roofline (same stream, same buffers, > L2 working set)
+    ms_res = timed(residual, args.steps) / args.steps
+    ms_sao = timed(sao, args.steps) / args.steps
+    clocks = sampler.stop()
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total_max = float(t.item())
+    pixels_step = PIC_W * PIC_H * args.pics * world
+    value = pixels_step * args.steps / (ms_total_max * 1e-3) / 1e6
+
+    # ---- end to end through the host API (pinned host buffers, copies timed) ----
+    e2e_pics = min(args.pics, args.e2e_pics)
+    res_h, sgeom_h, rec_h, params_h = (res, sgeom, rec, params) if e2e_pics == args.pics else \
+        make_workload(e2e_pics, 26510 + rank)
+    eng2 = Engine(local)
+
+    def pin(a):
+        a = np.ascontiguousarray(a)
+        t_ = pinned(a.nbytes)
+        v = t_.numpy().view(a.dtype).reshape(a.shape)
+        v[...] = a
+        return t_, v
+
+    keep = []
+    k_tus, h_tus = pin(res_h.tus)
+    k_co, h_co = pin(res_h.coeffs)
+    k_rec, h_rec = pin(rec_h)
+    k_ro = pinned(res_h.geom.total_elems() * 2)
+    h_ro = k_ro.numpy().view(np.int16)
+    k_so = pinned(rec_h.nbytes)
+    h_so = k_so.numpy().view(rec_h.dtype)
+    keep += [k_tus, k_co, k_rec, k_ro, k_so]
+    from p265_b200.picture import ResidualBatch
+    hb = ResidualBatch(res_h.geom, h_tus, h_co, res_h.scaling_factor, res_h.covers_all)
+
+    def e2e_step():
+        eng2.residual(hb, out=h_ro)
+        eng2.sao(h_rec, sgeom_h, 6, params_h, out=h_so)
+
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = PIC_W * PIC_H * e2e_pics * world * e2e_steps / float(t.item()) / 1e6
+    h2d = res_h.tus.nbytes + res_h.coeffs.nbytes + rec_h.nbytes + params_h.nbytes + \
+        (res_h.scaling_factor.nbytes if res_h.scaling_factor is not None else 0)
+    d2h = h_ro.nbytes + h_so.nbytes
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_kind = measured_peaks()
+    b_res, b_sao, n_samples, s_samples = alg_bytes(res, sgeom)
+    kernels = {"residual_kernel": (b_res, ms_res), "sao_kernel": (b_sao, ms_sao)}
+    dom = max(kernels, key=lambda k: kernels[k][1])
+    ach = kernels[dom][0] / (kernels[dom][1] * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(REPO, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(dom, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    int_peak = {}
+    for kind, name in ((0, "imad"), (1, "iadd3"), (2, "imad+iadd3"), (3, "dp2a"), (4, "shf"), (5, "dp2a+iadd3")):
+        try:
+            int_peak[name] = round(eng.int_peak(kind)[0] / 1e12, 3)
+        except Exception as e:  # pragma: no cover
+            int_peak[name] = str(e)
+    best_int = max(v for v in int_peak.values() if isinstance(v, float))
+    ops = alg_int_ops(res)
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(ms_total_max / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32 (int16 data x int8 basis, dp2a)",
+        "data": "synthetic",
+        "config": {"workload": "4K 10-bit 4:2:0: residual (config 3: 5/10/25/60 % 4/8/16/32 luma area, default "
+                               "scaling lists, TS 10 % of 4x4, bypass 1 %) + SAO (config 4) per picture",
+                   "pics_per_step_per_gpu": args.pics, "tbs_per_step": int(len(res.tus)),
+                   "partition": "stream s -> GPU s mod G, no collective",
+                   "l2": "inputs larger than L2 (%.0f MB touched per step)" % ((b_res + b_sao) / 1e6)},
+        "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "pics_per_step_per_gpu": e2e_pics, "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1),
+                     "peak": peaks["hbm_gbs"], "peak_source": peak_kind, "unit": "GB/s",
+                     "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": traffic,
+                     "alg_bytes_per_launch": int(kernels[dom][0]),
+                     "kernels": {k: {"ms": round(v[1], 4), "alg_gbs": round(v[0] / (v[1] * 1e-3) / 1e9, 1),
+                                     "frac_hbm": round(v[0] / (v[1] * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)}
+                                 for k, v in kernels.items()},
+                     "combined_frac_hbm": round((b_res + b_sao) / ((ms_res + ms_sao) * 1e-3) / 1e9
+                                                / peaks["hbm_gbs"], 4),
+                     "int32": {"peak_tops_measured": int_peak,
+                               "residual_alg_gops_per_launch": round(ops / 1e9, 2),
+                               "residual_alg_tops": round(ops / (ms_res * 1e-3) / 1e12, 2),
+                               "residual_frac_of_best_int_peak": round(ops / (ms_res * 1e-3) / 1e12 / best_int, 4)}},
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(single_core=True)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ CPU arms
+def _ref_worker(task):
+    """Times the reference's own inverse_scaling + inverse_transform on a share of the
+    stratified sample (runs in a worker process)."""
+    seed, counts = task
+    sys.path.insert(0, REPO)
+    from oracle import refshim
+    import tempfile
+    ns = refshim.load(tempfile.mkdtemp(prefix="p265ref_"))
+    sys.path.insert(0, os.path.join(REPO, "tests", "golden"))
+    from make_fixtures import fake_pu
+    from p265_b200 import scaling_list
+    sf = scaling_list.as_reference_object(scaling_list.default_scaling_factor())
+    rng = np.random.default_rng(seed)
+    out = {}
+    for l2, cnt in counts.items():
+        n = 1 << l2
+        t = 0.0
+        for _ in range(cnt):
+            lv = (rng.laplace(0, 6, (n, n)) * (rng.random((n, n)) < 0.2)).astype(np.int64)
+            pu = fake_pu(lv, 0, int(rng.integers(34, 50)), 10, sf=sf)
+            t0 = time.perf_counter()
+            ns.scaling.inverse_scaling(pu=pu, x0=0, y0=0, log2size=l2)
+            ns.transform.inverse_transform(pu=pu, x0=0, y0=0, log2size=l2)
+            t += time.perf_counter() - t0
+        out[l2] = (cnt, t)
+    return out
+
+
+def cpu_residual_reference(cores: int):
+    """Seconds per 4K picture of the reference's pure-Python residual path, extrapolated
+    from a stratified TB sample by the config-3 TB counts.  Returns (sec, kind, sample)."""
+    from oracle import refshim
+    from p265_b200 import synth
+    pic = synth.residual_batch("4k10", n_pics=1, seed=26510)
+    l2 = pic.tus["log2n"]
+    tb_counts = {k: int((l2 == k).sum()) for k in (2, 3, 4, 5)}
+    if not refshim.shim_available():
+        return None, "port", tb_counts
+    per_core = {5: 24, 4: 48, 3: 96, 2: 192}
+    tasks = [(100 + i, per_core) for i in range(cores)]
+    t0 = time.perf_counter()
+    if cores == 1:
+        results = [_ref_worker(tasks[0])]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("spawn").Pool(cores) as pool:
+            results = pool.map(_ref_worker, tasks)
+    wall = time.perf_counter() - t0
+    sec = 0.0
+    for k in (2, 3, 4, 5):
+        cnt = sum(r[k][0] for r in results)
+        tt = sum(r[k][1] for r in results)
+        sec += tb_counts[k] * (tt / cnt)
+    sample = ("stratified %s TBs per size per core (32/16/8/4), %d core(s), %.1f s wall; per-TB time x "
+              "config-3 TB counts %s" % (per_core, cores, wall, tb_counts))
+    return sec / cores, "reference", sample
+
+
+def cpu_sao_port(threads: int):
+    """Seconds per 4K picture of the oracle's SAO (the reference has no SAO filter)."""
+    from oracle import c_oracle
+    from p265_b200 import synth
+    c_oracle.build()
+    c_oracle.lib().oracle_set_threads(threads)
+    geom, rec, params = synth.sao_batch(PIC_W, PIC_H, 10, n_pics=1, seed=27510)
+    t0 = time.perf_counter()
+    c_oracle.sao_batch(rec, geom, 6, params)
+    dt = time.perf_counter() - t0
+    c_oracle.lib().oracle_set_threads(0)
+    return dt
+
+
+def cpu_residual_port(threads: int):
+    from oracle import c_oracle
+    from p265_b200 import synth
+    c_oracle.build()
+    c_oracle.lib().oracle_set_threads(threads)
+    pic = synth.residual_batch("4k10", n_pics=1, seed=26510)
+    t0 = time.perf_counter()
+    c_oracle.residual_batch(pic, zero_fill=False)
+    dt = time.perf_counter() - t0
+    c_oracle.lib().oracle_set_threads(0)
+    return dt
+
+
+def cpu_baseline(single_core: bool):
+    cores = 1 if single_core else (os.cpu_count() or 1)
+    sec_res, kind, sample = cpu_residual_reference(cores)
+    if sec_res is None:
+        sec_res = cpu_residual_port(cores)
+        sample = "oracle/spec_oracle.c on one full 4K picture (reference shim not present on this box)"
+    sec_sao = cpu_sao_port(cores)
+    port_all = cpu_residual_port(0) + cpu_sao_port(0)
+    return {"value": round(PIC_W * PIC_H / (sec_res + sec_sao) / 1e6, 6), "unit": "Mpixel/s", "cores": cores,
+            "kind": kind,
+            "sample": "residual: %s; SAO: oracle/spec_oracle.c on one 4K picture (the reference has no SAO "
+                      "filter)" % sample,
+            "sec_per_picture": {"residual": round(sec_res, 3), "sao": round(sec_sao, 4)},
+            "port_all_cores": {"value": round(PIC_W * PIC_H / port_all / 1e6, 3), "unit": "Mpixel/s",
+                               "cores": os.cpu_count(), "what": "oracle/spec_oracle.c residual + SAO, one 4K "
+                                                                "picture, pthreads"}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    values, last = [], None
+    for i in range(max(1, min(args.steps, 3)) + min(args.warmup, 1)):
+        last = cpu_baseline(single_core=False)
+        if i >= min(args.warmup, 1):
+            values.append(last["value"])
+    v = float(np.mean(values))
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 6), "unit": "Mpixel/s",
+            "n_gpus": args.gpus, "steps": len(values), "warmup": min(args.warmup, 1),
+            "ms_per_step": round(PIC_W * PIC_H / (v * 1e6) * 1e3, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int64 (numpy / Python int)", "data": "synthetic",
+            "config": {"workload": "4K 10-bit 4:2:0 residual (config 3) + SAO (config 4), one picture per step, "
+                                   "bounded stratified sample (see cpu_baseline.sample)"},
+            "cpu_baseline": dict(last, value=round(v, 6), cores=cores),
+            "e2e": {"value": round(v, 6), "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--pics", type=int, default=8, help="4K pictures per step per GPU")
+    ap.add_argument("--e2e-pics", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

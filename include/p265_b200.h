@@ -1,0 +1,153 @@
+/*
+ * p265_b200 -- C-ABI of the B200 (sm_100a) residual + SAO path.
+ *
+ * Reference: jacke121/p265 is pure Python and has no FFI; the interface this
+ * library replaces is the Python function surface of
+ *     decoder/scaling.py:4     inverse_scaling(pu, x0, y0, log2size)
+ *     decoder/transform.py:89  inverse_transform(pu, x0, y0, log2size)
+ *     decoder/sao.py:4         class Sao   (per-CTB parameters; the filter itself
+ *                              does not exist in the reference)
+ * re-cut at picture granularity: the host packs every coded TB of
+ * a batch of pictures into a descriptor list + coefficient arena and one call
+ * produces the residual planes; a second call applies SAO to reconstructed planes.
+ * p265_b200/{scaling,transform,sao}.py bind these entry points with ctypes and keep
+ * the reference's per-TB names on top.
+ *
+ * All entry points return 0 on success or a negative p265_status; the message of
+ * the last failure on the calling thread is available from p265_last_error().
+ * There is no CPU fallback: without a CUDA device p265_ctx_create() fails.
+ *
+ * Thread-safety: one p265_ctx per host thread / GPU; calls on one context are
+ * serialised by the caller; every context owns (or borrows) exactly one stream.
+ */
+#ifndef P265_B200_H
+#define P265_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P265_ABI_VERSION 1
+
+typedef enum p265_status {
+    P265_OK = 0,
+    P265_EINVAL = -1,  /* bad argument (Python wrapper raises ValueError)   */
+    P265_ECUDA = -2,   /* CUDA runtime failure (RuntimeError)               */
+    P265_ENOMEM = -3   /* device or pinned allocation failed (RuntimeError) */
+} p265_status;
+
+typedef struct p265_ctx p265_ctx;
+
+/* One coded transform block.  Replaces the per-coefficient
+ * tu.get_trans_coeff_level(x, y, c_idx) walk (tu.py:667-684) and the per-call
+ * pu / cu / sps attribute reads of scaling.py:13-44.                               */
+typedef struct p265_tu_desc {
+    uint16_t x, y;       /* top-left sample in the component's plane                */
+    uint8_t log2n;       /* 2..5                                                    */
+    uint8_t c_idx;       /* 0 Y, 1 Cb, 2 Cr                                         */
+    uint8_t qp;          /* qP including QpBdOffset (scaling.py:13-18)              */
+    uint8_t flags;       /* P265_TU_*                                               */
+    uint32_t coeff_off;  /* offset into the coefficient arena, units of 16 coeffs   */
+    uint16_t pic;        /* picture index inside the batch                          */
+    uint16_t rsvd;
+} p265_tu_desc;
+
+#define P265_TU_DST 1u    /* trType 1: 4x4 luma of an intra CU (transform.py:97)     */
+#define P265_TU_SKIP 2u   /* transform_skip_flag (tu.py:142-143)                     */
+#define P265_TU_BYPASS 4u /* cu_transquant_bypass_flag (scaling.py:20-21 raises)     */
+#define P265_TU_INTRA 8u  /* selects matrixId (scaling.py:33-42)                     */
+#define P265_TU_PRESCALED 16u /* arena already holds d[] (pu.scaled_samples): skip 8.6.3;
+                                 only with scaling_factor == NULL                      */
+
+/* Planes of a batch of 4:2:0 pictures inside ONE buffer: picture p, component c
+ * starts at element p * pic_stride + plane_off[c]; rows are stride_{y,c} elements
+ * apart.  Element = int16 for residual planes, uint8 (both bit depths <= 8) or
+ * uint16 for sample planes.                                                        */
+typedef struct p265_pic_geom {
+    int32_t width, height; /* luma samples; chroma planes are width/2 x height/2    */
+    int32_t n_pics;
+    int32_t bit_depth_y, bit_depth_c;
+    int32_t stride_y, stride_c;
+    int32_t rsvd;
+    int64_t plane_off[3];
+    int64_t pic_stride;
+} p265_pic_geom;
+
+/* SAO parameters of one CTB: the fields sao.Sao.parse() fills (sao.py:43-77), with
+ * SaoOffsetVal[1..4] already derived (7.4.9.3.2).                                  */
+typedef struct p265_sao_ctb {
+    uint8_t type[3];          /* 0 off, 1 band, 2 edge                              */
+    uint8_t band_pos[3];
+    uint8_t eo_class[3];
+    int8_t offset_val[3][4];
+    uint8_t pad;
+    uint16_t avail;           /* bit (dy+1)*3+(dx+1): neighbour CTB usable (8.7.3)   */
+} p265_sao_ctb;
+
+#define P265_SF_BYTES 4064 /* ScalingFactor table: [sizeId][matrixId][y][x] uint8    */
+
+#define P265_RES_ZERO_FILL 1 /* clear the planes first (TBs do not cover them)       */
+
+/* ---- context ------------------------------------------------------------------ */
+int p265_abi_version(void);
+const char *p265_last_error(void);
+int p265_device_count(void);
+/* stream == NULL: the context creates its own non-blocking stream                  */
+int p265_ctx_create(int device, void *stream, p265_ctx **out);
+int p265_ctx_destroy(p265_ctx *ctx);
+int p265_sync(p265_ctx *ctx);
+int p265_sm_count(p265_ctx *ctx);
+/* kernels launched through this context so far (bench.py reports it as gpu_launches) */
+uint64_t p265_launch_count(p265_ctx *ctx);
+
+/* ---- residual: dequantisation + inverse transform (scaling.py + transform.py) --- */
+/* tus sorted by log2n descending; bin_counts = number of 32x32,16x16,8x8,4x4 TBs.  */
+int p265_residual_batch(p265_ctx *ctx, const p265_tu_desc *tus, const int32_t bin_counts[4],
+                        const int16_t *coeffs, size_t n_coeffs,
+                        const uint8_t *scaling_factor /* P265_SF_BYTES or NULL = flat 16 */,
+                        const p265_pic_geom *geom, int16_t *residual /* host out */,
+                        int flags);
+/* same, every pointer already resident in device memory; asynchronous on the stream */
+int p265_residual_batch_dev(p265_ctx *ctx, const p265_tu_desc *d_tus,
+                            const int32_t bin_counts[4], const int16_t *d_coeffs,
+                            const uint8_t *d_scaling_factor, const p265_pic_geom *geom,
+                            int16_t *d_residual, int flags);
+/* scaling.inverse_scaling only: d[] in arena layout (pu.scaled_samples content)    */
+int p265_dequant_batch(p265_ctx *ctx, const p265_tu_desc *tus, int32_t n_tus,
+                       const int16_t *coeffs, size_t n_coeffs, const uint8_t *scaling_factor,
+                       int bit_depth_y, int bit_depth_c, int16_t *scaled /* host out */);
+/* transform.py:89-109 exactly as written (parity-test-only): in d[]
+ * arena ([y][x] per TB), out r[] int32 arena, [x][y] per TB like the reference     */
+int p265_ref_literal_batch(p265_ctx *ctx, const p265_tu_desc *tus, int32_t n_tus,
+                           const int16_t *scaled, size_t n_coeffs, int32_t *out);
+
+/* transform.inverse_transform_1d(x, log2size, tr_type) (transform.py:74-87) on one
+ * vector: mode 0 = the standard's orientation y[i] = sum_j M[j][i] x[j] (8.6.4.2),
+ * mode 1 = as written in the reference, y[i] = sum_j M[i][j*32/N] x[j].  Host in/out. */
+int p265_idct_1d(p265_ctx *ctx, const int32_t *x, int log2size, int tr_type, int mode,
+                 int32_t *y);
+
+/* ---- SAO (8.7.3; parameters from sao.py) ---------------------------------------- */
+/* params: n_pics * ctbs_h * ctbs_w records, raster order per picture.
+ * no_filter: NULL or n_pics * ceil(h/8) * ceil(w/8) bytes, non-zero = luma 8x8 block
+ * (and its 4x4 chroma blocks) keeps its samples (pcm + pcm_loop_filter_disabled,
+ * cu_transquant_bypass).                                                           */
+int p265_sao_batch(p265_ctx *ctx, const void *rec /* host in */, void *out /* host out */,
+                   const p265_pic_geom *geom, int ctb_log2, const p265_sao_ctb *params,
+                   const uint8_t *no_filter);
+int p265_sao_batch_dev(p265_ctx *ctx, const void *d_rec, void *d_out,
+                       const p265_pic_geom *geom, int ctb_log2, const p265_sao_ctb *d_params,
+                       const uint8_t *d_no_filter);
+
+/* ---- measurement helpers ------------------------------------------------------- */
+/* Register-resident integer-pipe microbenchmark; kind: 0 IMAD, 1 IADD3, 2 IMAD+IADD3
+ * interleaved, 3 DP2A, 4 SHF, 5 DP2A+IADD3.  Returns lane-ops per second.           */
+int p265_int_peak(p265_ctx *ctx, int kind, double *ops_per_s, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P265_B200_H */

@@ -1,0 +1,370 @@
+// C-ABI of libp265b200.so (include/p265_b200.h): contexts, argument validation, the
+// host-buffer entry points (H2D -> kernel -> D2H on the context's stream) and the
+// device-resident entry points the benchmark times.  No CPU fallback anywhere: every
+// entry point needs a live CUDA context or fails with P265_ECUDA.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "internal.h"
+
+namespace p265 {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_error(cudaError_t e, const char *what, const char *file, int line) {
+    const char *base = strrchr(file, '/');
+    set_error(P265_ECUDA, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), base ? base + 1 : file,
+              line, what);
+    return e == cudaErrorMemoryAllocation ? P265_ENOMEM : P265_ECUDA;
+}
+
+static int ensure(p265_ctx *ctx, int slot, size_t bytes, void **out) {
+    if (bytes == 0) bytes = 16;
+    if (ctx->scratch_bytes[slot] < bytes) {
+        if (ctx->scratch[slot]) P265_CUDA(cudaFree(ctx->scratch[slot]));
+        ctx->scratch[slot] = nullptr;
+        ctx->scratch_bytes[slot] = 0;
+        size_t cap = bytes + bytes / 4;  // grow-only with head-room
+        P265_CUDA(cudaMalloc(&ctx->scratch[slot], cap));
+        ctx->scratch_bytes[slot] = cap;
+    }
+    *out = ctx->scratch[slot];
+    return P265_OK;
+}
+
+static int check_geom(const p265_pic_geom *g, int elem_align) {
+    if (!g) return set_error(P265_EINVAL, "geometry is NULL");
+    if (g->width <= 0 || g->height <= 0 || (g->width & 1) || (g->height & 1))
+        return set_error(P265_EINVAL, "picture size %dx%d must be positive and even", g->width, g->height);
+    if (g->n_pics <= 0) return set_error(P265_EINVAL, "n_pics must be positive");
+    if (g->bit_depth_y < 8 || g->bit_depth_y > 12 || g->bit_depth_c < 8 || g->bit_depth_c > 12)
+        return set_error(P265_EINVAL, "bit depths %d/%d outside 8..12", g->bit_depth_y, g->bit_depth_c);
+    if (g->stride_y < g->width || g->stride_c < g->width / 2)
+        return set_error(P265_EINVAL, "strides %d/%d smaller than the plane widths", g->stride_y, g->stride_c);
+    if (g->stride_y % elem_align || g->stride_c % elem_align || g->pic_stride % elem_align)
+        return set_error(P265_EINVAL, "strides must be multiples of %d elements (16-byte rows)", elem_align);
+    for (int c = 0; c < 3; c++)
+        if (g->plane_off[c] < 0 || g->plane_off[c] % elem_align)
+            return set_error(P265_EINVAL, "plane_off[%d] must be a non-negative multiple of %d", c, elem_align);
+    const int64_t need_y = (int64_t)g->stride_y * g->height, need_c = (int64_t)g->stride_c * (g->height / 2);
+    if (g->plane_off[0] + need_y > g->pic_stride || g->plane_off[1] + need_c > g->pic_stride ||
+        g->plane_off[2] + need_c > g->pic_stride)
+        return set_error(P265_EINVAL, "planes do not fit inside pic_stride");
+    return P265_OK;
+}
+
+// host-side validation of a descriptor list (host entry points only)
+static int check_tus(const p265_tu_desc *tus, const int32_t bin_counts[4], size_t n_coeffs, const p265_pic_geom *g) {
+    int64_t k = 0;
+    for (int b = 0; b < 4; b++) {
+        if (bin_counts[b] < 0) return set_error(P265_EINVAL, "negative bin count");
+        const int log2n = 5 - b, n = 1 << log2n;
+        for (int32_t i = 0; i < bin_counts[b]; i++, k++) {
+            const p265_tu_desc &t = tus[k];
+            if (t.log2n != log2n)
+                return set_error(P265_EINVAL, "descriptor %lld: log2n %d where bin expects %d (list must be sorted "
+                                 "32,16,8,4)", (long long)k, t.log2n, log2n);
+            if (t.c_idx > 2) return set_error(P265_EINVAL, "descriptor %lld: c_idx %d", (long long)k, t.c_idx);
+            const int w = t.c_idx ? g->width / 2 : g->width, h = t.c_idx ? g->height / 2 : g->height;
+            if (t.x % n || t.y % n || t.x + n > w || t.y + n > h)
+                return set_error(P265_EINVAL, "descriptor %lld: %dx%d block at (%d,%d) outside the %dx%d plane or "
+                                 "unaligned", (long long)k, n, n, t.x, t.y, w, h);
+            if (t.pic >= g->n_pics) return set_error(P265_EINVAL, "descriptor %lld: picture %d", (long long)k, t.pic);
+            if ((size_t)t.coeff_off * 16 + (size_t)n * n > n_coeffs)
+                return set_error(P265_EINVAL, "descriptor %lld: coefficients beyond the arena", (long long)k);
+            if ((t.flags & P265_TU_SKIP) && log2n != 2)
+                return set_error(P265_EINVAL, "descriptor %lld: transform_skip on a %dx%d block", (long long)k, n, n);
+            if ((t.flags & P265_TU_DST) && (log2n != 2 || t.c_idx != 0))
+                return set_error(P265_EINVAL, "descriptor %lld: DST on a non-4x4-luma block", (long long)k);
+            if (t.qp > 51 + 6 * ((t.c_idx ? g->bit_depth_c : g->bit_depth_y) - 8))
+                return set_error(P265_EINVAL, "descriptor %lld: qP %d out of range", (long long)k, t.qp);
+        }
+    }
+    return P265_OK;
+}
+
+}  // namespace p265
+
+using namespace p265;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int p265_abi_version(void) { return P265_ABI_VERSION; }
+
+const char *p265_last_error(void) { return g_err; }
+
+int p265_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int p265_ctx_create(int device, void *stream, p265_ctx **out) {
+    if (!out) return set_error(P265_EINVAL, "p265_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    P265_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return set_error(P265_EINVAL, "device %d out of range (have %d)", device, n);
+    P265_CUDA(cudaSetDevice(device));
+    p265_ctx *ctx = new p265_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return cuda_error(e, "cudaGetDeviceProperties", __FILE__, __LINE__);
+    }
+    if (prop.major < 10) {
+        delete ctx;
+        return set_error(P265_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                         prop.minor);
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete ctx;
+            return cuda_error(e, "cudaStreamCreateWithFlags", __FILE__, __LINE__);
+        }
+        ctx->owns_stream = true;
+    }
+    *out = ctx;
+    return P265_OK;
+}
+
+int p265_ctx_destroy(p265_ctx *ctx) {
+    if (!ctx) return P265_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 8; i++)
+        if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return P265_OK;
+}
+
+int p265_sync(p265_ctx *ctx) {
+    if (!ctx) return set_error(P265_EINVAL, "ctx is NULL");
+    P265_CUDA(cudaStreamSynchronize(ctx->stream));
+    return P265_OK;
+}
+
+int p265_sm_count(p265_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+uint64_t p265_launch_count(p265_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int p265_residual_batch_dev(p265_ctx *ctx, const p265_tu_desc *d_tus, const int32_t bin_counts[4],
+                            const int16_t *d_coeffs, const uint8_t *d_sf, const p265_pic_geom *geom,
+                            int16_t *d_residual, int flags) {
+    if (!ctx || !bin_counts || !d_residual) return set_error(P265_EINVAL, "p265_residual_batch_dev: NULL argument");
+    int rc = check_geom(geom, 8);
+    if (rc) return rc;
+    int64_t n = 0;
+    for (int b = 0; b < 4; b++) {
+        if (bin_counts[b] < 0) return set_error(P265_EINVAL, "negative bin count");
+        n += bin_counts[b];
+    }
+    if (n && (!d_tus || !d_coeffs)) return set_error(P265_EINVAL, "descriptor / coefficient pointer is NULL");
+    P265_CUDA(cudaSetDevice(ctx->device));
+    return launch_residual(ctx, d_tus, bin_counts, d_coeffs, d_sf, geom, d_residual, flags);
+}
+
+int p265_residual_batch(p265_ctx *ctx, const p265_tu_desc *tus, const int32_t bin_counts[4], const int16_t *coeffs,
+                        size_t n_coeffs, const uint8_t *scaling_factor, const p265_pic_geom *geom, int16_t *residual,
+                        int flags) {
+    if (!ctx || !bin_counts || !residual) return set_error(P265_EINVAL, "p265_residual_batch: NULL argument");
+    int rc = check_geom(geom, 8);
+    if (rc) return rc;
+    int64_t n = 0;
+    for (int b = 0; b < 4; b++) n += bin_counts[b] > 0 ? bin_counts[b] : 0;
+    if (n && (!tus || !coeffs)) return set_error(P265_EINVAL, "descriptor / coefficient pointer is NULL");
+    if ((rc = check_tus(tus, bin_counts, n_coeffs, geom))) return rc;
+    if (scaling_factor)
+        for (int64_t i = 0; i < n; i++)
+            if (tus[i].flags & P265_TU_PRESCALED)
+                return set_error(P265_EINVAL, "descriptor %lld: PRESCALED needs scaling_factor == NULL", (long long)i);
+    P265_CUDA(cudaSetDevice(ctx->device));
+    void *d_tus, *d_co, *d_sf = nullptr, *d_out;
+    const size_t out_bytes = sizeof(int16_t) * (size_t)geom->pic_stride * geom->n_pics;
+    if ((rc = ensure(ctx, 0, sizeof(p265_tu_desc) * (size_t)n, &d_tus))) return rc;
+    if ((rc = ensure(ctx, 1, sizeof(int16_t) * n_coeffs + 64, &d_co))) return rc;
+    if ((rc = ensure(ctx, 2, out_bytes, &d_out))) return rc;
+    if (scaling_factor) {
+        if ((rc = ensure(ctx, 3, P265_SF_BYTES, &d_sf))) return rc;
+        P265_CUDA(cudaMemcpyAsync(d_sf, scaling_factor, P265_SF_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (n) {
+        P265_CUDA(cudaMemcpyAsync(d_tus, tus, sizeof(p265_tu_desc) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        P265_CUDA(cudaMemcpyAsync(d_co, coeffs, sizeof(int16_t) * n_coeffs, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = launch_residual(ctx, (const p265_tu_desc *)d_tus, bin_counts, (const int16_t *)d_co, (const uint8_t *)d_sf,
+                         geom, (int16_t *)d_out, flags);
+    if (rc) return rc;
+    P265_CUDA(cudaMemcpyAsync(residual, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    P265_CUDA(cudaStreamSynchronize(ctx->stream));
+    return P265_OK;
+}
+
+int p265_dequant_batch(p265_ctx *ctx, const p265_tu_desc *tus, int32_t n_tus, const int16_t *coeffs, size_t n_coeffs,
+                       const uint8_t *scaling_factor, int bit_depth_y, int bit_depth_c, int16_t *scaled) {
+    if (!ctx || n_tus < 0 || (n_tus && (!tus || !coeffs || !scaled)))
+        return set_error(P265_EINVAL, "p265_dequant_batch: bad argument");
+    if (bit_depth_y < 8 || bit_depth_y > 12 || bit_depth_c < 8 || bit_depth_c > 12)
+        return set_error(P265_EINVAL, "bit depths %d/%d outside 8..12", bit_depth_y, bit_depth_c);
+    for (int32_t i = 0; i < n_tus; i++) {
+        const int n = 1 << tus[i].log2n;
+        if (tus[i].log2n < 2 || tus[i].log2n > 5 || tus[i].c_idx > 2 ||
+            (size_t)tus[i].coeff_off * 16 + (size_t)n * n > n_coeffs)
+            return set_error(P265_EINVAL, "descriptor %d is malformed", i);
+    }
+    if (n_tus == 0) return P265_OK;
+    P265_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    void *d_tus, *d_co, *d_sf = nullptr, *d_out;
+    if ((rc = ensure(ctx, 0, sizeof(p265_tu_desc) * (size_t)n_tus, &d_tus))) return rc;
+    if ((rc = ensure(ctx, 1, sizeof(int16_t) * n_coeffs + 64, &d_co))) return rc;
+    if ((rc = ensure(ctx, 4, sizeof(int16_t) * n_coeffs, &d_out))) return rc;
+    if (scaling_factor) {
+        if ((rc = ensure(ctx, 3, P265_SF_BYTES, &d_sf))) return rc;
+        P265_CUDA(cudaMemcpyAsync(d_sf, scaling_factor, P265_SF_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    P265_CUDA(cudaMemcpyAsync(d_tus, tus, sizeof(p265_tu_desc) * (size_t)n_tus, cudaMemcpyHostToDevice, ctx->stream));
+    P265_CUDA(cudaMemcpyAsync(d_co, coeffs, sizeof(int16_t) * n_coeffs, cudaMemcpyHostToDevice, ctx->stream));
+    P265_CUDA(cudaMemsetAsync(d_out, 0, sizeof(int16_t) * n_coeffs, ctx->stream));
+    if ((rc = launch_dequant(ctx, (const p265_tu_desc *)d_tus, n_tus, (const int16_t *)d_co, (const uint8_t *)d_sf,
+                             bit_depth_y, bit_depth_c, (int16_t *)d_out)))
+        return rc;
+    P265_CUDA(cudaMemcpyAsync(scaled, d_out, sizeof(int16_t) * n_coeffs, cudaMemcpyDeviceToHost, ctx->stream));
+    P265_CUDA(cudaStreamSynchronize(ctx->stream));
+    return P265_OK;
+}
+
+int p265_ref_literal_batch(p265_ctx *ctx, const p265_tu_desc *tus, int32_t n_tus, const int16_t *scaled,
+                           size_t n_coeffs, int32_t *out) {
+    if (!ctx || n_tus < 0 || (n_tus && (!tus || !scaled || !out)))
+        return set_error(P265_EINVAL, "p265_ref_literal_batch: bad argument");
+    for (int32_t i = 0; i < n_tus; i++) {
+        const int n = 1 << tus[i].log2n;
+        if (tus[i].log2n < 2 || tus[i].log2n > 5 || (size_t)tus[i].coeff_off * 16 + (size_t)n * n > n_coeffs)
+            return set_error(P265_EINVAL, "descriptor %d is malformed", i);
+    }
+    if (n_tus == 0) return P265_OK;
+    P265_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    void *d_tus, *d_in, *d_out;
+    if ((rc = ensure(ctx, 0, sizeof(p265_tu_desc) * (size_t)n_tus, &d_tus))) return rc;
+    if ((rc = ensure(ctx, 1, sizeof(int16_t) * n_coeffs + 64, &d_in))) return rc;
+    if ((rc = ensure(ctx, 5, sizeof(int32_t) * n_coeffs, &d_out))) return rc;
+    P265_CUDA(cudaMemcpyAsync(d_tus, tus, sizeof(p265_tu_desc) * (size_t)n_tus, cudaMemcpyHostToDevice, ctx->stream));
+    P265_CUDA(cudaMemcpyAsync(d_in, scaled, sizeof(int16_t) * n_coeffs, cudaMemcpyHostToDevice, ctx->stream));
+    P265_CUDA(cudaMemsetAsync(d_out, 0, sizeof(int32_t) * n_coeffs, ctx->stream));
+    if ((rc = launch_ref_literal(ctx, (const p265_tu_desc *)d_tus, n_tus, (const int16_t *)d_in, (int32_t *)d_out)))
+        return rc;
+    P265_CUDA(cudaMemcpyAsync(out, d_out, sizeof(int32_t) * n_coeffs, cudaMemcpyDeviceToHost, ctx->stream));
+    P265_CUDA(cudaStreamSynchronize(ctx->stream));
+    return P265_OK;
+}
+
+int p265_idct_1d(p265_ctx *ctx, const int32_t *x, int log2size, int tr_type, int mode, int32_t *y) {
+    if (!ctx || !x || !y) return set_error(P265_EINVAL, "p265_idct_1d: NULL argument");
+    if (log2size < 2 || log2size > 5) return set_error(P265_EINVAL, "log2size %d outside 2..5", log2size);
+    if (tr_type != 0 && !(tr_type == 1 && log2size == 2))
+        return set_error(P265_EINVAL, "tr_type %d invalid for log2size %d", tr_type, log2size);
+    P265_CUDA(cudaSetDevice(ctx->device));
+    const int n = 1 << log2size;
+    void *d;
+    int rc = ensure(ctx, 5, sizeof(int32_t) * 64, &d);
+    if (rc) return rc;
+    int32_t *d_x = (int32_t *)d, *d_y = d_x + 32;
+    P265_CUDA(cudaMemcpyAsync(d_x, x, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = launch_idct1d(ctx, d_x, log2size, tr_type, mode ? 1 : 0, d_y))) return rc;
+    P265_CUDA(cudaMemcpyAsync(y, d_y, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    P265_CUDA(cudaStreamSynchronize(ctx->stream));
+    return P265_OK;
+}
+
+static int check_sao(const p265_pic_geom *geom, int ctb_log2, int *bytes) {
+    *bytes = (geom->bit_depth_y > 8 || geom->bit_depth_c > 8) ? 2 : 1;
+    int rc = check_geom(geom, 16 / *bytes);
+    if (rc) return rc;
+    if (ctb_log2 < 4 || ctb_log2 > 6) return set_error(P265_EINVAL, "ctb_log2 %d outside 4..6", ctb_log2);
+    if (geom->width % 8 || geom->height % 8)
+        return set_error(P265_EINVAL, "picture size must be a multiple of MinCbSize 8 (got %dx%d)", geom->width,
+                         geom->height);
+    const int ctb = 1 << ctb_log2;
+    const int ctbs_w = (geom->width + ctb - 1) / ctb;
+    if (geom->stride_y < ctbs_w * ctb || geom->stride_c < ctbs_w * ctb / 2)
+        return set_error(P265_EINVAL, "strides must cover whole CTB columns (%d / %d elements)", ctbs_w * ctb,
+                         ctbs_w * ctb / 2);
+    return P265_OK;
+}
+
+int p265_sao_batch_dev(p265_ctx *ctx, const void *d_rec, void *d_out, const p265_pic_geom *geom, int ctb_log2,
+                       const p265_sao_ctb *d_params, const uint8_t *d_no_filter) {
+    if (!ctx || !d_rec || !d_out || !d_params || !geom) return set_error(P265_EINVAL, "p265_sao_batch_dev: NULL argument");
+    if (d_rec == d_out) return set_error(P265_EINVAL, "SAO runs out of place: rec and out must differ");
+    int bytes;
+    int rc = check_sao(geom, ctb_log2, &bytes);
+    if (rc) return rc;
+    P265_CUDA(cudaSetDevice(ctx->device));
+    return launch_sao(ctx, d_rec, d_out, geom, ctb_log2, d_params, d_no_filter);
+}
+
+int p265_sao_batch(p265_ctx *ctx, const void *rec, void *out, const p265_pic_geom *geom, int ctb_log2,
+                   const p265_sao_ctb *params, const uint8_t *no_filter) {
+    if (!ctx || !rec || !out || !params || !geom) return set_error(P265_EINVAL, "p265_sao_batch: NULL argument");
+    int bytes;
+    int rc = check_sao(geom, ctb_log2, &bytes);
+    if (rc) return rc;
+    const int ctb = 1 << ctb_log2;
+    const size_t ctbs = (size_t)((geom->width + ctb - 1) / ctb) * ((geom->height + ctb - 1) / ctb) * geom->n_pics;
+    for (size_t i = 0; i < ctbs; i++)
+        for (int c = 0; c < 3; c++)
+            if (params[i].type[c] > 2 || params[i].eo_class[c] > 3 || params[i].band_pos[c] > 31)
+                return set_error(P265_EINVAL, "SAO parameters of CTB %zu component %d out of range", i, c);
+    P265_CUDA(cudaSetDevice(ctx->device));
+    const size_t plane_bytes = (size_t)bytes * geom->pic_stride * geom->n_pics;
+    const size_t nf_bytes = (size_t)((geom->width + 7) / 8) * ((geom->height + 7) / 8) * geom->n_pics;
+    void *d_rec, *d_out, *d_par, *d_nf = nullptr;
+    if ((rc = ensure(ctx, 2, plane_bytes, &d_rec))) return rc;
+    if ((rc = ensure(ctx, 6, plane_bytes, &d_out))) return rc;
+    if ((rc = ensure(ctx, 0, sizeof(p265_sao_ctb) * ctbs, &d_par))) return rc;
+    P265_CUDA(cudaMemcpyAsync(d_rec, rec, plane_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    P265_CUDA(cudaMemcpyAsync(d_par, params, sizeof(p265_sao_ctb) * ctbs, cudaMemcpyHostToDevice, ctx->stream));
+    if (no_filter) {
+        if ((rc = ensure(ctx, 7, nf_bytes, &d_nf))) return rc;
+        P265_CUDA(cudaMemcpyAsync(d_nf, no_filter, nf_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // row padding and inter-plane gaps of `out` keep the caller's content of `rec`
+    P265_CUDA(cudaMemcpyAsync(d_out, d_rec, plane_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    if ((rc = launch_sao(ctx, d_rec, d_out, geom, ctb_log2, (const p265_sao_ctb *)d_par, (const uint8_t *)d_nf)))
+        return rc;
+    P265_CUDA(cudaMemcpyAsync(out, d_out, plane_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    P265_CUDA(cudaStreamSynchronize(ctx->stream));
+    return P265_OK;
+}
+
+int p265_int_peak(p265_ctx *ctx, int kind, double *ops_per_s, double *ms) {
+    if (!ctx || !ops_per_s || !ms) return set_error(P265_EINVAL, "p265_int_peak: NULL argument");
+    P265_CUDA(cudaSetDevice(ctx->device));
+    return run_int_peak(ctx, kind, ops_per_s, ms);
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,43 @@
+// Internal glue shared by the translation units of libp265b200.so (not installed).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "p265_b200.h"
+
+struct p265_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int sm_count = 0;
+    uint64_t launches = 0;  // kernels launched by this context (bench.py: gpu_launches)
+    // grow-only device scratch for the host-buffer entry points
+    void *scratch[8] = {nullptr};
+    size_t scratch_bytes[8] = {0};
+};
+
+namespace p265 {
+
+int set_error(int code, const char *fmt, ...);
+int cuda_error(cudaError_t e, const char *what, const char *file, int line);
+
+#define P265_CUDA(expr)                                                        \
+    do {                                                                       \
+        cudaError_t e__ = (expr);                                              \
+        if (e__ != cudaSuccess) return ::p265::cuda_error(e__, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+int launch_residual(p265_ctx *ctx, const p265_tu_desc *d_tus, const int32_t bin_counts[4], const int16_t *d_coeffs,
+                    const uint8_t *d_sf, const p265_pic_geom *g, int16_t *d_out, int flags);
+int launch_dequant(p265_ctx *ctx, const p265_tu_desc *d_tus, int n_tus, const int16_t *d_coeffs, const uint8_t *d_sf,
+                   int bit_depth_y, int bit_depth_c, int16_t *d_scaled);
+int launch_ref_literal(p265_ctx *ctx, const p265_tu_desc *d_tus, int n_tus, const int16_t *d_scaled, int32_t *d_out);
+int launch_idct1d(p265_ctx *ctx, const int32_t *d_x, int log2size, int tr_type, int mode, int32_t *d_y);
+int launch_sao(p265_ctx *ctx, const void *d_rec, void *d_out, const p265_pic_geom *g, int ctb_log2,
+               const p265_sao_ctb *d_params, const uint8_t *d_no_filter);
+int run_int_peak(p265_ctx *ctx, int kind, double *ops_per_s, double *ms);
+
+}  // namespace p265

@@ -1,0 +1,560 @@
+// Residual path core: dequantisation (scaling.py:23-47, H.265 8.6.3) + two-stage inverse
+// transform with the 16-bit clip between the stages (transform.py:89-106 structure,
+// H.265 8.6.4.1-2) + final bdShift (8.6.2), for ONE warp work item.
+//
+// The code is written against a "lane" index instead of threadIdx so that the very same
+// functions run (a) inside the sm_100a kernel, 32 lanes in lock step separated by
+// __syncwarp(), and (b) on the host, lane after lane, phase after phase
+// (tests/host_core.cpp) -- the indexing, permutations and packed constants can be
+// checked bit-exactly against the oracle without a GPU.
+//
+// Arithmetic design (B200): every multiply-accumulate is an IDP.2A (dp2a): two int16
+// data values packed in one register times two int8 basis coefficients from a uniform
+// register, accumulated in int32.  All basis coefficients fit int8 (|c| <= 90), all
+// data are int16 by the standard's clips, all sums stay below 2^27, so the result is
+// exact.  The even/odd partial butterfly is kept (N^2/2 -> ~N^2/5.3 MACs for N=32) and
+// halves again because one IDP.2A does two MACs.  Saturating packs (I2IP.S16.S32.SAT)
+// implement both 16-bit clips for free while building the packed operands of the next
+// stage.
+//
+// Work item = 64 TB columns: 2 TBs of 32x32, 4 of 16x16, 8 of 8x8 or 16 of 4x4.  Each
+// lane owns two columns in stage 1 (the two columns that form one packed operand
+// "slot" of stage 2) and two rows in stage 2.
+#pragma once
+
+#include <stdint.h>
+
+#include "p265_b200.h"
+
+#if defined(__CUDACC__)
+#define P265_HD __host__ __device__ __forceinline__
+#define P265_UNROLL _Pragma("unroll")
+#else
+#define P265_HD inline
+#define P265_UNROLL
+// host-only build (tests/host_core.cpp): minimal stand-ins for the CUDA vector types
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+#endif
+
+namespace p265 {
+
+// ------------------------------------------------------------------ primitives
+P265_HD int dp2a_lo(int a, int b, int c) {
+#if defined(__CUDA_ARCH__)
+    return __dp2a_lo(a, b, c);
+#else
+    return c + (int)(int16_t)(a & 0xffff) * (int)(int8_t)(b & 0xff) +
+           (int)(int16_t)((uint32_t)a >> 16) * (int)(int8_t)((b >> 8) & 0xff);
+#endif
+}
+P265_HD int dp2a_hi(int a, int b, int c) {
+#if defined(__CUDA_ARCH__)
+    return __dp2a_hi(a, b, c);
+#else
+    return c + (int)(int16_t)(a & 0xffff) * (int)(int8_t)((b >> 16) & 0xff) +
+           (int)(int16_t)((uint32_t)a >> 16) * (int)(int8_t)((b >> 24) & 0xff);
+#endif
+}
+// {lo, hi} int32 -> s16x2 with signed saturation
+P265_HD int pack_sat(int lo, int hi) {
+#if defined(__CUDA_ARCH__)
+    int r;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(r) : "r"(hi), "r"(lo));
+    return r;
+#else
+    int l = lo < -32768 ? -32768 : (lo > 32767 ? 32767 : lo);
+    int h = hi < -32768 ? -32768 : (hi > 32767 ? 32767 : hi);
+    return (int)(((uint32_t)(uint16_t)(int16_t)h << 16) | (uint16_t)(int16_t)l);
+#endif
+}
+P265_HD int ilog2(unsigned v) {
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz((int)v);
+#else
+    return 31 - __builtin_clz(v);
+#endif
+}
+
+// ------------------------------------------------------------------ basis tables
+// H.265 8.6.4.2 transMatrix, rebuilt from its cosine structure (see oracle for the
+// same derivation; tests compare both with transform.py:7-72).
+struct Basis {
+    int8_t m[32][32];
+    constexpr Basis() : m() {
+        const int mag[33] = {64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64,
+                             61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9,  4,  0};
+        for (int j = 0; j < 32; j++)
+            for (int i = 0; i < 32; i++) {
+                int a = (j * (2 * i + 1)) % 128;
+                if (a > 64) a = 128 - a;
+                m[j][i] = (int8_t)(j == 0 ? 64 : (a <= 32 ? mag[a] : -mag[64 - a]));
+            }
+    }
+};
+constexpr int kDst[4][4] = {{29, 55, 74, 84}, {74, 74, 0, -74}, {84, -29, -74, 55}, {55, -84, 74, -29}};
+
+constexpr int pack4(int b0, int b1, int b2, int b3) {
+    return (int)((uint32_t)(b0 & 0xff) | ((uint32_t)(b1 & 0xff) << 8) | ((uint32_t)(b2 & 0xff) << 16) |
+                 ((uint32_t)(b3 & 0xff) << 24));
+}
+
+// Packed odd-part constants.  For an N-point transform the odd part is
+//   O[k] = sum over odd rows j of T_N[j][k] * x[j],  k < N/2,  T_N[j] = T_32[j*32/N].
+// Word q of output k holds the coefficients of odd rows 8q+1, 8q+3 (dp2a.lo) and 8q+5,
+// 8q+7 (dp2a.hi); the matching data registers are odd slots 2q and 2q+1.
+struct Consts {
+    int o32[16][4];
+    int o16[8][2];
+    int o8[4][1];
+    int e4;     // (64, 64 | 64, -64)   on slot (x0, x2): lo -> E0, hi -> E1
+    int o4;     // (83, 36 | 36, -83)   on slot (x1, x3): lo -> O0, hi -> O1
+    int dst[4]; // DST-VII: (D[0][i], D[2][i] | D[1][i], D[3][i])
+    constexpr Consts() : o32(), o16(), o8(), e4(0), o4(0), dst() {
+        Basis b;
+        for (int k = 0; k < 16; k++)
+            for (int q = 0; q < 4; q++)
+                o32[k][q] = pack4(b.m[8 * q + 1][k], b.m[8 * q + 3][k], b.m[8 * q + 5][k], b.m[8 * q + 7][k]);
+        for (int k = 0; k < 8; k++)
+            for (int q = 0; q < 2; q++)
+                o16[k][q] = pack4(b.m[2 * (8 * q + 1)][k], b.m[2 * (8 * q + 3)][k], b.m[2 * (8 * q + 5)][k],
+                                  b.m[2 * (8 * q + 7)][k]);
+        for (int k = 0; k < 4; k++) o8[k][0] = pack4(b.m[4][k], b.m[12][k], b.m[20][k], b.m[28][k]);
+        e4 = pack4(b.m[0][0], b.m[16][0], b.m[0][1], b.m[16][1]);
+        o4 = pack4(b.m[8][0], b.m[24][0], b.m[8][1], b.m[24][1]);
+        for (int i = 0; i < 4; i++) dst[i] = pack4(kDst[0][i], kDst[2][i], kDst[1][i], kDst[3][i]);
+    }
+};
+
+#if defined(__CUDA_ARCH__)
+#define P265_K(x) (g_consts.x)
+#else
+#define P265_K(x) (h_consts.x)
+#endif
+#if defined(__CUDACC__)
+__constant__ Consts g_consts = Consts();
+#endif
+static const Consts h_consts = Consts();
+
+// Which natural index (row of a column / column of a row) sits in packed-operand slot
+// `s`, half `h` (0 = low 16 bits) of an N-point transform.  Slot order is the order the
+// recursive even/odd split consumes its inputs: slot 0 = (0, N/2); slot 1 = (N/4, 3N/4);
+// slots [2^L, 2^(L+1)) hold the odd rows of the (N >> (log2N-2-L))-point sub-transform.
+P265_HD constexpr int slot_index(int n, int s, int h) {
+    if (s == 0) return h * (n >> 1);
+    const int l = s >= 8 ? 3 : (s >= 4 ? 2 : (s >= 2 ? 1 : 0));
+    int r = s - (1 << l);
+    int scale = (n >> 2) >> l;
+    return scale * (4 * r + 2 * h + 1);
+}
+P265_HD int slot_index_rt(int n, int s, int h) {
+    if (s == 0) return h * (n >> 1);
+    int l = ilog2((unsigned)s);
+    int r = s - (1 << l);
+    int scale = (n >> 2) >> l;
+    return scale * (4 * r + 2 * h + 1);
+}
+
+// ------------------------------------------------------------------ 1-D transforms
+// C independent vectors in lock step (they share every uniform-register constant).
+// p[c][s]: packed operands in slot order; out[c][i]: natural order, int32, includes
+// `rnd` (the rounding offset of the shift that follows) exactly once per output.
+template <int N, int C>
+struct Idct;
+
+template <int C>
+struct Idct<4, C> {
+    static P265_HD void run(const int (&p)[C][2], int rnd, int (&out)[C][4]) {
+        P265_UNROLL
+        for (int c = 0; c < C; c++) {
+            int e0 = dp2a_lo(p[c][0], P265_K(e4), rnd);
+            int e1 = dp2a_hi(p[c][0], P265_K(e4), rnd);
+            int o0 = dp2a_lo(p[c][1], P265_K(o4), 0);
+            int o1 = dp2a_hi(p[c][1], P265_K(o4), 0);
+            out[c][0] = e0 + o0;
+            out[c][3] = e0 - o0;
+            out[c][1] = e1 + o1;
+            out[c][2] = e1 - o1;
+        }
+    }
+};
+
+template <int N>
+struct OddK;
+template <>
+struct OddK<8> {
+    static P265_HD int w(int k, int q) { return P265_K(o8)[k][q]; }
+};
+template <>
+struct OddK<16> {
+    static P265_HD int w(int k, int q) { return P265_K(o16)[k][q]; }
+};
+template <>
+struct OddK<32> {
+    static P265_HD int w(int k, int q) { return P265_K(o32)[k][q]; }
+};
+
+template <int N, int C>
+struct Idct {
+    static P265_HD void run(const int (&p)[C][N / 2], int rnd, int (&out)[C][N]) {
+        int pe[C][N / 4];
+        int e[C][N / 2];
+        P265_UNROLL
+        for (int c = 0; c < C; c++) {
+            P265_UNROLL
+            for (int s = 0; s < N / 4; s++) pe[c][s] = p[c][s];
+        }
+        Idct<N / 2, C>::run(pe, rnd, e);
+        P265_UNROLL
+        for (int k = 0; k < N / 2; k++) {
+            int o[C];
+            P265_UNROLL
+            for (int c = 0; c < C; c++) o[c] = 0;
+            P265_UNROLL
+            for (int s = 0; s < N / 4; s++) {
+                const int w = OddK<N>::w(k, s >> 1);
+                P265_UNROLL
+                for (int c = 0; c < C; c++)
+                    o[c] = (s & 1) ? dp2a_hi(p[c][N / 4 + s], w, o[c]) : dp2a_lo(p[c][N / 4 + s], w, o[c]);
+            }
+            P265_UNROLL
+            for (int c = 0; c < C; c++) {
+                out[c][k] = e[c][k] + o[c];
+                out[c][N - 1 - k] = e[c][k] - o[c];
+            }
+        }
+    }
+};
+
+template <int C>
+P265_HD void dst4(const int (&p)[C][2], int rnd, int (&out)[C][4]) {
+    P265_UNROLL
+    for (int c = 0; c < C; c++) {
+        P265_UNROLL
+        for (int i = 0; i < 4; i++) out[c][i] = dp2a_hi(p[c][1], P265_K(dst)[i], dp2a_lo(p[c][0], P265_K(dst)[i], rnd));
+    }
+}
+
+// ------------------------------------------------------------------ per-TB parameters
+struct TbParams {
+    const int16_t *src;  // coefficients of this TB (arena)
+    int16_t *dst;        // top-left of the TB in the residual plane
+    const uint8_t *sf;   // ScalingFactor matrix for this TB ([y][x]) or nullptr
+    int stride;          // plane stride (elements)
+    int w;               // 16 * levelScale[qP % 6]  (or levelScale when sf != nullptr)
+    int rnd, sh;         // dequant: (lv * m' + rnd) >> sh      (per < bdShift)
+    int lsh;             // dequant: clip16(lv * m') << lsh      (per >= bdShift)
+    int rnd2, sh2;       // final 8.6.2 shift: bdShift = 20 - BitDepth
+    int flags;
+    bool valid;
+};
+
+struct KernelArgs {
+    const p265_tu_desc *tus;
+    const int16_t *coeffs;
+    const uint8_t *sf;  // P265_SF_BYTES or nullptr
+    int16_t *out;
+    int64_t plane_off[3];
+    int64_t pic_stride;
+    int32_t stride_y, stride_c;
+    int32_t bit_depth_y, bit_depth_c;
+    int32_t first_tb[4];  // index of the first descriptor of each size bin (32,16,8,4)
+    int32_t n_tb[4];
+    int32_t first_item[5];  // warp-item prefix sums per bin
+};
+
+P265_HD int sf_matrix_offset(int log2n, int c_idx, int intra) {
+    // [sizeId][matrixId][y][x]; matrixId per scaling.py:33-42
+    const int n2 = 1 << (2 * log2n);
+    const int base = log2n == 2 ? 0 : (log2n == 3 ? 96 : (log2n == 4 ? 480 : 2016));
+    const int mid = log2n == 5 ? (intra ? 0 : 1) : (intra ? c_idx : c_idx + 3);
+    return base + mid * n2;
+}
+
+P265_HD TbParams make_params(const KernelArgs &a, int tb_index, bool valid) {
+    TbParams t;
+    t.valid = valid;
+    if (!valid) {
+        t.src = nullptr; t.dst = nullptr; t.sf = nullptr; t.stride = 0; t.w = 0; t.rnd = 0; t.sh = 0;
+        t.lsh = 0; t.rnd2 = 0; t.sh2 = 0; t.flags = 0;
+        return t;
+    }
+    // 16-byte descriptor read as one vector
+    const uint4 d = *reinterpret_cast<const uint4 *>(&a.tus[tb_index]);
+    const int x = (int)(d.x & 0xffff), y = (int)(d.x >> 16);
+    const int log2n = (int)(d.y & 0xff), c_idx = (int)((d.y >> 8) & 0xff);
+    const int qp = (int)((d.y >> 16) & 0xff);
+    t.flags = (int)(d.y >> 24);
+    const uint32_t coeff_off = d.z;
+    const int pic = (int)(d.w & 0xffff);
+    const int bit_depth = c_idx ? a.bit_depth_c : a.bit_depth_y;
+    t.stride = c_idx ? a.stride_c : a.stride_y;
+    t.src = a.coeffs + (size_t)coeff_off * 16;
+    t.dst = a.out + (size_t)pic * a.pic_stride + a.plane_off[c_idx] + (size_t)y * t.stride + x;
+    const int per = (qp * 43) >> 8;  // qp / 6 for qp < 128
+    const int rem = qp - per * 6;
+    // levelScale = {40,45,51,57,64,72} (scaling.py:28)
+    const int ls = rem == 0 ? 40 : rem == 1 ? 45 : rem == 2 ? 51 : rem == 3 ? 57 : rem == 4 ? 64 : 72;
+    const int bd_shift = bit_depth + log2n - 5;
+    if (a.sf) {
+        t.sf = a.sf + sf_matrix_offset(log2n, c_idx, (t.flags & P265_TU_INTRA) != 0);
+        t.w = ls;
+    } else {
+        t.sf = nullptr;
+        t.w = ls * 16;
+    }
+    if (per < bd_shift) {
+        t.sh = bd_shift - per;
+        t.rnd = 1 << (t.sh - 1);
+        t.lsh = 0;
+    } else {
+        t.sh = 0;
+        t.rnd = 0;
+        t.lsh = per - bd_shift;
+    }
+    if (t.flags & P265_TU_PRESCALED) {  // arena holds d[] already: identity "dequantisation"
+        t.sf = nullptr;
+        t.w = 1;
+        t.sh = 0;
+        t.rnd = 0;
+        t.lsh = 0;
+    }
+    t.sh2 = 20 - bit_depth;
+    t.rnd2 = 1 << (t.sh2 - 1);
+    return t;
+}
+
+// d = Clip3(-32768, 32767, (lv * m * levelScale << per + round) >> bdShift) without the
+// final clip (the saturating pack that follows applies it).  Exact in int32:
+// |lv * m * ls| <= 32768 * 255 * 72 < 2^30.
+P265_HD int dequant_fast(int lv, int m, const TbParams &t) {  // valid when t.lsh == 0
+    return (lv * m + t.rnd) >> t.sh;
+}
+P265_HD int dequant(int lv, int m, const TbParams &t) {
+    int v = lv * m;
+    if (t.lsh == 0) return (v + t.rnd) >> t.sh;
+    v = v < -32768 ? -32768 : (v > 32767 ? 32767 : v);  // clip commutes with << for lsh >= 0
+    return v << t.lsh;
+}
+
+// ------------------------------------------------------------------ shared layout
+template <int LOG2N>
+struct Layout {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int TPB = N / 2;         // lanes per TB
+    static constexpr int TBS = 64 / N;        // TBs per warp item
+    // input tile: row-major int16 [y][x] + one pad row (bank spreading across TBs)
+    static constexpr int IN_BYTES = N * N * 2 + 2 * N;
+    // stage-1 output: N rows of N/2 packed words (slot order) + row padding
+    static constexpr int G_ROW = (N == 32) ? 20 : (N == 16) ? 12 : (N == 8) ? 4 : 2;  // words
+    static constexpr int G_BYTES = N * G_ROW * 4 + ((N == 32) ? 64 : (N == 16) ? 32 : (N == 8) ? 64 : 8);
+    static constexpr int TB_BYTES = IN_BYTES > G_BYTES ? IN_BYTES : G_BYTES;  // g aliases in
+    static constexpr int WARP_BYTES = TB_BYTES * TBS;
+};
+constexpr int kWarpSmemBytes = 5376;  // >= Layout<5>::WARP_BYTES, multiple of 128
+static_assert(Layout<5>::WARP_BYTES <= kWarpSmemBytes, "smem");
+static_assert(Layout<4>::WARP_BYTES <= kWarpSmemBytes, "smem");
+static_assert(Layout<3>::WARP_BYTES <= kWarpSmemBytes, "smem");
+static_assert(Layout<2>::WARP_BYTES <= kWarpSmemBytes, "smem");
+
+P265_HD int lds_s16(const unsigned char *smem, int byte_off) {
+    return (int)*reinterpret_cast<const int16_t *>(smem + byte_off);
+}
+
+// ---------------------------------------------------------------- phase 0: global -> smem
+// Each lane copies its share (two columns' worth = 4N bytes) of its TB, 16 bytes at a
+// time, fully coalesced across the TB's lanes.  TS / bypass TBs are finished here,
+// element-wise, straight from the registers.
+template <int LOG2N>
+P265_HD void phase_load(int lane, const TbParams &t, unsigned char *wsmem) {
+    using L = Layout<LOG2N>;
+    constexpr int N = L::N;
+    const int tb = lane / L::TPB, tl = lane % L::TPB;
+    if (!t.valid) return;
+    unsigned char *in = wsmem + tb * L::TB_BYTES;
+    const bool special = (t.flags & (P265_TU_SKIP | P265_TU_BYPASS)) != 0;
+    if (!special) {
+        uint4 v[N / 4];
+        P265_UNROLL
+        for (int i = 0; i < N / 4; i++) v[i] = *reinterpret_cast<const uint4 *>(t.src + (tl + i * L::TPB) * 8);
+        P265_UNROLL
+        for (int i = 0; i < N / 4; i++) {
+            const int chunk = tl + i * L::TPB;  // 16-byte chunk index inside the TB
+            if (N >= 8) {
+                *reinterpret_cast<uint4 *>(in + chunk * 16) = v[i];
+            } else {
+                *reinterpret_cast<uint2 *>(in + chunk * 16) = make_uint2(v[i].x, v[i].y);
+                *reinterpret_cast<uint2 *>(in + chunk * 16 + 8) = make_uint2(v[i].z, v[i].w);
+            }
+        }
+        return;
+    }
+    // transform-skip (8.6.4.2, tsShift = 7) / transquant-bypass (8.6.2): element-wise
+    for (int i = 0; i < N / 4; i++) {
+        const int chunk = tl + i * L::TPB;
+        const uint4 v = *reinterpret_cast<const uint4 *>(t.src + chunk * 8);
+        // 8 consecutive coefficients: one row segment (N >= 8) or two rows (N == 4)
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[4];
+        P265_UNROLL
+        for (int k = 0; k < 4; k++) {
+            int r[2];
+            P265_UNROLL
+            for (int h = 0; h < 2; h++) {
+                const int lv = (int)(int16_t)(h ? (w[k] >> 16) : (w[k] & 0xffff));
+                if (t.flags & P265_TU_BYPASS) {
+                    r[h] = lv;
+                } else {
+                    const int e = chunk * 8 + k * 2 + h;
+                    const int m = t.sf ? (int)t.sf[e] * t.w : t.w;
+                    int d = dequant(lv, m, t);
+                    d = d < -32768 ? -32768 : (d > 32767 ? 32767 : d);
+                    r[h] = (d * 128 + t.rnd2) >> t.sh2;
+                }
+            }
+            o[k] = (uint32_t)pack_sat(r[0], r[1]);
+        }
+        const int e0 = chunk * 8;
+        if (N >= 8) {
+            int16_t *dst = t.dst + (size_t)(e0 / N) * t.stride + (e0 % N);
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
+            int16_t *dst = t.dst + (size_t)(e0 / 4) * t.stride;
+            *reinterpret_cast<uint2 *>(dst) = make_uint2(o[0], o[1]);
+            *reinterpret_cast<uint2 *>(dst + t.stride) = make_uint2(o[2], o[3]);
+        }
+    }
+}
+
+// ------------------------------------------- phase 1a: smem -> packed, dequantised operands
+// SLOW must be chosen warp-uniformly: true when any lane of the warp has a TB with
+// per >= bdShift (left-shift dequantisation, only reachable at very high qP on small TBs).
+template <int LOG2N, bool HAS_SF, bool SLOW>
+P265_HD void phase_gather(int lane, const TbParams &t, const unsigned char *wsmem,
+                          int (&p)[2][(1 << LOG2N) / 2]) {
+    using L = Layout<LOG2N>;
+    constexpr int N = L::N;
+    const int tb = lane / L::TPB, tl = lane % L::TPB;
+    const unsigned char *in = wsmem + tb * L::TB_BYTES;
+    const int x[2] = {slot_index_rt(N, tl, 0), slot_index_rt(N, tl, 1)};
+    const uint8_t *sf = (HAS_SF && t.sf) ? t.sf : nullptr;
+    if (HAS_SF && !sf) {  // invalid lane: keep the loads in bounds
+        P265_UNROLL
+        for (int c = 0; c < 2; c++) {
+            P265_UNROLL
+            for (int s = 0; s < N / 2; s++) p[c][s] = 0;
+        }
+        return;
+    }
+    P265_UNROLL
+    for (int c = 0; c < 2; c++) {
+        P265_UNROLL
+        for (int s = 0; s < N / 2; s++) {
+            const int y0 = slot_index(N, s, 0), y1 = slot_index(N, s, 1);
+            const int e0 = y0 * N + x[c], e1 = y1 * N + x[c];
+            const int l0 = lds_s16(in, e0 * 2), l1 = lds_s16(in, e1 * 2);
+            int m0 = t.w, m1 = t.w;
+            if (HAS_SF) {
+                m0 *= (int)sf[e0];
+                m1 *= (int)sf[e1];
+            }
+            if (!SLOW) p[c][s] = pack_sat(dequant_fast(l0, m0, t), dequant_fast(l1, m1, t));
+            else p[c][s] = pack_sat(dequant(l0, m0, t), dequant(l1, m1, t));
+        }
+    }
+}
+
+// ------------------------------------------- phase 1b: column transforms -> g (smem)
+template <int LOG2N>
+P265_HD void phase_stage1(int lane, const TbParams &t, unsigned char *wsmem, const int (&p)[2][(1 << LOG2N) / 2]) {
+    using L = Layout<LOG2N>;
+    constexpr int N = L::N;
+    const int tb = lane / L::TPB, tl = lane % L::TPB;
+    uint32_t *g = reinterpret_cast<uint32_t *>(wsmem + tb * L::TB_BYTES);
+    int e[2][N];
+    if (N == 4 && (t.flags & P265_TU_DST)) {
+        int p4[2][2] = {{p[0][0], p[0][1]}, {p[1][0], p[1][1]}};
+        int e4[2][4];
+        dst4<2>(p4, 64, e4);
+        P265_UNROLL
+        for (int i = 0; i < 4; i++) {
+            e[0][i] = e4[0][i];
+            e[1][i] = e4[1][i];
+        }
+    } else {
+        Idct<N, 2>::run(p, 64, e);
+    }
+    // g[y][slot tl] = (clip16((e[x_lo][y] + 64) >> 7), clip16((e[x_hi][y] + 64) >> 7))
+    P265_UNROLL
+    for (int y = 0; y < N; y++) g[y * L::G_ROW + tl] = (uint32_t)pack_sat(e[0][y] >> 7, e[1][y] >> 7);
+}
+
+// ------------------------------------------- phase 2: row transforms -> residual plane
+template <int LOG2N>
+P265_HD void phase_stage2(int lane, const TbParams &t, const unsigned char *wsmem) {
+    using L = Layout<LOG2N>;
+    constexpr int N = L::N;
+    const int tb = lane / L::TPB, tl = lane % L::TPB;
+    if (!t.valid || (t.flags & (P265_TU_SKIP | P265_TU_BYPASS))) return;
+    const uint32_t *g = reinterpret_cast<const uint32_t *>(wsmem + tb * L::TB_BYTES);
+    int p[2][N / 2];
+    P265_UNROLL
+    for (int c = 0; c < 2; c++) {
+        const uint32_t *row = g + (tl + c * L::TPB) * L::G_ROW;
+        if (N >= 8) {
+            P265_UNROLL
+            for (int q = 0; q < N / 8; q++) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(row + 4 * q);
+                p[c][4 * q + 0] = (int)v.x;
+                p[c][4 * q + 1] = (int)v.y;
+                p[c][4 * q + 2] = (int)v.z;
+                p[c][4 * q + 3] = (int)v.w;
+            }
+        } else {
+            const uint2 v = *reinterpret_cast<const uint2 *>(row);
+            p[c][0] = (int)v.x;
+            p[c][1] = (int)v.y;
+        }
+    }
+    int r[2][N];
+    if (N == 4 && (t.flags & P265_TU_DST)) {
+        int p4[2][2] = {{p[0][0], p[0][1]}, {p[1][0], p[1][1]}};
+        int r4[2][4];
+        dst4<2>(p4, t.rnd2, r4);
+        P265_UNROLL
+        for (int i = 0; i < 4; i++) {
+            r[0][i] = r4[0][i];
+            r[1][i] = r4[1][i];
+        }
+    } else {
+        Idct<N, 2>::run(p, t.rnd2, r);
+    }
+    P265_UNROLL
+    for (int c = 0; c < 2; c++) {
+        int16_t *dst = t.dst + (size_t)(tl + c * L::TPB) * t.stride;
+        uint32_t w[N / 2];
+        P265_UNROLL
+        for (int i = 0; i < N / 2; i++) w[i] = (uint32_t)pack_sat(r[c][2 * i] >> t.sh2, r[c][2 * i + 1] >> t.sh2);
+        if (N >= 8) {
+            P265_UNROLL
+            for (int q = 0; q < N / 8; q++)
+                *reinterpret_cast<uint4 *>(dst + 8 * q) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        } else {
+            *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
+        }
+    }
+}
+
+// TB index handled by `lane` of warp item `item` in bin LOG2N (bins: 0 -> 32x32 ...)
+template <int LOG2N>
+P265_HD int lane_tb(const KernelArgs &a, int item, int lane, bool &valid) {
+    using L = Layout<LOG2N>;
+    constexpr int bin = 5 - LOG2N;
+    const int local = item * L::TBS + lane / L::TPB;
+    valid = local < a.n_tb[bin];
+    return a.first_tb[bin] + local;
+}
+
+}  // namespace p265

@@ -1,0 +1,406 @@
+// sm_100a SAO kernel: H.265 8.7.3 sample adaptive offset (band offset and the four
+// edge-offset classes) over reconstructed pictures, out of place, driven by the per-CTB
+// parameters sao.Sao.parse() produces (sao.py:15-136).  The reference has no SAO filter
+// at all; parity is against the spec oracle.
+//
+// One warp per (picture, component, CTB).  A lane owns an 8-sample-wide strip of R rows
+// and walks it with a three-row window kept in registers: 16-byte (10-bit) / 8-byte
+// (8-bit) coalesced loads and stores, horizontal neighbours through warp shuffles, no
+// shared memory.  All arithmetic is packed 2 x 16 bit in one 32-bit register:
+//   sign(c - n)      : (c + 0x4000_4000 - n) clamped to [0x3fff, 0x4001] per half-word
+//                      (VIMNMX.S16x2 twice)
+//   SaoOffsetVal[..] : byte-permute LUT (PRMT with sign replication) over the CTB's four
+//                      int8 offsets
+//   Clip1(c + off)   : VIADDMNMX.S16x2.RELU
+// Type / class / offsets are uniform per warp, so every branch is warp-uniform.
+#include <cuda_runtime.h>
+
+#include "internal.h"
+
+namespace p265 {
+
+constexpr int kSaoWarpsPerCta = 4;
+
+struct SaoArgs {
+    const void *rec;
+    void *out;
+    const p265_sao_ctb *params;
+    const uint8_t *no_filter;
+    int64_t plane_off[3];
+    int64_t pic_stride;
+    int32_t width, height, stride_y, stride_c;
+    int32_t bit_depth_y, bit_depth_c;
+    int32_t ctb_log2, ctbs_w, ctbs_h, n_pics;
+    int32_t ctbs;        // ctbs_w * ctbs_h
+    int32_t luma_items;  // n_pics * ctbs
+    int32_t items;       // 3 * luma_items
+};
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// A row of the strip: e[1..4] = the lane's 8 samples as 4 x u16x2, e[0] = word whose
+// HIGH half is the sample left of the strip, e[5] = word whose LOW half is the sample
+// right of it.
+struct Row {
+    uint32_t e[6];
+};
+
+template <typename T>
+__device__ __forceinline__ void load8(const T *p, uint32_t (&w)[4]);
+template <>
+__device__ __forceinline__ void load8<uint16_t>(const uint16_t *p, uint32_t (&w)[4]) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(p);
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+}
+template <>
+__device__ __forceinline__ void load8<uint8_t>(const uint8_t *p, uint32_t (&w)[4]) {
+    const uint2 v = *reinterpret_cast<const uint2 *>(p);
+    w[0] = prmt(v.x, 0, 0x4140); w[1] = prmt(v.x, 0, 0x4342);
+    w[2] = prmt(v.y, 0, 0x4140); w[3] = prmt(v.y, 0, 0x4342);
+}
+template <typename T>
+__device__ __forceinline__ void store8(T *p, const uint32_t (&w)[4]);
+template <>
+__device__ __forceinline__ void store8<uint16_t>(uint16_t *p, const uint32_t (&w)[4]) {
+    *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+template <>
+__device__ __forceinline__ void store8<uint8_t>(uint8_t *p, const uint32_t (&w)[4]) {
+    *reinterpret_cast<uint2 *>(p) = make_uint2(prmt(w[0], w[1], 0x6420), prmt(w[2], w[3], 0x6420));
+}
+
+struct Strip {
+    int lx, lanes_w;         // lane column inside the CTB, lanes per CTB row
+    bool first_col, last_col;  // lane touches the CTB's left / right edge
+    bool mem_left, mem_right;  // a sample exists in memory left / right of the CTB
+};
+
+// Load one row of the strip (+ halo when HALO).  Every lane of the warp must call this
+// (shuffles); `p` points at the lane's first sample of the row.
+template <typename T, bool HALO>
+__device__ __forceinline__ void load_row(Row &r, const T *p, const Strip &s) {
+    uint32_t w[4];
+    load8<T>(p, w);
+    r.e[1] = w[0]; r.e[2] = w[1]; r.e[3] = w[2]; r.e[4] = w[3];
+    if (HALO) {
+        uint32_t l = __shfl_up_sync(0xffffffffu, w[3], 1);
+        uint32_t rr = __shfl_down_sync(0xffffffffu, w[0], 1);
+        if (s.first_col) l = s.mem_left ? ((uint32_t)p[-1] << 16) : 0u;
+        if (s.last_col) rr = s.mem_right ? (uint32_t)p[8] : 0u;
+        r.e[0] = l;
+        r.e[5] = rr;
+    }
+}
+
+struct ItemConst {
+    uint32_t pool_lo, pool_hi;  // int8 offsets, indexable by PRMT
+    uint32_t maxv2;             // (1 << bitDepth) - 1 in both halves
+    uint32_t band_k;            // (32 - band_position) in both halves
+    int band_shift;
+};
+
+__device__ __forceinline__ uint32_t apply_offset(uint32_t c, uint32_t idx2, const ItemConst &k) {
+    // idx2: LUT index (0..4) per half-word -> packed int16 offsets -> clip(c + off)
+    const uint32_t j = prmt(idx2, 0, 0x4420);   // idx_lo | idx_hi << 8
+    const uint32_t sel = j * 0x11u + 0x8080u;   // nibbles: idx, idx|8 (sign replicate)
+    const uint32_t off = prmt(k.pool_lo, k.pool_hi, sel);
+    return __viaddmin_s16x2_relu(c, off, k.maxv2);
+}
+
+__device__ __forceinline__ uint32_t edge_word(uint32_t c, uint32_t a, uint32_t b, const ItemConst &k) {
+    uint32_t da = c + 0x40004000u - a;  // 0x4000 + (c - a) per half, no cross-half borrow
+    uint32_t db = c + 0x40004000u - b;
+    da = __vmins2(__vmaxs2(da, 0x3fff3fffu), 0x40014001u);  // 0x4000 + sign(c - a)
+    db = __vmins2(__vmaxs2(db, 0x3fff3fffu), 0x40014001u);
+    const uint32_t idx2 = da + db - 0x7ffe7ffeu;  // 2 + sign + sign: 0..4
+    return apply_offset(c, idx2, k);               // LUT order folds the edgeIdx remap
+}
+
+__device__ __forceinline__ uint32_t band_word(uint32_t c, const ItemConst &k) {
+    const uint32_t band = (c >> k.band_shift) & 0x001f001fu;
+    const uint32_t rel = (band + k.band_k) & 0x001f001fu;  // (band - band_position) mod 32
+    return apply_offset(c, __vminu2(rel, 0x00040004u), k);
+}
+
+// keep-original masks of a row: 0xffff per half-word whose neighbour is unavailable.
+struct MaskCtx {
+    uint32_t col_l[4], col_r[4], beyond[4];  // sample is first / last valid column / outside
+    bool aL, aR, aU, aD, aUL, aUR, aDL, aDR;
+};
+
+template <int CLS>
+__device__ __forceinline__ void row_mask(const MaskCtx &m, bool top, bool bot, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t k = m.beyond[i];
+        if (CLS == 0) {
+            if (!m.aL) k |= m.col_l[i];
+            if (!m.aR) k |= m.col_r[i];
+        } else if (CLS == 1) {
+            if ((top && !m.aU) || (bot && !m.aD)) k = 0xffffffffu;
+        } else if (CLS == 2) {  // a = (-1,-1), b = (+1,+1)
+            if (top) k |= (m.aUL ? 0u : m.col_l[i]) | (m.aU ? 0u : ~m.col_l[i]);
+            else if (!m.aL) k |= m.col_l[i];
+            if (bot) k |= (m.aDR ? 0u : m.col_r[i]) | (m.aD ? 0u : ~m.col_r[i]);
+            else if (!m.aR) k |= m.col_r[i];
+        } else {                // a = (+1,-1), b = (-1,+1)
+            if (top) k |= (m.aUR ? 0u : m.col_r[i]) | (m.aU ? 0u : ~m.col_r[i]);
+            else if (!m.aR) k |= m.col_r[i];
+            if (bot) k |= (m.aDL ? 0u : m.col_l[i]) | (m.aD ? 0u : ~m.col_l[i]);
+            else if (!m.aL) k |= m.col_l[i];
+        }
+        out[i] = k;
+    }
+}
+
+template <int CLS>
+__device__ __forceinline__ void edge_row(const Row &P, const Row &C, const Row &N, const ItemConst &k,
+                                         const uint32_t (&keep)[4], uint32_t (&out)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t c = C.e[i + 1];
+        uint32_t a, b;
+        if (CLS == 0) {
+            a = prmt(C.e[i], C.e[i + 1], 0x5432);
+            b = prmt(C.e[i + 1], C.e[i + 2], 0x5432);
+        } else if (CLS == 1) {
+            a = P.e[i + 1];
+            b = N.e[i + 1];
+        } else if (CLS == 2) {
+            a = prmt(P.e[i], P.e[i + 1], 0x5432);
+            b = prmt(N.e[i + 1], N.e[i + 2], 0x5432);
+        } else {
+            a = prmt(P.e[i + 1], P.e[i + 2], 0x5432);
+            b = prmt(N.e[i], N.e[i + 1], 0x5432);
+        }
+        const uint32_t r = edge_word(c, a, b, k);
+        out[i] = (c & keep[i]) | (r & ~keep[i]);
+    }
+}
+
+struct Geo {
+    int y0, vh, row0, rows;  // CTB top row, valid rows, lane's first local row, rows per lane
+    int h;                   // plane height
+    int64_t stride;
+    bool active;             // lane covers valid columns
+};
+
+template <typename T, int CLS, bool NOFILT>
+__device__ __forceinline__ void edge_strip(const T *in, T *out, const Geo &g, const Strip &s, const MaskCtx &m,
+                                           const ItemConst &k, const uint8_t *nf_row, int nf_stride, int nf_shift) {
+    // `in` / `out` point at (row y0, lane's first column)
+    constexpr bool HALO = CLS != 1;
+    Row P, C, N;
+    auto rowptr = [&](int ly) {
+        int y = g.y0 + ly;
+        y = y < 0 ? 0 : (y >= g.h ? g.h - 1 : y);
+        return in + (int64_t)(y - g.y0) * g.stride;
+    };
+    load_row<T, HALO>(P, rowptr(g.row0 - 1), s);
+    load_row<T, HALO>(C, rowptr(g.row0), s);
+    uint32_t mid[4];
+    row_mask<CLS>(m, false, false, mid);
+    for (int r = 0; r < g.rows; r++) {
+        const int ly = g.row0 + r;
+        load_row<T, HALO>(N, rowptr(ly + 1), s);
+        const bool top = ly == 0, bot = ly == g.vh - 1;
+        uint32_t keep[4], o[4];
+        if (top || bot) row_mask<CLS>(m, top, bot, keep);
+        else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) keep[i] = mid[i];
+        }
+        if (NOFILT) {
+            const uint8_t *f = nf_row + (int64_t)(min(ly, g.vh - 1) >> nf_shift) * nf_stride;
+            if (nf_shift == 3) {
+                if (f[0]) keep[0] = keep[1] = keep[2] = keep[3] = 0xffffffffu;
+            } else {
+                if (f[0]) keep[0] = keep[1] = 0xffffffffu;
+                if (f[1]) keep[2] = keep[3] = 0xffffffffu;
+            }
+        }
+        edge_row<CLS>(P, C, N, k, keep, o);
+        if (g.active && ly < g.vh) store8<T>(out + (int64_t)ly * g.stride, o);
+        P = C;
+        C = N;
+    }
+}
+
+template <typename T, bool NOFILT>
+__device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int rx, int ry, int lane) {
+    const p265_sao_ctb q = a.params[((int64_t)pic * a.ctbs_h + ry) * a.ctbs_w + rx];
+    const int type = q.type[c];
+    const int cs = (1 << a.ctb_log2) >> (c ? 1 : 0);
+    const int w = c ? a.width >> 1 : a.width, h = c ? a.height >> 1 : a.height;
+    const int bd = c ? a.bit_depth_c : a.bit_depth_y;
+    Geo g;
+    g.stride = c ? a.stride_c : a.stride_y;
+    g.h = h;
+    const int x0 = rx * cs;
+    g.y0 = ry * cs;
+    const int vw = min(cs, w - x0);
+    g.vh = min(cs, h - g.y0);
+
+    Strip s;
+    s.lanes_w = max(cs >> 3, 1);
+    const int lane_rows = 32 / s.lanes_w;
+    g.rows = max(1, cs / lane_rows);
+    s.lx = lane % s.lanes_w;
+    const int ly = lane / s.lanes_w;
+    g.row0 = ly * g.rows;
+    g.active = s.lx * 8 < vw && g.row0 < g.vh;
+    if (g.row0 >= cs) {  // lane has no rows at all (chroma of 16x16 CTBs): park it on row 0
+        g.row0 = 0;
+        g.active = false;
+    }
+    s.first_col = s.lx == 0;
+    s.last_col = s.lx == s.lanes_w - 1;
+    s.mem_left = x0 > 0;
+    s.mem_right = x0 + cs < (int)g.stride;  // row padding is readable; masked if outside
+
+    const int64_t base = (int64_t)pic * a.pic_stride + a.plane_off[c] + (int64_t)g.y0 * g.stride + x0 + s.lx * 8;
+    const T *in = reinterpret_cast<const T *>(a.rec) + base;
+    T *out = reinterpret_cast<T *>(a.out) + base;
+
+    const uint8_t *nf_row = nullptr;
+    int nf_stride = 0, nf_shift = 3;
+    if (NOFILT) {
+        nf_stride = (a.width + 7) >> 3;
+        const int h8 = (a.height + 7) >> 3;
+        nf_shift = c ? 2 : 3;
+        // luma: lane strip = one 8x8 block column; chroma: two 4x4 block columns
+        const int bx = c ? ((x0 + s.lx * 8) >> 2) : ((x0 + s.lx * 8) >> 3);
+        const int by0 = g.y0 >> nf_shift;
+        nf_row = a.no_filter + ((int64_t)pic * h8 + by0) * nf_stride + min(bx, nf_stride - (c ? 2 : 1));
+    }
+
+    ItemConst k;
+    k.maxv2 = ((1u << bd) - 1u) * 0x00010001u;
+    k.band_shift = bd - 5;
+    k.band_k = (uint32_t)(32 - q.band_pos[c]) * 0x00010001u;
+    const uint32_t o1 = (uint8_t)q.offset_val[c][0], o2 = (uint8_t)q.offset_val[c][1];
+    const uint32_t o3 = (uint8_t)q.offset_val[c][2], o4 = (uint8_t)q.offset_val[c][3];
+
+    if (type != 2) {
+        // off: copy; band: bandTable lookup (pool index = band - band_position, 4 = none)
+        k.pool_lo = o1 | (o2 << 8) | (o3 << 16) | (o4 << 24);
+        k.pool_hi = 0;
+        for (int r = 0; r < g.rows; r++) {
+            const int lyr = g.row0 + r;
+            if (!(g.active && lyr < g.vh)) continue;
+            uint32_t wv[4], o[4];
+            load8<T>(in + (int64_t)lyr * g.stride, wv);
+            bool skip[2] = {false, false};
+            if (NOFILT) {
+                const uint8_t *f = nf_row + (int64_t)(lyr >> nf_shift) * nf_stride;
+                skip[0] = f[0] != 0;
+                skip[1] = nf_shift == 3 ? skip[0] : (f[1] != 0);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) o[i] = (type == 1 && !skip[i >> 1]) ? band_word(wv[i], k) : wv[i];
+            store8<T>(out + (int64_t)lyr * g.stride, o);
+        }
+        return;
+    }
+
+    // edge offset: pool index = 2 + sign + sign -> {off1, off2, 0, off3, off4}
+    k.pool_lo = o1 | (o2 << 8) | (o3 << 24);
+    k.pool_hi = o4;
+    MaskCtx m;
+    const uint32_t av = q.avail;
+    const bool has_l = x0 > 0, has_r = x0 + cs < w, has_u = g.y0 > 0, has_d = g.y0 + cs < h;
+    m.aUL = has_u && has_l && (av >> 0 & 1);
+    m.aU = has_u && (av >> 1 & 1);
+    m.aUR = has_u && has_r && (av >> 2 & 1);
+    m.aL = has_l && (av >> 3 & 1);
+    m.aR = has_r && (av >> 5 & 1);
+    m.aDL = has_d && has_l && (av >> 6 & 1);
+    m.aD = has_d && (av >> 7 & 1);
+    m.aDR = has_d && has_r && (av >> 8 & 1);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t cl = 0, cr = 0, be = 0;
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+            const int xl = s.lx * 8 + 2 * i + hh;
+            const uint32_t bit = 0xffffu << (16 * hh);
+            if (xl == 0) cl |= bit;
+            if (xl == vw - 1) cr |= bit;
+            if (xl >= vw) be |= bit;
+        }
+        m.col_l[i] = cl; m.col_r[i] = cr; m.beyond[i] = be;
+    }
+    switch (q.eo_class[c]) {
+        case 0: edge_strip<T, 0, NOFILT>(in, out, g, s, m, k, nf_row, nf_stride, nf_shift); break;
+        case 1: edge_strip<T, 1, NOFILT>(in, out, g, s, m, k, nf_row, nf_stride, nf_shift); break;
+        case 2: edge_strip<T, 2, NOFILT>(in, out, g, s, m, k, nf_row, nf_stride, nf_shift); break;
+        default: edge_strip<T, 3, NOFILT>(in, out, g, s, m, k, nf_row, nf_stride, nf_shift); break;
+    }
+}
+
+template <typename T, bool NOFILT>
+__global__ void __launch_bounds__(kSaoWarpsPerCta * 32) sao_kernel(const __grid_constant__ SaoArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * kSaoWarpsPerCta + (threadIdx.x >> 5);
+    if (item >= a.items) return;
+    // luma CTBs first (4x the work of a chroma CTB) so the tail is made of small items
+    int c, rest;
+    if (item < a.luma_items) {
+        c = 0;
+        rest = item;
+    } else {
+        const int j = item - a.luma_items;
+        c = 1 + (j & 1);
+        rest = j >> 1;
+    }
+    const int pic = rest / a.ctbs, ctb = rest - pic * a.ctbs;
+    const int ry = ctb / a.ctbs_w, rx = ctb - ry * a.ctbs_w;
+    sao_item<T, NOFILT>(a, pic, c, rx, ry, lane);
+}
+
+int launch_sao(p265_ctx *ctx, const void *d_rec, void *d_out, const p265_pic_geom *g, int ctb_log2,
+               const p265_sao_ctb *d_params, const uint8_t *d_no_filter) {
+    SaoArgs a;
+    a.rec = d_rec;
+    a.out = d_out;
+    a.params = d_params;
+    a.no_filter = d_no_filter;
+    for (int c = 0; c < 3; c++) a.plane_off[c] = g->plane_off[c];
+    a.pic_stride = g->pic_stride;
+    a.width = g->width;
+    a.height = g->height;
+    a.stride_y = g->stride_y;
+    a.stride_c = g->stride_c;
+    a.bit_depth_y = g->bit_depth_y;
+    a.bit_depth_c = g->bit_depth_c;
+    a.ctb_log2 = ctb_log2;
+    const int ctb = 1 << ctb_log2;
+    a.ctbs_w = (g->width + ctb - 1) / ctb;
+    a.ctbs_h = (g->height + ctb - 1) / ctb;
+    a.n_pics = g->n_pics;
+    a.ctbs = a.ctbs_w * a.ctbs_h;
+    const int64_t luma = (int64_t)a.ctbs * g->n_pics;
+    if (luma * 3 > INT32_MAX) return set_error(P265_EINVAL, "too many CTBs in one SAO batch");
+    a.luma_items = (int32_t)luma;
+    a.items = (int32_t)(luma * 3);
+    if (a.items == 0) return P265_OK;
+    const int grid = (a.items + kSaoWarpsPerCta - 1) / kSaoWarpsPerCta;
+    const bool wide = g->bit_depth_y > 8 || g->bit_depth_c > 8;
+    const int threads = kSaoWarpsPerCta * 32;
+    if (wide) {
+        if (d_no_filter) sao_kernel<uint16_t, true><<<grid, threads, 0, ctx->stream>>>(a);
+        else sao_kernel<uint16_t, false><<<grid, threads, 0, ctx->stream>>>(a);
+    } else {
+        if (d_no_filter) sao_kernel<uint8_t, true><<<grid, threads, 0, ctx->stream>>>(a);
+        else sao_kernel<uint8_t, false><<<grid, threads, 0, ctx->stream>>>(a);
+    }
+    P265_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return P265_OK;
+}
+
+}  // namespace p265

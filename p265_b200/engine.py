@@ -1,0 +1,161 @@
+"""Engine: one C-ABI context (one GPU, one stream) behind a small Python surface.
+
+Host-array methods copy in, run the sm_100a kernels and copy out (what the drop-in
+modules and the end-to-end benchmark use); `*_dev` methods take raw device pointers of
+buffers that are already resident (what the roofline benchmark times).  torch is not
+needed here; bench.py uses it only to own device memory and the stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _lib
+from .picture import SAO_CTB, SF_BYTES, TU_DESC, PicGeom, ResidualBatch
+
+
+class Engine:
+    def __init__(self, device: int = 0, stream: int | None = None):
+        lib = _lib.load()
+        if lib.p265_abi_version() != 1:
+            raise RuntimeError("libp265b200.so ABI mismatch")
+        handle = C.c_void_p()
+        _lib.check(lib.p265_ctx_create(int(device), C.c_void_p(stream) if stream else None,
+                                       C.byref(handle)))
+        self._lib, self._ctx, self.device = lib, handle, int(device)
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.p265_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _lib.check(self._lib.p265_sync(self._ctx))
+
+    @property
+    def sm_count(self) -> int:
+        return int(self._lib.p265_sm_count(self._ctx))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.p265_launch_count(self._ctx))
+
+    # ------------------------------------------------------------------- residual
+    def residual(self, batch: ResidualBatch, out: np.ndarray | None = None) -> np.ndarray:
+        """Residual planes (flat int16 buffer laid out by `batch.geom`) of a batch."""
+        g = batch.geom
+        if out is None:
+            out = np.empty(g.total_elems(), dtype=np.int16)
+        elif out.dtype != np.int16 or out.size < g.total_elems():
+            raise ValueError("out must be int16 with at least geom.total_elems() elements")
+        tus = _lib.as_array(batch.tus, TU_DESC)
+        co = _lib.as_array(batch.coeffs, np.int16)
+        sf = None
+        if batch.scaling_factor is not None:
+            sf = _lib.as_array(batch.scaling_factor, np.uint8)
+            if sf.size != SF_BYTES:
+                raise ValueError("scaling_factor table must have %d bytes" % SF_BYTES)
+        gs = _lib.geom_struct(g)
+        flags = 0 if batch.covers_all else _lib.RES_ZERO_FILL
+        _lib.check(self._lib.p265_residual_batch(
+            self._ctx, _lib.ptr(tus), _lib.bins(batch.bin_counts()), _lib.ptr(co), co.size,
+            _lib.ptr(sf), C.byref(gs), _lib.ptr(out), flags))
+        return out
+
+    def residual_dev(self, d_tus: int, bin_counts, d_coeffs: int, d_sf: int | None, geom: PicGeom,
+                     d_out: int, zero_fill: bool = False):
+        gs = _lib.geom_struct(geom)
+        _lib.check(self._lib.p265_residual_batch_dev(
+            self._ctx, C.c_void_p(d_tus), _lib.bins(bin_counts), C.c_void_p(d_coeffs),
+            C.c_void_p(d_sf) if d_sf else None, C.byref(gs), C.c_void_p(d_out),
+            _lib.RES_ZERO_FILL if zero_fill else 0))
+
+    def dequant(self, batch: ResidualBatch) -> np.ndarray:
+        """scaling.inverse_scaling for every TB: d[] in arena layout ([y][x] per TB)."""
+        tus = _lib.as_array(batch.tus, TU_DESC)
+        co = _lib.as_array(batch.coeffs, np.int16)
+        sf = None if batch.scaling_factor is None else _lib.as_array(batch.scaling_factor, np.uint8)
+        out = np.zeros(co.size, dtype=np.int16)
+        _lib.check(self._lib.p265_dequant_batch(
+            self._ctx, _lib.ptr(tus), len(tus), _lib.ptr(co), co.size, _lib.ptr(sf),
+            batch.geom.bit_depth_y, batch.geom.bit_depth_c, _lib.ptr(out)))
+        return out
+
+    def ref_literal(self, tus: np.ndarray, scaled: np.ndarray) -> np.ndarray:
+        """transform.py:89-109 as written (parity tests only): int32 arena, [x][y] per TB."""
+        tus = _lib.as_array(tus, TU_DESC)
+        sc = _lib.as_array(scaled, np.int16)
+        out = np.zeros(sc.size, dtype=np.int32)
+        _lib.check(self._lib.p265_ref_literal_batch(self._ctx, _lib.ptr(tus), len(tus), _lib.ptr(sc),
+                                                    sc.size, _lib.ptr(out)))
+        return out
+
+    def idct_1d(self, x, log2size: int, tr_type: int, as_written: bool = False) -> np.ndarray:
+        n = 1 << int(log2size)
+        xv = _lib.as_array(np.asarray(x).reshape(-1), np.int32)
+        if xv.size != n:
+            raise ValueError("vector length %d does not match log2size %d" % (xv.size, log2size))
+        out = np.zeros(n, dtype=np.int32)
+        _lib.check(self._lib.p265_idct_1d(self._ctx, _lib.ptr(xv), int(log2size), int(tr_type),
+                                          1 if as_written else 0, _lib.ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------------ SAO
+    def sao(self, rec: np.ndarray, geom: PicGeom, ctb_log2: int, params: np.ndarray,
+            no_filter: np.ndarray | None = None, out: np.ndarray | None = None) -> np.ndarray:
+        dtype = np.uint8 if max(geom.bit_depth_y, geom.bit_depth_c) <= 8 else np.uint16
+        rec = _lib.as_array(rec, dtype).reshape(-1)
+        if rec.size < geom.total_elems():
+            raise ValueError("rec buffer smaller than the geometry")
+        if out is None:
+            out = np.empty_like(rec)
+        par = _lib.as_array(params, SAO_CTB)
+        ctb = 1 << ctb_log2
+        ctbs = ((geom.width + ctb - 1) // ctb) * ((geom.height + ctb - 1) // ctb) * geom.n_pics
+        if par.size != ctbs:
+            raise ValueError("expected %d SAO CTB records, got %d" % (ctbs, par.size))
+        nf = None
+        if no_filter is not None:
+            nf = _lib.as_array(no_filter, np.uint8)
+            need = ((geom.width + 7) // 8) * ((geom.height + 7) // 8) * geom.n_pics
+            if nf.size != need:
+                raise ValueError("no_filter needs %d entries" % need)
+        gs = _lib.geom_struct(geom)
+        _lib.check(self._lib.p265_sao_batch(self._ctx, _lib.ptr(rec), _lib.ptr(out), C.byref(gs),
+                                            int(ctb_log2), _lib.ptr(par), _lib.ptr(nf)))
+        return out
+
+    def sao_dev(self, d_rec: int, d_out: int, geom: PicGeom, ctb_log2: int, d_params: int,
+                d_no_filter: int | None = None):
+        gs = _lib.geom_struct(geom)
+        _lib.check(self._lib.p265_sao_batch_dev(
+            self._ctx, C.c_void_p(d_rec), C.c_void_p(d_out), C.byref(gs), int(ctb_log2),
+            C.c_void_p(d_params), C.c_void_p(d_no_filter) if d_no_filter else None))
+
+    # ---------------------------------------------------------------- measurement
+    def int_peak(self, kind: int):
+        ops, ms = C.c_double(), C.c_double()
+        _lib.check(self._lib.p265_int_peak(self._ctx, int(kind), C.byref(ops), C.byref(ms)))
+        return ops.value, ms.value
+
+
+_engines: dict = {}
+_lock = threading.Lock()
+
+
+def get_engine(device: int = 0) -> Engine:
+    """Process-wide default engine per device (what the drop-in modules use)."""
+    with _lock:
+        e = _engines.get(device)
+        if e is None:
+            e = _engines[device] = Engine(device)
+        return e

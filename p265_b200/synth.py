@@ -1,0 +1,241 @@
+"""Synthetic workloads of the BASELINE.json configs.
+
+There is no network and the reference ships one 352x288 bitstream, so the 1080p / 4K
+numbers are measured on synthetic TB / coefficient mixes of the documented shape:
+
+  config 2  1920x1088 4:2:0  8-bit, luma area 4x4 23 % (DST) / 8x8 29 % / 16x16 31 % /
+            32x32 17 %, flat lists, qP in {22,27,32,37}, TS on 1 % of 4x4   rng 26502
+  config 3  3840x2176 4:2:0 10-bit, 5 / 10 / 25 / 60 %, default scaling lists, qP in
+            34..49, TS on 10 % of 4x4, bypass on 1 % of CUs                  rng 26503
+  config 4  3840x2160 10-bit reconstructed picture + per-CTB SAO parameters  rng 26504
+  config 5  streams 26510.. = config 3 + config 4 per picture
+
+Every TB of a picture is coded (the planes are covered completely).  Coefficients: a
+non-zero mask of density ~0.20 biased to low frequencies, P(nz at (x,y)) ~
+exp(-(x+y)/(N/4)), Laplacian magnitudes (scale 6, DC scale 40).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .picture import (AVAIL_ALL, SAO_CTB, TU_BYPASS, TU_DESC, TU_DST, TU_INTRA, TU_SKIP,
+                      PicGeom, ResidualBatch, pack_scaling_factor, sort_by_size)
+from .scaling_list import default_scaling_factor
+
+CONFIGS = {
+    "1080p8": dict(width=1920, height=1088, bit_depth=8, shares=(0.23, 0.29, 0.31, 0.17),
+                   qps=(22, 27, 32, 37), ts_frac=0.01, bypass_frac=0.0, scaling_lists=False,
+                   seed=26502),
+    "4k10": dict(width=3840, height=2176, bit_depth=10, shares=(0.05, 0.10, 0.25, 0.60),
+                 qps=tuple(range(34, 50)), ts_frac=0.10, bypass_frac=0.01, scaling_lists=True,
+                 seed=26503),
+}
+
+
+def _nz_prob(n: int, density: float) -> np.ndarray:
+    yy, xx = np.mgrid[0:n, 0:n]
+    p = np.exp(-(xx + yy) / (n / 4.0))
+    return np.minimum(1.0, p * (density * n * n / p.sum()))
+
+
+def _coeff_blocks(rng, count: int, n: int, stress: bool) -> np.ndarray:
+    if count == 0:
+        return np.zeros((0, n, n), np.int16)
+    if stress:
+        return rng.integers(-32768, 32768, (count, n, n), dtype=np.int64).astype(np.int16)
+    mask = rng.random((count, n, n), dtype=np.float32) < _nz_prob(n, 0.20).astype(np.float32)
+    mag = rng.laplace(0.0, 6.0, (count, n, n)).astype(np.float32)
+    mag[:, 0, 0] = rng.laplace(0.0, 40.0, count)
+    lv = np.where(mask, np.rint(mag), 0.0)
+    return np.clip(lv, -32767, 32767).astype(np.int16)
+
+
+def _quadrant_tbs(qx, qy, cls):
+    """Luma TB origins (x, y, log2n) for 32x32 quadrants split into class `cls`
+    (0: 4x4, 1: 8x8, 2: 16x16, 3: 32x32)."""
+    log2n = 2 + cls
+    n = 1 << log2n
+    per = 32 // n
+    oy, ox = np.mgrid[0:per, 0:per]
+    # z-order inside the quadrant is irrelevant for the result; keep raster order
+    x = (qx[:, None] + (ox.reshape(-1) * n)[None, :]).reshape(-1)
+    y = (qy[:, None] + (oy.reshape(-1) * n)[None, :]).reshape(-1)
+    return x, y, log2n
+
+
+def residual_picture(cfg: dict, rng, pic: int = 0, stress: bool = False):
+    """TU descriptors (unsorted, coeff_off relative to 0) + coefficient arena of one
+    synthetic picture.  Returns (tus, coeffs)."""
+    w, h = cfg["width"], cfg["height"]
+    bd = cfg["bit_depth"]
+    qx, qy = np.meshgrid(np.arange(0, w, 32), np.arange(0, h, 32))
+    qx, qy = qx.reshape(-1), qy.reshape(-1)
+    nq = qx.size
+    cls = rng.choice(4, size=nq, p=np.array(cfg["shares"]) / sum(cfg["shares"]))
+    qp_q = rng.choice(np.array(cfg["qps"]), size=nq)
+    byp_q = rng.random(nq) < cfg["bypass_frac"]
+    recs, arenas, off = [], [], 0
+
+    def emit(x, y, log2n, c_idx, qp, flags):
+        nonlocal off
+        cnt, n = x.size, 1 << log2n
+        if cnt == 0:
+            return
+        r = np.zeros(cnt, dtype=TU_DESC)
+        r["x"], r["y"], r["log2n"], r["c_idx"] = x, y, log2n, c_idx
+        r["qp"], r["flags"], r["pic"] = qp, flags, pic
+        r["coeff_off"] = (off + np.arange(cnt, dtype=np.int64) * n * n) >> 4
+        blocks = _coeff_blocks(rng, cnt, n, stress)
+        byp = (flags & TU_BYPASS) != 0
+        if byp.any():      # bypass "coefficients" are residual samples: keep them small
+            blocks[byp] = np.clip(blocks[byp], -(1 << bd), (1 << bd) - 1)
+        recs.append(r)
+        arenas.append(blocks.reshape(-1))
+        off += cnt * n * n
+
+    for c in range(4):
+        sel = cls == c
+        if not sel.any():
+            continue
+        x, y, log2n = _quadrant_tbs(qx[sel], qy[sel], c)
+        per_q = (32 >> log2n) ** 2
+        qp = np.repeat(qp_q[sel], per_q)
+        byp = np.repeat(byp_q[sel], per_q)
+        fl = np.full(x.size, TU_INTRA, np.uint8) | np.where(byp, TU_BYPASS, 0).astype(np.uint8)
+        if log2n == 2:
+            fl |= TU_DST
+            ts = (rng.random(x.size) < cfg["ts_frac"]) & ~byp
+            fl |= np.where(ts, TU_SKIP, 0).astype(np.uint8)
+        emit(x, y, log2n, 0, qp, fl)
+        # chroma: half-size TBs; four 4x4 luma TBs share one 4x4 Cb + Cr pair
+        if log2n == 2:
+            keep = ((x & 7) == 0) & ((y & 7) == 0)
+            cx, cy, cl2 = x[keep] >> 1, y[keep] >> 1, 2
+            cqp, cbyp = qp[keep], byp[keep]
+        else:
+            cx, cy, cl2 = x >> 1, y >> 1, log2n - 1
+            cqp, cbyp = qp, byp
+        for c_idx in (1, 2):
+            cfl = np.full(cx.size, TU_INTRA, np.uint8) | np.where(cbyp, TU_BYPASS, 0).astype(np.uint8)
+            if cl2 == 2:
+                ts = (rng.random(cx.size) < cfg["ts_frac"]) & ~cbyp
+                cfl |= np.where(ts, TU_SKIP, 0).astype(np.uint8)
+            # chroma qP: one below luma as in the fixture stream (qp.log: 32 / 31)
+            emit(cx, cy, cl2, c_idx, np.maximum(cqp - 1, 0), cfl)
+    return np.concatenate(recs), np.concatenate(arenas)
+
+
+def residual_batch(name: str, n_pics: int = 1, seed: int | None = None, stress: bool = False,
+                   n_unique: int | None = None) -> ResidualBatch:
+    """A batch of `n_pics` synthetic pictures of config `name`.  `n_unique` < n_pics
+    generates that many distinct pictures and repeats them (distinct memory, same
+    values) to keep host generation time down for large benchmark batches."""
+    cfg = CONFIGS[name]
+    rng = np.random.default_rng(cfg["seed"] if seed is None else seed)
+    n_unique = n_pics if n_unique is None else min(n_unique, n_pics)
+    uniq = [residual_picture(cfg, rng, 0, stress) for _ in range(n_unique)]
+    tus, arenas, off = [], [], 0
+    for p in range(n_pics):
+        t, a = uniq[p % n_unique]
+        t = t.copy()
+        t["pic"] = p
+        t["coeff_off"] = t["coeff_off"].astype(np.int64) + (off >> 4)
+        tus.append(t)
+        arenas.append(a)
+        off += a.size
+    geom = PicGeom(cfg["width"], cfg["height"], n_pics, cfg["bit_depth"], cfg["bit_depth"])
+    sf = pack_scaling_factor(default_scaling_factor()) if cfg["scaling_lists"] else None
+    # kinds cluster inside a size bin (normal, DST, TS, bypass) so warps stay uniform
+    all_t = np.concatenate(tus)
+    key = (-(all_t["log2n"].astype(np.int32)) * 16 + (all_t["flags"] & (TU_SKIP | TU_BYPASS | TU_DST)))
+    order = np.argsort(key, kind="stable")
+    return ResidualBatch(geom=geom, tus=np.ascontiguousarray(all_t[order]),
+                         coeffs=np.concatenate(arenas), scaling_factor=sf, covers_all=True)
+
+
+# ------------------------------------------------------------------------------ SAO
+def sao_picture(width: int, height: int, bit_depth: int, rng, geom: PicGeom, buf: np.ndarray,
+                pic: int) -> None:
+    """Fill picture `pic` of `buf` with a smooth gradient + Gaussian noise (sigma 12 at
+    10 bits) so that all five edge categories occur."""
+    maxv = (1 << bit_depth) - 1
+    scale = maxv / 1023.0
+    for c in range(3):
+        h, w = geom.plane_shape(c)
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+        base = (0.15 + 0.7 * (xx / w * 0.6 + yy / h * 0.4)) * maxv
+        if c:
+            base = maxv - base if c == 2 else base * 0.9
+        noise = rng.normal(0.0, 12.0 * scale, (h, w)).astype(np.float32)
+        geom.plane_view(buf, pic, c)[:] = np.clip(np.rint(base + noise), 0, maxv).astype(buf.dtype)
+
+
+def sao_params(ctbs_h: int, ctbs_w: int, bit_depth: int, rng, two_slices: bool = False) -> np.ndarray:
+    """Per-CTB parameters of config 4: type uniform {off, band, edge} for luma and for
+    the chroma pair (Cb/Cr share type and class, sao.py:58-59,76-77), class / band
+    position uniform, offsets uniform 0..cMax, 25 % merge-left, 15 % merge-up."""
+    c_max = (1 << (min(bit_depth, 10) - 5)) - 1
+    shift = bit_depth - min(bit_depth, 10)
+    tab = np.zeros((ctbs_h, ctbs_w), dtype=SAO_CTB)
+    tab["avail"] = AVAIL_ALL
+    split = (ctbs_h // 2) * ctbs_w + ctbs_w // 3 if two_slices else None   # 2nd slice start
+    for ry in range(ctbs_h):
+        for rx in range(ctbs_w):
+            addr = ry * ctbs_w + rx
+            e = tab[ry, rx]
+            u = rng.random()
+            first_in_slice = addr == 0 or addr == split
+            left_ok = rx > 0 and not (split is not None and addr == split)
+            up_ok = ry > 0 and not (split is not None and addr - ctbs_w < split <= addr)
+            if u < 0.25 and left_ok and not first_in_slice:
+                for f in ("type", "band_pos", "eo_class", "offset_val"):
+                    e[f] = tab[ry, rx - 1][f]
+                continue
+            if u < 0.40 and up_ok:
+                for f in ("type", "band_pos", "eo_class", "offset_val"):
+                    e[f] = tab[ry - 1, rx][f]
+                continue
+            t_l, t_c = rng.integers(0, 3), rng.integers(0, 3)
+            cls_l, cls_c = rng.integers(0, 4), rng.integers(0, 4)
+            for c in range(3):
+                t = t_l if c == 0 else t_c
+                e["type"][c] = t
+                if t == 0:
+                    continue
+                mag = rng.integers(0, c_max + 1, 4) << shift
+                if t == 1:
+                    e["band_pos"][c] = rng.integers(0, 32)
+                    e["offset_val"][c] = mag * rng.choice((-1, 1), 4)
+                else:
+                    e["eo_class"][c] = cls_l if c == 0 else cls_c
+                    e["offset_val"][c] = mag * np.array((1, 1, -1, -1))
+    if two_slices:
+        from .packer import ctb_availability
+        addr = np.arange(ctbs_h * ctbs_w).reshape(ctbs_h, ctbs_w)
+        slice_addr = np.where(addr >= split, split, 0)
+        tab["avail"] = ctb_availability(slice_addr, {0: 1, int(split): 0},
+                                        np.zeros_like(addr), True)
+    return tab
+
+
+def sao_batch(width: int = 3840, height: int = 2160, bit_depth: int = 10, n_pics: int = 1,
+              ctb_log2: int = 6, seed: int = 26504, two_slices: bool = False, n_unique=None):
+    """Returns (geom, rec_buffer, params[n_pics, ctbs_h, ctbs_w])."""
+    rng = np.random.default_rng(seed)
+    geom = PicGeom(width, height, n_pics, bit_depth, bit_depth)
+    dtype = np.uint8 if bit_depth <= 8 else np.uint16
+    buf = np.zeros(geom.total_elems(), dtype=dtype)
+    ctb = 1 << ctb_log2
+    ch, cw = (height + ctb - 1) // ctb, (width + ctb - 1) // ctb
+    n_unique = n_pics if n_unique is None else min(n_unique, n_pics)
+    params = np.zeros((n_pics, ch, cw), dtype=SAO_CTB)
+    for p in range(n_pics):
+        if p < n_unique:
+            sao_picture(width, height, bit_depth, rng, geom, buf, p)
+            params[p] = sao_params(ch, cw, bit_depth, rng, two_slices)
+        else:
+            q = p % n_unique
+            buf[p * geom.pic_stride:(p + 1) * geom.pic_stride] = \
+                buf[q * geom.pic_stride:(q + 1) * geom.pic_stride]
+            params[p] = params[q]
+    return geom, buf, params
