@@ -56,43 +56,59 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons through NVML (same counters nvidia-smi
+    prints, ~1 ms per query) while the timed region runs."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        self.max_mhz, self.err = None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            uuid = None
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                tok = vis.split(",")[index].strip()
+                if tok.startswith("GPU-"):
+                    uuid = tok
+                else:
+                    index = int(tok)
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid) if uuid else pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, repr(e)
 
     def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([f.strip() for f in out.split(",")])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.1)
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((float(mhz), int(reasons)))
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
+                break
+            self._stop_evt.wait(0.002)
 
     def stop(self):
         self._stop_evt.set()
-        self.join(timeout=6)
-        sm, mx, reasons = [], 0.0, set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for s in self.samples:
-            try:
-                sm.append(float(s[0]))
-                mx = max(mx, float(s[1]))
-                for n, v in zip(names, s[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.join(timeout=5)
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                "sw_power_cap": 0x4}
+        sm = [s[0] for s in self.samples]
+        reasons = sorted(n for n, b in bits.items() if any(s[1] & b for s in self.samples))
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+               "reasons": reasons, "samples": len(sm), "how": "NVML, every 2 ms during the timed region"}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 def pinned(n_bytes):
@@ -161,7 +177,8 @@ def run_gpu(args):
 
     def residual():
         eng.residual_dev(d_tus.data_ptr(), bins, d_co.data_ptr(), d_sf.data_ptr() if d_sf is not None else None,
-                         res.geom, d_res.data_ptr(), zero_fill=not res.covers_all)
+                         res.geom, d_res.data_ptr(), zero_fill=not res.covers_all,
+                         sf_replicated=bool(res.sf_replicated))
 
     def sao():
         eng.sao_dev(d_rec.data_ptr(), d_sao.data_ptr(), sgeom, 6, d_par.data_ptr())

@@ -90,6 +90,10 @@ typedef struct p265_sao_ctb {
 #define P265_SF_BYTES 4064 /* ScalingFactor table: [sizeId][matrixId][y][x] uint8    */
 
 #define P265_RES_ZERO_FILL 1 /* clear the planes first (TBs do not cover them)       */
+#define P265_RES_SF_REPLICATED 2 /* the 16x16 / 32x32 matrices of scaling_factor are the
+                                    7.4.5 up-sampling of an 8x8 list (+ DC at [0][0]), as
+                                    every conformant stream has them: enables the fast
+                                    per-column factor path.  Unset: any table works.   */
 
 /* ---- context ------------------------------------------------------------------ */
 int p265_abi_version(void);

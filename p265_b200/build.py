@@ -37,14 +37,15 @@ def stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not stale():
+    extra = os.environ.get("P265_NVCC_EXTRA", "").split()   # e.g. -DP265_CTAS_PER_SM=5 (tuning runs)
+    if not force and not extra and not stale():
         return LIB
     objs = []
     bdir = os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)
     for src in SOURCES:
         obj = os.path.join(bdir, src.replace(".cu", ".o"))
-        cmd = [nvcc(), *NVCC_FLAGS, "-I", os.path.join(REPO, "include"), "-I", CSRC,
+        cmd = [nvcc(), *NVCC_FLAGS, *extra, "-I", os.path.join(REPO, "include"), "-I", CSRC,
                "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

@@ -15,35 +15,117 @@
 namespace p265 {
 
 constexpr int kWarpsPerCta = 4;
+#ifndef P265_CTAS_PER_SM
+#define P265_CTAS_PER_SM 4
+#endif
+constexpr int kCtasPerSm = P265_CTAS_PER_SM;  // 4: 128 regs/thread, 5: 96 regs (small spills)
+constexpr int kCtaSmemBytes = kWarpsPerCta * 2 * kWarpSmemBytes;  // two tiles per warp
 
-template <int LOG2N, bool HAS_SF>
-__device__ __forceinline__ void run_item(const KernelArgs &a, int item, int lane, unsigned char *wsmem) {
-    bool valid;
-    const int tb = lane_tb<LOG2N>(a, item, lane, valid);
-    const TbParams t = make_params(a, tb, valid);
-    phase_load<LOG2N>(lane, t, wsmem);
-    const bool slow = __any_sync(0xffffffffu, t.lsh != 0);  // also fences the tile (bar.warp.sync semantics)
-    __syncwarp();
-    int p[2][(1 << LOG2N) / 2];
-    if (slow) phase_gather<LOG2N, HAS_SF, true>(lane, t, wsmem, p);  // rare
-    else phase_gather<LOG2N, HAS_SF, false>(lane, t, wsmem, p);
-    __syncwarp();  // every lane has read its columns: the tile may be overwritten by g
-    phase_stage1<LOG2N>(lane, t, wsmem, p);
-    __syncwarp();
-    phase_stage2<LOG2N>(lane, t, wsmem);
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int KEEP>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(KEEP) : "memory");
 }
 
-template <bool HAS_SF>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) residual_kernel(const __grid_constant__ KernelArgs a) {
-    __shared__ __align__(128) unsigned char smem[kWarpsPerCta * kWarpSmemBytes];
+__device__ __forceinline__ int bin_of(const KernelArgs &a, int item) {
+    return (item >= a.first_item[1]) + (item >= a.first_item[2]) + (item >= a.first_item[3]);
+}
+
+// descriptor of the TB this lane owns in work item `item`
+__device__ __forceinline__ uint4 fetch_desc(const KernelArgs &a, int item, int lane, bool &valid) {
+    const int bin = bin_of(a, item);
+    int tb;
+    switch (bin) {
+        case 0: tb = lane_tb<5>(a, item - a.first_item[0], lane, valid); break;
+        case 1: tb = lane_tb<4>(a, item - a.first_item[1], lane, valid); break;
+        case 2: tb = lane_tb<3>(a, item - a.first_item[2], lane, valid); break;
+        default: tb = lane_tb<2>(a, item - a.first_item[3], lane, valid); break;
+    }
+    return load_desc(a, tb, valid);
+}
+
+__device__ __forceinline__ void issue_tile(const KernelArgs &a, int item, int lane, const TbParams &t,
+                                           unsigned char *buf) {
+    switch (bin_of(a, item)) {
+        case 0: tile_issue<5>(lane, t, buf); break;
+        case 1: tile_issue<4>(lane, t, buf); break;
+        case 2: tile_issue<3>(lane, t, buf); break;
+        default: tile_issue<2>(lane, t, buf); break;
+    }
+}
+
+// Out of line on purpose: each size path gets its own register allocation instead of
+// inflating the pipeline loop (one call per ~4000-instruction work item).
+template <int LOG2N, int SF>
+__device__ __noinline__ void compute_item(int lane, const TbParams &t, unsigned char *buf) {
+    const bool slow = __any_sync(0xffffffffu, t.lsh != 0);
+    const bool special = __any_sync(0xffffffffu, t.valid && (t.flags & (P265_TU_SKIP | P265_TU_BYPASS)) != 0);
+    if (special) phase_special<LOG2N>(lane, t, buf);
+    int p[2][(1 << LOG2N) / 2];
+    if (slow) phase_gather<LOG2N, SF, true>(lane, t, buf, p);  // rare
+    else phase_gather<LOG2N, SF, false>(lane, t, buf, p);
+    __syncwarp();  // every lane has read its columns: the tile may be overwritten by g
+    phase_stage1<LOG2N>(lane, t, buf, p);
+    __syncwarp();
+    phase_stage2<LOG2N>(lane, t, buf);
+}
+
+// Persistent warps: warp w handles work items w, w + W, w + 2W, ... of the size-sorted
+// list (all warps therefore sit in the same size bin at any time -> one code path hot in
+// the instruction cache).  Three-deep software pipeline per warp:
+//   descriptor of item k+2 (LDG)  |  tile of item k+1 (cp.async into the other buffer)
+//   |  transform of item k
+// so both dependent global-memory latencies of an item are hidden behind arithmetic.
+template <int SF>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) residual_kernel(const __grid_constant__ KernelArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w = blockIdx.x * kWarpsPerCta + warp;
-    if (w >= a.first_item[4]) return;
-    unsigned char *wsmem = smem + warp * kWarpSmemBytes;
-    if (w < a.first_item[1]) run_item<5, HAS_SF>(a, w - a.first_item[0], lane, wsmem);
-    else if (w < a.first_item[2]) run_item<4, HAS_SF>(a, w - a.first_item[1], lane, wsmem);
-    else if (w < a.first_item[3]) run_item<3, HAS_SF>(a, w - a.first_item[2], lane, wsmem);
-    else run_item<2, HAS_SF>(a, w - a.first_item[3], lane, wsmem);
+    const int stride = gridDim.x * kWarpsPerCta, n_items = a.first_item[4];
+    int it = blockIdx.x * kWarpsPerCta + warp;
+    if (it >= n_items) return;
+    unsigned char *buf = smem + warp * (2 * kWarpSmemBytes);
+    int b = 0;
+
+    bool v_cur, v_next = false;
+    const uint4 d_cur = fetch_desc(a, it, lane, v_cur);
+    TbParams t_cur = make_params(a, d_cur, v_cur);
+    issue_tile(a, it, lane, t_cur, buf);
+    cp_async_commit();
+    int it_next = it + stride;
+    uint4 d_next = make_uint4(0, 0, 0, 0);
+    if (it_next < n_items) d_next = fetch_desc(a, it_next, lane, v_next);
+
+    while (true) {
+        const bool has_next = it_next < n_items;
+        TbParams t_next = t_cur;
+        if (has_next) {
+            t_next = make_params(a, d_next, v_next);
+            issue_tile(a, it_next, lane, t_next, buf + (b ^ 1) * kWarpSmemBytes);
+        }
+        cp_async_commit();
+        const int it_nn = it_next + stride;
+        bool v_nn = false;
+        uint4 d_nn = make_uint4(0, 0, 0, 0);
+        if (it_nn < n_items) d_nn = fetch_desc(a, it_nn, lane, v_nn);
+
+        cp_async_wait<1>();  // the current tile has landed (the newest group may be in flight)
+        __syncwarp();
+        unsigned char *cur = buf + b * kWarpSmemBytes;
+        switch (bin_of(a, it)) {
+            case 0: compute_item<5, SF>(lane, t_cur, cur); break;
+            case 1: compute_item<4, SF>(lane, t_cur, cur); break;
+            case 2: compute_item<3, SF>(lane, t_cur, cur); break;
+            default: compute_item<2, SF>(lane, t_cur, cur); break;
+        }
+        __syncwarp();
+        if (!has_next) break;
+        it = it_next;
+        t_cur = t_next;
+        it_next = it_nn;
+        d_next = d_nn;
+        v_next = v_nn;
+        b ^= 1;
+    }
 }
 
 // ---- auxiliary, non-hot kernels ------------------------------------------------------
@@ -129,6 +211,7 @@ static int fill_args(KernelArgs &a, const p265_tu_desc *d_tus, const int32_t bin
     a.tus = d_tus;
     a.coeffs = d_coeffs;
     a.sf = d_sf;
+    a.sf_replicated = 0;
     a.out = d_out;
     for (int c = 0; c < 3; c++) a.plane_off[c] = g->plane_off[c];
     a.pic_stride = g->pic_stride;
@@ -150,21 +233,38 @@ static int fill_args(KernelArgs &a, const p265_tu_desc *d_tus, const int32_t bin
     return P265_OK;
 }
 
+template <int SF>
+static int launch_residual_sf(p265_ctx *ctx, const KernelArgs &a) {
+    static int occ = 0;  // CTAs per SM the kernel really gets (same for every device of a box)
+    if (!occ) {
+        P265_CUDA(cudaFuncSetAttribute(residual_kernel<SF>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared));
+        P265_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, residual_kernel<SF>, kWarpsPerCta * 32,
+                                                                kCtaSmemBytes));
+        if (occ < 1) occ = 1;
+    }
+    const int items = a.first_item[4];
+    int grid = (items + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int persistent = ctx->sm_count * occ;
+    if (grid > persistent) grid = persistent;
+    residual_kernel<SF><<<grid, kWarpsPerCta * 32, kCtaSmemBytes, ctx->stream>>>(a);
+    P265_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return P265_OK;
+}
+
 int launch_residual(p265_ctx *ctx, const p265_tu_desc *d_tus, const int32_t bin_counts[4], const int16_t *d_coeffs,
                     const uint8_t *d_sf, const p265_pic_geom *g, int16_t *d_out, int flags) {
     KernelArgs a;
     int rc = fill_args(a, d_tus, bin_counts, d_coeffs, d_sf, g, d_out);
     if (rc) return rc;
+    a.sf_replicated = (flags & P265_RES_SF_REPLICATED) != 0;
     if (flags & P265_RES_ZERO_FILL)
         P265_CUDA(cudaMemsetAsync(d_out, 0, sizeof(int16_t) * (size_t)g->pic_stride * g->n_pics, ctx->stream));
-    const int items = a.first_item[4];
-    if (items == 0) return P265_OK;
-    const int grid = (items + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (a.sf) residual_kernel<true><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(a);
-    else residual_kernel<false><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(a);
-    P265_CUDA(cudaGetLastError());
-    ctx->launches++;
-    return P265_OK;
+    if (a.first_item[4] == 0) return P265_OK;
+    if (!a.sf) return launch_residual_sf<SF_NONE>(ctx, a);
+    if (a.sf_replicated) return launch_residual_sf<SF_REPLICATED>(ctx, a);
+    return launch_residual_sf<SF_GENERAL>(ctx, a);
 }
 
 int launch_dequant(p265_ctx *ctx, const p265_tu_desc *d_tus, int n_tus, const int16_t *d_coeffs, const uint8_t *d_sf,

@@ -78,6 +78,27 @@ P265_HD int ilog2(unsigned v) {
 #endif
 }
 
+// global -> shared tile copies: LDGSTS (cp.async) on the device so the tile of the NEXT
+// work item streams in while the current one is being transformed; memcpy on the host.
+P265_HD void copy16_async(void *smem_dst, const void *gmem_src) {
+#if defined(__CUDA_ARCH__)
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#else
+    const uint4 v = *reinterpret_cast<const uint4 *>(gmem_src);
+    *reinterpret_cast<uint4 *>(smem_dst) = v;
+#endif
+}
+P265_HD void copy8_async(void *smem_dst, const void *gmem_src) {
+#if defined(__CUDA_ARCH__)
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+#else
+    const uint2 v = *reinterpret_cast<const uint2 *>(gmem_src);
+    *reinterpret_cast<uint2 *>(smem_dst) = v;
+#endif
+}
+
 // ------------------------------------------------------------------ basis tables
 // H.265 8.6.4.2 transMatrix, rebuilt from its cosine structure (see oracle for the
 // same derivation; tests compare both with transform.py:7-72).
@@ -255,6 +276,7 @@ struct KernelArgs {
     const p265_tu_desc *tus;
     const int16_t *coeffs;
     const uint8_t *sf;  // P265_SF_BYTES or nullptr
+    int32_t sf_replicated;  // 16x16 / 32x32 matrices obey the 7.4.5 up-sampling (+ DC at [0][0])
     int16_t *out;
     int64_t plane_off[3];
     int64_t pic_stride;
@@ -273,7 +295,16 @@ P265_HD int sf_matrix_offset(int log2n, int c_idx, int intra) {
     return base + mid * n2;
 }
 
+P265_HD uint4 load_desc(const KernelArgs &a, int tb_index, bool valid) {
+    // 16-byte descriptor read as one vector
+    return valid ? *reinterpret_cast<const uint4 *>(&a.tus[tb_index]) : make_uint4(0, 0, 0, 0);
+}
+
+P265_HD TbParams make_params(const KernelArgs &a, const uint4 d, bool valid);
 P265_HD TbParams make_params(const KernelArgs &a, int tb_index, bool valid) {
+    return make_params(a, load_desc(a, tb_index, valid), valid);
+}
+P265_HD TbParams make_params(const KernelArgs &a, const uint4 d, bool valid) {
     TbParams t;
     t.valid = valid;
     if (!valid) {
@@ -281,8 +312,6 @@ P265_HD TbParams make_params(const KernelArgs &a, int tb_index, bool valid) {
         t.lsh = 0; t.rnd2 = 0; t.sh2 = 0; t.flags = 0;
         return t;
     }
-    // 16-byte descriptor read as one vector
-    const uint4 d = *reinterpret_cast<const uint4 *>(&a.tus[tb_index]);
     const int x = (int)(d.x & 0xffff), y = (int)(d.x >> 16);
     const int log2n = (int)(d.y & 0xff), c_idx = (int)((d.y >> 8) & 0xff);
     const int qp = (int)((d.y >> 16) & 0xff);
@@ -365,38 +394,48 @@ P265_HD int lds_s16(const unsigned char *smem, int byte_off) {
 
 // ---------------------------------------------------------------- phase 0: global -> smem
 // Each lane copies its share (two columns' worth = 4N bytes) of its TB, 16 bytes at a
-// time, fully coalesced across the TB's lanes.  TS / bypass TBs are finished here,
-// element-wise, straight from the registers.
+// time, fully coalesced across the TB's lanes.  Asynchronous on the device: the caller
+// commits / waits the cp.async group and __syncwarp()s before anyone reads the tile.
 template <int LOG2N>
-P265_HD void phase_load(int lane, const TbParams &t, unsigned char *wsmem) {
+P265_HD void tile_issue(int lane, const TbParams &t, unsigned char *wsmem) {
     using L = Layout<LOG2N>;
     constexpr int N = L::N;
     const int tb = lane / L::TPB, tl = lane % L::TPB;
     if (!t.valid) return;
     unsigned char *in = wsmem + tb * L::TB_BYTES;
-    const bool special = (t.flags & (P265_TU_SKIP | P265_TU_BYPASS)) != 0;
-    if (!special) {
-        uint4 v[N / 4];
-        P265_UNROLL
-        for (int i = 0; i < N / 4; i++) v[i] = *reinterpret_cast<const uint4 *>(t.src + (tl + i * L::TPB) * 8);
-        P265_UNROLL
-        for (int i = 0; i < N / 4; i++) {
-            const int chunk = tl + i * L::TPB;  // 16-byte chunk index inside the TB
-            if (N >= 8) {
-                *reinterpret_cast<uint4 *>(in + chunk * 16) = v[i];
-            } else {
-                *reinterpret_cast<uint2 *>(in + chunk * 16) = make_uint2(v[i].x, v[i].y);
-                *reinterpret_cast<uint2 *>(in + chunk * 16 + 8) = make_uint2(v[i].z, v[i].w);
-            }
+    P265_UNROLL
+    for (int i = 0; i < N / 4; i++) {
+        const int chunk = tl + i * L::TPB;  // 16-byte chunk index inside the TB
+        if (N >= 8) {
+            copy16_async(in + chunk * 16, t.src + chunk * 8);
+        } else {  // 4x4 tiles are only 8-byte aligned in shared memory (40-byte pitch)
+            copy8_async(in + chunk * 16, t.src + chunk * 8);
+            copy8_async(in + chunk * 16 + 8, t.src + chunk * 8 + 4);
         }
-        return;
     }
-    // transform-skip (8.6.4.2, tsShift = 7) / transquant-bypass (8.6.2): element-wise
+}
+
+// transform-skip (8.6.4.2, tsShift = 7) / transquant-bypass (8.6.2) TBs: element-wise,
+// straight from the tile to the plane.  Runs before stage 1 overwrites the tile.
+template <int LOG2N>
+P265_HD void phase_special(int lane, const TbParams &t, const unsigned char *wsmem) {
+    using L = Layout<LOG2N>;
+    constexpr int N = L::N;
+    const int tb = lane / L::TPB, tl = lane % L::TPB;
+    if (!t.valid || !(t.flags & (P265_TU_SKIP | P265_TU_BYPASS))) return;
+    const unsigned char *in = wsmem + tb * L::TB_BYTES;
     for (int i = 0; i < N / 4; i++) {
         const int chunk = tl + i * L::TPB;
-        const uint4 v = *reinterpret_cast<const uint4 *>(t.src + chunk * 8);
+        uint32_t w[4];
+        if (N >= 8) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(in + chunk * 16);
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        } else {
+            const uint2 v0 = *reinterpret_cast<const uint2 *>(in + chunk * 16);
+            const uint2 v1 = *reinterpret_cast<const uint2 *>(in + chunk * 16 + 8);
+            w[0] = v0.x; w[1] = v0.y; w[2] = v1.x; w[3] = v1.y;
+        }
         // 8 consecutive coefficients: one row segment (N >= 8) or two rows (N == 4)
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
         uint32_t o[4];
         P265_UNROLL
         for (int k = 0; k < 4; k++) {
@@ -429,24 +468,50 @@ P265_HD void phase_load(int lane, const TbParams &t, unsigned char *wsmem) {
 }
 
 // ------------------------------------------- phase 1a: smem -> packed, dequantised operands
+// Scaling-factor access modes of the gather.
+//   SF_NONE        flat m = 16 (scaling_list_enabled_flag == 0, scaling.py:32-33)
+//   SF_GENERAL     m[y][x] read per coefficient from the 4064-byte table (any table)
+//   SF_REPLICATED  the table obeys 7.4.5: 16x16 / 32x32 entries are the 8x8 list
+//                  up-sampled 2x / 4x with the DC value at [0][0]; a column then has only
+//                  8 distinct factors, fetched once per column and pre-multiplied by
+//                  levelScale -- no per-coefficient load or multiply is left.
+enum { SF_NONE = 0, SF_GENERAL = 1, SF_REPLICATED = 2 };
+
 // SLOW must be chosen warp-uniformly: true when any lane of the warp has a TB with
 // per >= bdShift (left-shift dequantisation, only reachable at very high qP on small TBs).
-template <int LOG2N, bool HAS_SF, bool SLOW>
+template <int LOG2N, int SF, bool SLOW>
 P265_HD void phase_gather(int lane, const TbParams &t, const unsigned char *wsmem,
                           int (&p)[2][(1 << LOG2N) / 2]) {
     using L = Layout<LOG2N>;
     constexpr int N = L::N;
+    constexpr int K = N < 8 ? N : 8;      // distinct factors per column (SF_REPLICATED)
+    constexpr int REP = N / K;            // 1, 1, 2, 4
     const int tb = lane / L::TPB, tl = lane % L::TPB;
     const unsigned char *in = wsmem + tb * L::TB_BYTES;
     const int x[2] = {slot_index_rt(N, tl, 0), slot_index_rt(N, tl, 1)};
-    const uint8_t *sf = (HAS_SF && t.sf) ? t.sf : nullptr;
-    if (HAS_SF && !sf) {  // invalid lane: keep the loads in bounds
+    const uint8_t *sf = (SF != SF_NONE && t.sf) ? t.sf : nullptr;
+    if (SF != SF_NONE && !sf) {
+        // invalid lane, or a PRESCALED / bypass-only TB inside a scaling-list batch: keep
+        // the table loads in bounds by running the flat formula (w already set up)
         P265_UNROLL
         for (int c = 0; c < 2; c++) {
             P265_UNROLL
-            for (int s = 0; s < N / 2; s++) p[c][s] = 0;
+            for (int s = 0; s < N / 2; s++) {
+                const int e0 = slot_index(N, s, 0) * N + x[c], e1 = slot_index(N, s, 1) * N + x[c];
+                p[c][s] = pack_sat(dequant(lds_s16(in, e0 * 2), t.w, t), dequant(lds_s16(in, e1 * 2), t.w, t));
+            }
         }
         return;
+    }
+    int mw[2][K];
+    int dc[2] = {0, 0};
+    if (SF == SF_REPLICATED) {
+        P265_UNROLL
+        for (int c = 0; c < 2; c++) {
+            P265_UNROLL
+            for (int k = 0; k < K; k++) mw[c][k] = (int)sf[(k * REP + (REP > 1 ? 1 : 0)) * N + x[c]] * t.w;
+            dc[c] = (REP > 1 && x[c] == 0) ? (int)sf[0] * t.w : mw[c][0];
+        }
     }
     P265_UNROLL
     for (int c = 0; c < 2; c++) {
@@ -456,9 +521,12 @@ P265_HD void phase_gather(int lane, const TbParams &t, const unsigned char *wsme
             const int e0 = y0 * N + x[c], e1 = y1 * N + x[c];
             const int l0 = lds_s16(in, e0 * 2), l1 = lds_s16(in, e1 * 2);
             int m0 = t.w, m1 = t.w;
-            if (HAS_SF) {
+            if (SF == SF_GENERAL) {
                 m0 *= (int)sf[e0];
                 m1 *= (int)sf[e1];
+            } else if (SF == SF_REPLICATED) {
+                m0 = y0 == 0 ? dc[c] : mw[c][y0 / REP];
+                m1 = mw[c][y1 / REP];
             }
             if (!SLOW) p[c][s] = pack_sat(dequant_fast(l0, m0, t), dequant_fast(l1, m1, t));
             else p[c][s] = pack_sat(dequant(l0, m0, t), dequant(l1, m1, t));

@@ -79,20 +79,27 @@ struct Strip {
     bool mem_left, mem_right;  // a sample exists in memory left / right of the CTB
 };
 
-// Load one row of the strip (+ halo when HALO).  Every lane of the warp must call this
-// (shuffles); `p` points at the lane's first sample of the row.
+// Loading a row is split in two so that several rows can be in flight at once:
+// row_issue() only issues the global loads (strip + the two edge samples a CTB-border
+// lane needs), row_finish() exchanges the horizontal neighbours through shuffles.
+// Every lane of the warp must call row_finish(); `p` points at the lane's first sample.
 template <typename T, bool HALO>
-__device__ __forceinline__ void load_row(Row &r, const T *p, const Strip &s) {
+__device__ __forceinline__ void row_issue(Row &r, const T *p, const Strip &s) {
     uint32_t w[4];
     load8<T>(p, w);
     r.e[1] = w[0]; r.e[2] = w[1]; r.e[3] = w[2]; r.e[4] = w[3];
     if (HALO) {
-        uint32_t l = __shfl_up_sync(0xffffffffu, w[3], 1);
-        uint32_t rr = __shfl_down_sync(0xffffffffu, w[0], 1);
-        if (s.first_col) l = s.mem_left ? ((uint32_t)p[-1] << 16) : 0u;
-        if (s.last_col) rr = s.mem_right ? (uint32_t)p[8] : 0u;
-        r.e[0] = l;
-        r.e[5] = rr;
+        r.e[0] = (s.first_col && s.mem_left) ? ((uint32_t)p[-1] << 16) : 0u;
+        r.e[5] = (s.last_col && s.mem_right) ? (uint32_t)p[8] : 0u;
+    }
+}
+template <bool HALO>
+__device__ __forceinline__ void row_finish(Row &r, const Strip &s) {
+    if (HALO) {
+        const uint32_t l = __shfl_up_sync(0xffffffffu, r.e[4], 1);
+        const uint32_t rr = __shfl_down_sync(0xffffffffu, r.e[1], 1);
+        if (!s.first_col) r.e[0] = l;
+        if (!s.last_col) r.e[5] = rr;
     }
 }
 
@@ -194,46 +201,68 @@ __device__ __forceinline__ void edge_strip(const T *in, T *out, const Geo &g, co
                                            const ItemConst &k, const uint8_t *nf_row, int nf_stride, int nf_shift) {
     // `in` / `out` point at (row y0, lane's first column)
     constexpr bool HALO = CLS != 1;
-    Row P, C, N;
+    constexpr int CH = 4;  // rows fetched per batch: CH independent 16-byte loads in flight per lane
+    Row P, C;
     auto rowptr = [&](int ly) {
         int y = g.y0 + ly;
         y = y < 0 ? 0 : (y >= g.h ? g.h - 1 : y);
         return in + (int64_t)(y - g.y0) * g.stride;
     };
-    load_row<T, HALO>(P, rowptr(g.row0 - 1), s);
-    load_row<T, HALO>(C, rowptr(g.row0), s);
+    row_issue<T, HALO>(P, rowptr(g.row0 - 1), s);
+    row_issue<T, HALO>(C, rowptr(g.row0), s);
+    Row Nn[CH];
+#pragma unroll
+    for (int j = 0; j < CH; j++) row_issue<T, HALO>(Nn[j], rowptr(g.row0 + 1 + j), s);
+    row_finish<HALO>(P, s);
+    row_finish<HALO>(C, s);
     uint32_t mid[4];
     row_mask<CLS>(m, false, false, mid);
-    for (int r = 0; r < g.rows; r++) {
-        const int ly = g.row0 + r;
-        load_row<T, HALO>(N, rowptr(ly + 1), s);
-        const bool top = ly == 0, bot = ly == g.vh - 1;
-        uint32_t keep[4], o[4];
-        if (top || bot) row_mask<CLS>(m, top, bot, keep);
-        else {
+    for (int r = 0; r < g.rows; r += CH) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) keep[i] = mid[i];
-        }
-        if (NOFILT) {
-            const uint8_t *f = nf_row + (int64_t)(min(ly, g.vh - 1) >> nf_shift) * nf_stride;
-            if (nf_shift == 3) {
-                if (f[0]) keep[0] = keep[1] = keep[2] = keep[3] = 0xffffffffu;
-            } else {
-                if (f[0]) keep[0] = keep[1] = 0xffffffffu;
-                if (f[1]) keep[2] = keep[3] = 0xffffffffu;
+        for (int j = 0; j < CH; j++) {
+            if (r + j >= g.rows) break;  // warp-uniform
+            row_finish<HALO>(Nn[j], s);
+            const int ly = g.row0 + r + j;
+            const bool top = ly == 0, bot = ly == g.vh - 1;
+            uint32_t keep[4], o[4];
+            if (top || bot) row_mask<CLS>(m, top, bot, keep);
+            else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) keep[i] = mid[i];
             }
+            if (NOFILT) {
+                const uint8_t *f = nf_row + (int64_t)(min(ly, g.vh - 1) >> nf_shift) * nf_stride;
+                if (nf_shift == 3) {
+                    if (f[0]) keep[0] = keep[1] = keep[2] = keep[3] = 0xffffffffu;
+                } else {
+                    if (f[0]) keep[0] = keep[1] = 0xffffffffu;
+                    if (f[1]) keep[2] = keep[3] = 0xffffffffu;
+                }
+            }
+            edge_row<CLS>(P, C, Nn[j], k, keep, o);
+            if (g.active && ly < g.vh) store8<T>(out + (int64_t)ly * g.stride, o);
+            P = C;
+            C = Nn[j];
+            // refill this slot with the row CH ahead (consumed in the next batch)
+            if (r + j + CH < g.rows) row_issue<T, HALO>(Nn[j], rowptr(ly + 1 + CH), s);
         }
-        edge_row<CLS>(P, C, N, k, keep, o);
-        if (g.active && ly < g.vh) store8<T>(out + (int64_t)ly * g.stride, o);
-        P = C;
-        C = N;
     }
 }
 
 template <typename T, bool NOFILT>
 __device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int rx, int ry, int lane) {
-    const p265_sao_ctb q = a.params[((int64_t)pic * a.ctbs_h + ry) * a.ctbs_w + rx];
-    const int type = q.type[c];
+    // field-by-field reads (a by-value copy indexed by `c` would live in local memory)
+    const p265_sao_ctb *qp = &a.params[((int64_t)pic * a.ctbs_h + ry) * a.ctbs_w + rx];
+    struct {
+        int band_pos, eo_class, avail;
+        int offset_val[4];
+    } q;
+    const int type = qp->type[c];
+    q.band_pos = qp->band_pos[c];
+    q.eo_class = qp->eo_class[c];
+    q.avail = qp->avail;
+#pragma unroll
+    for (int i = 0; i < 4; i++) q.offset_val[i] = qp->offset_val[c][i];
     const int cs = (1 << a.ctb_log2) >> (c ? 1 : 0);
     const int w = c ? a.width >> 1 : a.width, h = c ? a.height >> 1 : a.height;
     const int bd = c ? a.bit_depth_c : a.bit_depth_y;
@@ -281,28 +310,37 @@ __device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int r
     ItemConst k;
     k.maxv2 = ((1u << bd) - 1u) * 0x00010001u;
     k.band_shift = bd - 5;
-    k.band_k = (uint32_t)(32 - q.band_pos[c]) * 0x00010001u;
-    const uint32_t o1 = (uint8_t)q.offset_val[c][0], o2 = (uint8_t)q.offset_val[c][1];
-    const uint32_t o3 = (uint8_t)q.offset_val[c][2], o4 = (uint8_t)q.offset_val[c][3];
+    k.band_k = (uint32_t)(32 - q.band_pos) * 0x00010001u;
+    const uint32_t o1 = (uint8_t)q.offset_val[0], o2 = (uint8_t)q.offset_val[1];
+    const uint32_t o3 = (uint8_t)q.offset_val[2], o4 = (uint8_t)q.offset_val[3];
 
     if (type != 2) {
         // off: copy; band: bandTable lookup (pool index = band - band_position, 4 = none)
         k.pool_lo = o1 | (o2 << 8) | (o3 << 16) | (o4 << 24);
         k.pool_hi = 0;
-        for (int r = 0; r < g.rows; r++) {
-            const int lyr = g.row0 + r;
-            if (!(g.active && lyr < g.vh)) continue;
-            uint32_t wv[4], o[4];
-            load8<T>(in + (int64_t)lyr * g.stride, wv);
-            bool skip[2] = {false, false};
-            if (NOFILT) {
-                const uint8_t *f = nf_row + (int64_t)(lyr >> nf_shift) * nf_stride;
-                skip[0] = f[0] != 0;
-                skip[1] = nf_shift == 3 ? skip[0] : (f[1] != 0);
+        constexpr int CH = 4;
+        for (int r = 0; r < g.rows; r += CH) {
+            uint32_t wv[CH][4];
+#pragma unroll
+            for (int j = 0; j < CH; j++) {
+                const int lyr = g.row0 + r + j;
+                if (r + j < g.rows && g.active && lyr < g.vh) load8<T>(in + (int64_t)lyr * g.stride, wv[j]);
             }
 #pragma unroll
-            for (int i = 0; i < 4; i++) o[i] = (type == 1 && !skip[i >> 1]) ? band_word(wv[i], k) : wv[i];
-            store8<T>(out + (int64_t)lyr * g.stride, o);
+            for (int j = 0; j < CH; j++) {
+                const int lyr = g.row0 + r + j;
+                if (!(r + j < g.rows && g.active && lyr < g.vh)) continue;
+                uint32_t o[4];
+                bool skip[2] = {false, false};
+                if (NOFILT) {
+                    const uint8_t *f = nf_row + (int64_t)(lyr >> nf_shift) * nf_stride;
+                    skip[0] = f[0] != 0;
+                    skip[1] = nf_shift == 3 ? skip[0] : (f[1] != 0);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) o[i] = (type == 1 && !skip[i >> 1]) ? band_word(wv[j][i], k) : wv[j][i];
+                store8<T>(out + (int64_t)lyr * g.stride, o);
+            }
         }
         return;
     }
@@ -334,7 +372,7 @@ __device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int r
         }
         m.col_l[i] = cl; m.col_r[i] = cr; m.beyond[i] = be;
     }
-    switch (q.eo_class[c]) {
+    switch (q.eo_class) {
         case 0: edge_strip<T, 0, NOFILT>(in, out, g, s, m, k, nf_row, nf_stride, nf_shift); break;
         case 1: edge_strip<T, 1, NOFILT>(in, out, g, s, m, k, nf_row, nf_stride, nf_shift); break;
         case 2: edge_strip<T, 2, NOFILT>(in, out, g, s, m, k, nf_row, nf_stride, nf_shift); break;

@@ -66,18 +66,21 @@ class Engine:
                 raise ValueError("scaling_factor table must have %d bytes" % SF_BYTES)
         gs = _lib.geom_struct(g)
         flags = 0 if batch.covers_all else _lib.RES_ZERO_FILL
+        if sf is not None and batch.sf_replicated:
+            flags |= _lib.RES_SF_REPLICATED
         _lib.check(self._lib.p265_residual_batch(
             self._ctx, _lib.ptr(tus), _lib.bins(batch.bin_counts()), _lib.ptr(co), co.size,
             _lib.ptr(sf), C.byref(gs), _lib.ptr(out), flags))
         return out
 
     def residual_dev(self, d_tus: int, bin_counts, d_coeffs: int, d_sf: int | None, geom: PicGeom,
-                     d_out: int, zero_fill: bool = False):
+                     d_out: int, zero_fill: bool = False, sf_replicated: bool = False):
         gs = _lib.geom_struct(geom)
+        flags = (_lib.RES_ZERO_FILL if zero_fill else 0) | \
+            (_lib.RES_SF_REPLICATED if (d_sf and sf_replicated) else 0)
         _lib.check(self._lib.p265_residual_batch_dev(
             self._ctx, C.c_void_p(d_tus), _lib.bins(bin_counts), C.c_void_p(d_coeffs),
-            C.c_void_p(d_sf) if d_sf else None, C.byref(gs), C.c_void_p(d_out),
-            _lib.RES_ZERO_FILL if zero_fill else 0))
+            C.c_void_p(d_sf) if d_sf else None, C.byref(gs), C.c_void_p(d_out), flags))
 
     def dequant(self, batch: ResidualBatch) -> np.ndarray:
         """scaling.inverse_scaling for every TB: d[] in arena layout ([y][x] per TB)."""

@@ -103,6 +103,11 @@ class ResidualBatch:
     coeffs: np.ndarray                      # int16 arena
     scaling_factor: np.ndarray | None = None    # uint8[4064] or None (flat 16)
     covers_all: bool = False                # TBs tile every plane completely
+    sf_replicated: bool | None = None       # None: detect from the table (see sf_is_replicated)
+
+    def __post_init__(self):
+        if self.scaling_factor is not None and self.sf_replicated is None:
+            self.sf_replicated = sf_is_replicated(self.scaling_factor)
 
     def bin_counts(self):
         l2 = self.tus["log2n"]
@@ -121,6 +126,24 @@ def sort_by_size(tus: np.ndarray) -> np.ndarray:
 def sf_offset(size_id: int, matrix_id: int) -> int:
     n = 4 << size_id
     return _SF_OFFSETS[size_id] + matrix_id * n * n
+
+
+def sf_is_replicated(table: np.ndarray) -> bool:
+    """True when the 16x16 / 32x32 matrices of a packed table are an 8x8 list up-sampled
+    2x / 4x with only [0][0] (the DC value) allowed to differ -- what 7.4.5 produces for
+    every conformant stream.  Enables the kernel's per-column factor path."""
+    table = np.asarray(table, dtype=np.uint8).reshape(-1)
+    if table.size != SF_BYTES:
+        return False
+    for size_id, count, rep in ((2, 6, 2), (3, 2, 4)):
+        n = 4 << size_id
+        for m in range(count):
+            off = sf_offset(size_id, m)
+            f = table[off:off + n * n].reshape(n, n).copy()
+            f[0, 0] = f[0, 1]
+            if not np.array_equal(f, np.kron(f[::rep, ::rep], np.ones((rep, rep), np.uint8))):
+                return False
+    return True
 
 
 def pack_scaling_factor(sf: dict) -> np.ndarray:

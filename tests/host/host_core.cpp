@@ -21,24 +21,28 @@ static void run_item(const KernelArgs &a, int item) {
         int tb = lane_tb<LOG2N>(a, item, lane, valid);
         t[lane] = make_params(a, tb, valid);
     }
-    for (int lane = 0; lane < 32; lane++) phase_load<LOG2N>(lane, t[lane], smem);
+    for (int lane = 0; lane < 32; lane++) tile_issue<LOG2N>(lane, t[lane], smem);
+    for (int lane = 0; lane < 32; lane++) phase_special<LOG2N>(lane, t[lane], smem);
     static int p[32][2][L::N / 2];
     bool slow = false;
     for (int lane = 0; lane < 32; lane++) slow |= t[lane].lsh != 0;
+    const int sf = !a.sf ? SF_NONE : (a.sf_replicated ? SF_REPLICATED : SF_GENERAL);
     for (int lane = 0; lane < 32; lane++) {
-        if (a.sf && slow) phase_gather<LOG2N, true, true>(lane, t[lane], smem, p[lane]);
-        else if (a.sf) phase_gather<LOG2N, true, false>(lane, t[lane], smem, p[lane]);
-        else if (slow) phase_gather<LOG2N, false, true>(lane, t[lane], smem, p[lane]);
-        else phase_gather<LOG2N, false, false>(lane, t[lane], smem, p[lane]);
+        if (sf == SF_NONE && slow) phase_gather<LOG2N, SF_NONE, true>(lane, t[lane], smem, p[lane]);
+        else if (sf == SF_NONE) phase_gather<LOG2N, SF_NONE, false>(lane, t[lane], smem, p[lane]);
+        else if (sf == SF_GENERAL && slow) phase_gather<LOG2N, SF_GENERAL, true>(lane, t[lane], smem, p[lane]);
+        else if (sf == SF_GENERAL) phase_gather<LOG2N, SF_GENERAL, false>(lane, t[lane], smem, p[lane]);
+        else if (slow) phase_gather<LOG2N, SF_REPLICATED, true>(lane, t[lane], smem, p[lane]);
+        else phase_gather<LOG2N, SF_REPLICATED, false>(lane, t[lane], smem, p[lane]);
     }
     for (int lane = 0; lane < 32; lane++) phase_stage1<LOG2N>(lane, t[lane], smem, p[lane]);
     for (int lane = 0; lane < 32; lane++) phase_stage2<LOG2N>(lane, t[lane], smem);
 }
 
 extern "C" int host_residual_batch(const p265_tu_desc *tus, const int32_t bin_counts[4], const int16_t *coeffs,
-                                   const uint8_t *sf, const p265_pic_geom *g, int16_t *out) {
+                                   const uint8_t *sf, int sf_replicated, const p265_pic_geom *g, int16_t *out) {
     KernelArgs a;
-    a.tus = tus; a.coeffs = coeffs; a.sf = sf; a.out = out;
+    a.tus = tus; a.coeffs = coeffs; a.sf = sf; a.out = out; a.sf_replicated = sf_replicated;
     for (int c = 0; c < 3; c++) a.plane_off[c] = g->plane_off[c];
     a.pic_stride = g->pic_stride;
     a.stride_y = g->stride_y; a.stride_c = g->stride_c;

@@ -170,3 +170,36 @@ def test_ref_literal_matches_reference_outputs(engine, sanity_batch):
     z = np.load(os.path.join(GOLDEN, "sanity_residual.npz"))
     got = engine.ref_literal(batch.tus, z["ref_scaled_yx"])
     assert np.array_equal(got, z["ref_literal_xy"])
+
+
+def test_sf_general_and_replicated_paths_agree(engine, c_oracle):
+    """Default (7.4.5-replicated) lists through both scaling-factor paths of the kernel."""
+    batch = synth.residual_batch(small_cfg("4k10", 320, 192), n_pics=2)
+    assert batch.sf_replicated is True
+    ref = c_oracle.residual_batch(batch, zero_fill=False)
+    assert_planes_equal(batch.geom, engine.residual(batch), ref)
+    batch.sf_replicated = False
+    assert_planes_equal(batch.geom, engine.residual(batch), ref)
+
+
+def test_custom_dc_and_lists(engine, c_oracle):
+    """Non-default lists with distinct DC values (still replicated -> fast path)."""
+    from p265_b200 import scaling_list
+    rng = np.random.default_rng(21)
+    lists, dc = scaling_list.default_lists()
+    for k in lists:
+        lists[k] = [int(v) for v in rng.integers(1, 256, len(lists[k]))]
+    for k in dc:
+        dc[k] = int(rng.integers(1, 256))
+    table = pack_scaling_factor(scaling_list.expand(lists, dc))
+    batch = synth.residual_batch(small_cfg("4k10", 256, 128), n_pics=1, seed=5)
+    batch = ResidualBatch(batch.geom, batch.tus, batch.coeffs, table, covers_all=True)
+    assert batch.sf_replicated is True
+    assert_planes_equal(batch.geom, engine.residual(batch), c_oracle.residual_batch(batch, zero_fill=False))
+
+
+def test_many_items_per_warp(engine, c_oracle):
+    """Enough TBs that every persistent warp loops over several work items of every size
+    (exercises the double-buffered tile prefetch)."""
+    batch = synth.residual_batch("1080p8", n_pics=6, n_unique=2)
+    assert_planes_equal(batch.geom, engine.residual(batch), c_oracle.residual_batch(batch, zero_fill=False))
