@@ -14,12 +14,19 @@
 
 namespace p265 {
 
-constexpr int kWarpsPerCta = 4;
-#ifndef P265_CTAS_PER_SM
-#define P265_CTAS_PER_SM 4
+// Occupancy plan (per SM): 11 CTAs x 2 warps = 22 warps, <= 93 registers/thread,
+// 11 x 18.5 KB = 204 KB of shared memory (tile + g + descriptor ring per warp).
+#ifndef P265_WARPS_PER_CTA
+#define P265_WARPS_PER_CTA 2
 #endif
-constexpr int kCtasPerSm = P265_CTAS_PER_SM;  // 4: 128 regs/thread, 5: 96 regs (small spills)
-constexpr int kCtaSmemBytes = kWarpsPerCta * 2 * kWarpSmemBytes;  // two tiles per warp
+#ifndef P265_CTAS_PER_SM
+#define P265_CTAS_PER_SM 11
+#endif
+constexpr int kWarpsPerCta = P265_WARPS_PER_CTA;
+constexpr int kCtasPerSm = P265_CTAS_PER_SM;
+constexpr int kDescRingBytes = 2 * 32 * 16;                          // 2 slots x 32 lanes x 16 B
+constexpr int kWarpBytes = 2 * kWarpSmemBytes + kDescRingBytes;      // in + g + ring = 9472
+constexpr int kCtaSmemBytes = kWarpsPerCta * kWarpBytes;
 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int KEEP>
@@ -27,105 +34,104 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(KEEP) : "memory");
 }
 
-__device__ __forceinline__ int bin_of(const KernelArgs &a, int item) {
-    return (item >= a.first_item[1]) + (item >= a.first_item[2]) + (item >= a.first_item[3]);
+// Out-of-line wrappers (see residual_core.cuh): one copy of each 1-D pass per size, shared
+// by the two columns / rows a lane owns.  Inside a loop ptxas would hoist the ~90 packed
+// basis constants of the 32-point butterfly and need > 180 registers; as functions each
+// pass keeps a small allocation and fetches its constants just in time (LDCU).
+template <int LOG2N, int SF, bool SLOW>
+__device__ __noinline__ void stage1_call(const unsigned char *in, unsigned char *g, int x, int tl, int half,
+                                         const uint8_t *sf, int w, int rnd, int sh, int lsh, int dst_flag) {
+    stage1_column<LOG2N, SF, SLOW>(in, g, x, tl, half, sf, w, rnd, sh, lsh, dst_flag);
+}
+template <int LOG2N>
+__device__ __noinline__ void stage2_call(const unsigned char *g, int row, int16_t *dst, int rnd2, int sh2,
+                                         int dst_flag) {
+    stage2_row<LOG2N>(g, row, dst, rnd2, sh2, dst_flag);
 }
 
-// descriptor of the TB this lane owns in work item `item`
-__device__ __forceinline__ uint4 fetch_desc(const KernelArgs &a, int item, int lane, bool &valid) {
-    const int bin = bin_of(a, item);
-    int tb;
-    switch (bin) {
-        case 0: tb = lane_tb<5>(a, item - a.first_item[0], lane, valid); break;
-        case 1: tb = lane_tb<4>(a, item - a.first_item[1], lane, valid); break;
-        case 2: tb = lane_tb<3>(a, item - a.first_item[2], lane, valid); break;
-        default: tb = lane_tb<2>(a, item - a.first_item[3], lane, valid); break;
-    }
-    return load_desc(a, tb, valid);
-}
-
-__device__ __forceinline__ void issue_tile(const KernelArgs &a, int item, int lane, const TbParams &t,
-                                           unsigned char *buf) {
-    switch (bin_of(a, item)) {
-        case 0: tile_issue<5>(lane, t, buf); break;
-        case 1: tile_issue<4>(lane, t, buf); break;
-        case 2: tile_issue<3>(lane, t, buf); break;
-        default: tile_issue<2>(lane, t, buf); break;
-    }
-}
-
-// Out of line on purpose: each size path gets its own register allocation instead of
-// inflating the pipeline loop (one call per ~4000-instruction work item).
+// One size bin, one warp: items w, w + W, w + 2W, ... of the bin.  Software pipeline,
+// everything asynchronous (cp.async / LDGSTS, no register staging):
+//     descriptor of item k+2  ->  lane-private slot of a 2-entry ring in shared memory
+//     tile of item k+1        ->  `in`, issued as soon as stage 1 of item k has consumed it
+//     stage 2 of item k       ->  overlaps the tile copy
+// so both dependent global-memory latencies of an item hide behind arithmetic.
 template <int LOG2N, int SF>
-__device__ __noinline__ void compute_item(int lane, const TbParams &t, unsigned char *buf) {
-    const bool slow = __any_sync(0xffffffffu, t.lsh != 0);
-    const bool special = __any_sync(0xffffffffu, t.valid && (t.flags & (P265_TU_SKIP | P265_TU_BYPASS)) != 0);
-    if (special) phase_special<LOG2N>(lane, t, buf);
-    int p[2][(1 << LOG2N) / 2];
-    if (slow) phase_gather<LOG2N, SF, true>(lane, t, buf, p);  // rare
-    else phase_gather<LOG2N, SF, false>(lane, t, buf, p);
-    __syncwarp();  // every lane has read its columns: the tile may be overwritten by g
-    phase_stage1<LOG2N>(lane, t, buf, p);
+__device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride, int lane, unsigned char *wbase) {
+    using L = Layout<LOG2N>;
+    constexpr int N = L::N, bin = 5 - LOG2N;
+    const int n_items = a.first_item[bin + 1] - a.first_item[bin];
+    if (gw >= n_items) return;
+    unsigned char *in_base = wbase, *g_base = wbase + kWarpSmemBytes;
+    uint4 *ring = reinterpret_cast<uint4 *>(wbase + 2 * kWarpSmemBytes) + lane;  // slot s at ring[32 * s]
+    const int tb_l = lane / L::TPB, tl = lane % L::TPB;
+    const unsigned char *in = in_base + tb_l * L::TB_BYTES;
+    unsigned char *g = g_base + tb_l * L::TB_BYTES;
+    const int x0 = slot_index_rt(N, tl, 0), x1 = slot_index_rt(N, tl, 1);
+    bool valid;
+    {   // prologue: first descriptor by plain load, its tile and the second descriptor async
+        const int tb = lane_tb<LOG2N>(a, gw, lane, valid);
+        const uint4 d0 = load_desc(a, tb, valid);
+        ring[0] = d0;
+        tile_issue<LOG2N>(lane, a.coeffs + (size_t)d0.z * 16, valid, in_base);
+        if (gw + stride < n_items) {
+            bool v1;
+            const int tb1 = lane_tb<LOG2N>(a, gw + stride, lane, v1);
+            if (v1) copy16_async(&ring[32], &a.tus[tb1]);
+        }
+        cp_async_commit();
+    }
+    int k = 0;
+    for (int it = gw; it < n_items; it += stride, k ^= 1) {
+        cp_async_wait<0>();  // tile k and descriptor k+1 have landed
+        __syncwarp();        // ... for every lane; also: all lanes are done with g of item k-1
+        lane_tb<LOG2N>(a, it, lane, valid);
+        const TbParams t = make_params(a, ring[32 * k], valid);
+        const bool is_special = (t.flags & (P265_TU_SKIP | P265_TU_BYPASS)) != 0;
+        const bool slow = __any_sync(0xffffffffu, t.lsh != 0);
+        if (__any_sync(0xffffffffu, t.valid && is_special)) phase_special<LOG2N>(lane, t, in_base);
+        const int dstf = t.flags & P265_TU_DST;
+        if (!slow) {
+            stage1_call<LOG2N, SF, false>(in, g, x0, tl, 0, t.sf, t.w, t.rnd, t.sh, 0, dstf);
+            stage1_call<LOG2N, SF, false>(in, g, x1, tl, 1, t.sf, t.w, t.rnd, t.sh, 0, dstf);
+        } else {  // rare
+            stage1_call<LOG2N, SF, true>(in, g, x0, tl, 0, t.sf, t.w, t.rnd, t.sh, t.lsh, dstf);
+            stage1_call<LOG2N, SF, true>(in, g, x1, tl, 1, t.sf, t.w, t.rnd, t.sh, t.lsh, dstf);
+        }
+        __syncwarp();  // `in` is consumed, g is complete
+        if (it + stride < n_items) {
+            bool v1;
+            lane_tb<LOG2N>(a, it + stride, lane, v1);
+            const uint4 dn = ring[32 * (k ^ 1)];
+            tile_issue<LOG2N>(lane, a.coeffs + (size_t)dn.z * 16, v1, in_base);
+            if (it + 2 * stride < n_items) {  // slot k is free: its descriptor sits in `t`
+                bool v2;
+                const int tb2 = lane_tb<LOG2N>(a, it + 2 * stride, lane, v2);
+                if (v2) copy16_async(&ring[32 * k], &a.tus[tb2]);
+            }
+        }
+        cp_async_commit();
+        if (t.valid && !is_special) {
+            stage2_call<LOG2N>(g, tl, t.dst + (size_t)tl * t.stride, t.rnd2, t.sh2, dstf);
+            stage2_call<LOG2N>(g, tl + L::TPB, t.dst + (size_t)(tl + L::TPB) * t.stride, t.rnd2, t.sh2, dstf);
+        }
+    }
+    cp_async_wait<0>();
     __syncwarp();
-    phase_stage2<LOG2N>(lane, t, buf);
 }
 
-// Persistent warps: warp w handles work items w, w + W, w + 2W, ... of the size-sorted
-// list (all warps therefore sit in the same size bin at any time -> one code path hot in
-// the instruction cache).  Three-deep software pipeline per warp:
-//   descriptor of item k+2 (LDG)  |  tile of item k+1 (cp.async into the other buffer)
-//   |  transform of item k
-// so both dependent global-memory latencies of an item are hidden behind arithmetic.
+// Persistent warps walk the size-sorted work-item list bin by bin (all warps therefore
+// run the same size path at any time -> one code path hot in the instruction cache).
 template <int SF>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) residual_kernel(const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int stride = gridDim.x * kWarpsPerCta, n_items = a.first_item[4];
-    int it = blockIdx.x * kWarpsPerCta + warp;
-    if (it >= n_items) return;
-    unsigned char *buf = smem + warp * (2 * kWarpSmemBytes);
-    int b = 0;
-
-    bool v_cur, v_next = false;
-    const uint4 d_cur = fetch_desc(a, it, lane, v_cur);
-    TbParams t_cur = make_params(a, d_cur, v_cur);
-    issue_tile(a, it, lane, t_cur, buf);
-    cp_async_commit();
-    int it_next = it + stride;
-    uint4 d_next = make_uint4(0, 0, 0, 0);
-    if (it_next < n_items) d_next = fetch_desc(a, it_next, lane, v_next);
-
-    while (true) {
-        const bool has_next = it_next < n_items;
-        TbParams t_next = t_cur;
-        if (has_next) {
-            t_next = make_params(a, d_next, v_next);
-            issue_tile(a, it_next, lane, t_next, buf + (b ^ 1) * kWarpSmemBytes);
-        }
-        cp_async_commit();
-        const int it_nn = it_next + stride;
-        bool v_nn = false;
-        uint4 d_nn = make_uint4(0, 0, 0, 0);
-        if (it_nn < n_items) d_nn = fetch_desc(a, it_nn, lane, v_nn);
-
-        cp_async_wait<1>();  // the current tile has landed (the newest group may be in flight)
-        __syncwarp();
-        unsigned char *cur = buf + b * kWarpSmemBytes;
-        switch (bin_of(a, it)) {
-            case 0: compute_item<5, SF>(lane, t_cur, cur); break;
-            case 1: compute_item<4, SF>(lane, t_cur, cur); break;
-            case 2: compute_item<3, SF>(lane, t_cur, cur); break;
-            default: compute_item<2, SF>(lane, t_cur, cur); break;
-        }
-        __syncwarp();
-        if (!has_next) break;
-        it = it_next;
-        t_cur = t_next;
-        it_next = it_nn;
-        d_next = d_nn;
-        v_next = v_nn;
-        b ^= 1;
-    }
+    const int stride = gridDim.x * kWarpsPerCta;
+    const int gw = blockIdx.x * kWarpsPerCta + warp;
+    unsigned char *wbase = smem + warp * kWarpBytes;
+    run_bin<5, SF>(a, gw, stride, lane, wbase);
+    run_bin<4, SF>(a, gw, stride, lane, wbase);
+    run_bin<3, SF>(a, gw, stride, lane, wbase);
+    run_bin<2, SF>(a, gw, stride, lane, wbase);
 }
 
 // ---- auxiliary, non-hot kernels ------------------------------------------------------

@@ -369,20 +369,23 @@ P265_HD int dequant(int lv, int m, const TbParams &t) {
 }
 
 // ------------------------------------------------------------------ shared layout
+// Per warp: one coefficient tile buffer `in` and one stage-1 output buffer `g`, the same
+// size (N*N int16 = N rows of N/2 packed words), plus one pad row per TB so that the TBs
+// of a warp start in different banks.  `g` rows are XOR-swizzled in 16-byte chunks so that
+// both the 16-bit column stores of stage 1 and the 128-bit row loads of stage 2 are free
+// of bank conflicts without padding.
 template <int LOG2N>
 struct Layout {
     static constexpr int N = 1 << LOG2N;
     static constexpr int TPB = N / 2;         // lanes per TB
     static constexpr int TBS = 64 / N;        // TBs per warp item
-    // input tile: row-major int16 [y][x] + one pad row (bank spreading across TBs)
-    static constexpr int IN_BYTES = N * N * 2 + 2 * N;
-    // stage-1 output: N rows of N/2 packed words (slot order) + row padding
-    static constexpr int G_ROW = (N == 32) ? 20 : (N == 16) ? 12 : (N == 8) ? 4 : 2;  // words
-    static constexpr int G_BYTES = N * G_ROW * 4 + ((N == 32) ? 64 : (N == 16) ? 32 : (N == 8) ? 64 : 8);
-    static constexpr int TB_BYTES = IN_BYTES > G_BYTES ? IN_BYTES : G_BYTES;  // g aliases in
+    static constexpr int ROW_BYTES = N * 2;   // tile row: N int16; g row: N/2 packed words
+    static constexpr int TB_BYTES = N * N * 2 + 2 * N;
     static constexpr int WARP_BYTES = TB_BYTES * TBS;
+    // 16-byte chunk swizzle of g row y (chunks per row: N/8)
+    static P265_HD constexpr int swz(int y) { return N == 32 ? ((y >> 1) & 3) : (N == 16 ? ((y >> 2) & 1) : 0); }
 };
-constexpr int kWarpSmemBytes = 5376;  // >= Layout<5>::WARP_BYTES, multiple of 128
+constexpr int kWarpSmemBytes = 4224;  // == Layout<5>::WARP_BYTES, multiple of 128
 static_assert(Layout<5>::WARP_BYTES <= kWarpSmemBytes, "smem");
 static_assert(Layout<4>::WARP_BYTES <= kWarpSmemBytes, "smem");
 static_assert(Layout<3>::WARP_BYTES <= kWarpSmemBytes, "smem");
@@ -391,39 +394,41 @@ static_assert(Layout<2>::WARP_BYTES <= kWarpSmemBytes, "smem");
 P265_HD int lds_s16(const unsigned char *smem, int byte_off) {
     return (int)*reinterpret_cast<const int16_t *>(smem + byte_off);
 }
+// int32 -> int16 with signed saturation (one I2IP against zero)
+P265_HD uint16_t sat_s16(int v) { return (uint16_t)(pack_sat(v, 0) & 0xffff); }
 
 // ---------------------------------------------------------------- phase 0: global -> smem
 // Each lane copies its share (two columns' worth = 4N bytes) of its TB, 16 bytes at a
 // time, fully coalesced across the TB's lanes.  Asynchronous on the device: the caller
 // commits / waits the cp.async group and __syncwarp()s before anyone reads the tile.
 template <int LOG2N>
-P265_HD void tile_issue(int lane, const TbParams &t, unsigned char *wsmem) {
+P265_HD void tile_issue(int lane, const int16_t *src, bool valid, unsigned char *in_base) {
     using L = Layout<LOG2N>;
     constexpr int N = L::N;
     const int tb = lane / L::TPB, tl = lane % L::TPB;
-    if (!t.valid) return;
-    unsigned char *in = wsmem + tb * L::TB_BYTES;
+    if (!valid) return;
+    unsigned char *in = in_base + tb * L::TB_BYTES;
     P265_UNROLL
     for (int i = 0; i < N / 4; i++) {
         const int chunk = tl + i * L::TPB;  // 16-byte chunk index inside the TB
         if (N >= 8) {
-            copy16_async(in + chunk * 16, t.src + chunk * 8);
+            copy16_async(in + chunk * 16, src + chunk * 8);
         } else {  // 4x4 tiles are only 8-byte aligned in shared memory (40-byte pitch)
-            copy8_async(in + chunk * 16, t.src + chunk * 8);
-            copy8_async(in + chunk * 16 + 8, t.src + chunk * 8 + 4);
+            copy8_async(in + chunk * 16, src + chunk * 8);
+            copy8_async(in + chunk * 16 + 8, src + chunk * 8 + 4);
         }
     }
 }
 
 // transform-skip (8.6.4.2, tsShift = 7) / transquant-bypass (8.6.2) TBs: element-wise,
-// straight from the tile to the plane.  Runs before stage 1 overwrites the tile.
+// straight from the tile to the plane.
 template <int LOG2N>
-P265_HD void phase_special(int lane, const TbParams &t, const unsigned char *wsmem) {
+P265_HD void phase_special(int lane, const TbParams &t, const unsigned char *in_base) {
     using L = Layout<LOG2N>;
     constexpr int N = L::N;
     const int tb = lane / L::TPB, tl = lane % L::TPB;
     if (!t.valid || !(t.flags & (P265_TU_SKIP | P265_TU_BYPASS))) return;
-    const unsigned char *in = wsmem + tb * L::TB_BYTES;
+    const unsigned char *in = in_base + tb * L::TB_BYTES;
     for (int i = 0; i < N / 4; i++) {
         const int chunk = tl + i * L::TPB;
         uint32_t w[4];
@@ -467,8 +472,7 @@ P265_HD void phase_special(int lane, const TbParams &t, const unsigned char *wsm
     }
 }
 
-// ------------------------------------------- phase 1a: smem -> packed, dequantised operands
-// Scaling-factor access modes of the gather.
+// Scaling-factor access modes of stage 1.
 //   SF_NONE        flat m = 16 (scaling_list_enabled_flag == 0, scaling.py:32-33)
 //   SF_GENERAL     m[y][x] read per coefficient from the 4064-byte table (any table)
 //   SF_REPLICATED  the table obeys 7.4.5: 16x16 / 32x32 entries are the 8x8 list
@@ -477,141 +481,110 @@ P265_HD void phase_special(int lane, const TbParams &t, const unsigned char *wsm
 //                  levelScale -- no per-coefficient load or multiply is left.
 enum { SF_NONE = 0, SF_GENERAL = 1, SF_REPLICATED = 2 };
 
-// SLOW must be chosen warp-uniformly: true when any lane of the warp has a TB with
-// per >= bdShift (left-shift dequantisation, only reachable at very high qP on small TBs).
+// ------------------------------------------------- stage 1: ONE column of one TB
+// Dequantise column x of the tile (8.6.3), inverse-transform it (8.6.4.2, vertical pass),
+// clip16((e + 64) >> 7) and store the N results as the `half`-th 16-bit half of slot
+// `tl` in the rows of g.  Called twice per lane and item (the two columns that form one
+// packed operand of stage 2); kept out of line on the device so that both calls share one
+// copy of the code (instruction-cache footprint) and one register allocation.
+// SLOW is chosen warp-uniformly: some TB of the warp has per >= bdShift (left-shift
+// dequantisation, only reachable at very high qP on small TBs).
 template <int LOG2N, int SF, bool SLOW>
-P265_HD void phase_gather(int lane, const TbParams &t, const unsigned char *wsmem,
-                          int (&p)[2][(1 << LOG2N) / 2]) {
+P265_HD void stage1_column(const unsigned char *in, unsigned char *g, int x, int tl, int half, const uint8_t *sf,
+                           int w, int rnd, int sh, int lsh, int dst_flag) {
     using L = Layout<LOG2N>;
     constexpr int N = L::N;
-    constexpr int K = N < 8 ? N : 8;      // distinct factors per column (SF_REPLICATED)
-    constexpr int REP = N / K;            // 1, 1, 2, 4
-    const int tb = lane / L::TPB, tl = lane % L::TPB;
-    const unsigned char *in = wsmem + tb * L::TB_BYTES;
-    const int x[2] = {slot_index_rt(N, tl, 0), slot_index_rt(N, tl, 1)};
-    const uint8_t *sf = (SF != SF_NONE && t.sf) ? t.sf : nullptr;
-    if (SF != SF_NONE && !sf) {
-        // invalid lane, or a PRESCALED / bypass-only TB inside a scaling-list batch: keep
-        // the table loads in bounds by running the flat formula (w already set up)
-        P265_UNROLL
-        for (int c = 0; c < 2; c++) {
-            P265_UNROLL
-            for (int s = 0; s < N / 2; s++) {
-                const int e0 = slot_index(N, s, 0) * N + x[c], e1 = slot_index(N, s, 1) * N + x[c];
-                p[c][s] = pack_sat(dequant(lds_s16(in, e0 * 2), t.w, t), dequant(lds_s16(in, e1 * 2), t.w, t));
-            }
-        }
-        return;
-    }
-    int mw[2][K];
-    int dc[2] = {0, 0};
+    constexpr int K = N < 8 ? N : 8;  // distinct factors per column (SF_REPLICATED)
+    constexpr int REP = N / K;        // 1, 1, 2, 4
+    if (SF != SF_NONE && sf == nullptr) return;  // lane without a TB (tail of a bin)
+    TbParams t;                       // only the dequantisation fields are used
+    t.rnd = rnd; t.sh = sh; t.lsh = lsh;
+    int mw[K];
+    int dc = 0;
     if (SF == SF_REPLICATED) {
         P265_UNROLL
-        for (int c = 0; c < 2; c++) {
-            P265_UNROLL
-            for (int k = 0; k < K; k++) mw[c][k] = (int)sf[(k * REP + (REP > 1 ? 1 : 0)) * N + x[c]] * t.w;
-            dc[c] = (REP > 1 && x[c] == 0) ? (int)sf[0] * t.w : mw[c][0];
-        }
+        for (int k = 0; k < K; k++) mw[k] = (int)sf[(k * REP + (REP > 1 ? 1 : 0)) * N + x] * w;
+        dc = (REP > 1 && x == 0) ? (int)sf[0] * w : mw[0];
     }
+    int p[1][N / 2];
     P265_UNROLL
-    for (int c = 0; c < 2; c++) {
-        P265_UNROLL
-        for (int s = 0; s < N / 2; s++) {
-            const int y0 = slot_index(N, s, 0), y1 = slot_index(N, s, 1);
-            const int e0 = y0 * N + x[c], e1 = y1 * N + x[c];
-            const int l0 = lds_s16(in, e0 * 2), l1 = lds_s16(in, e1 * 2);
-            int m0 = t.w, m1 = t.w;
-            if (SF == SF_GENERAL) {
-                m0 *= (int)sf[e0];
-                m1 *= (int)sf[e1];
-            } else if (SF == SF_REPLICATED) {
-                m0 = y0 == 0 ? dc[c] : mw[c][y0 / REP];
-                m1 = mw[c][y1 / REP];
-            }
-            if (!SLOW) p[c][s] = pack_sat(dequant_fast(l0, m0, t), dequant_fast(l1, m1, t));
-            else p[c][s] = pack_sat(dequant(l0, m0, t), dequant(l1, m1, t));
+    for (int s = 0; s < N / 2; s++) {
+        const int y0 = slot_index(N, s, 0), y1 = slot_index(N, s, 1);
+        const int e0 = y0 * N + x, e1 = y1 * N + x;
+        const int l0 = lds_s16(in, e0 * 2), l1 = lds_s16(in, e1 * 2);
+        int m0 = w, m1 = w;
+        if (SF == SF_GENERAL) {
+            m0 *= (int)sf[e0];
+            m1 *= (int)sf[e1];
+        } else if (SF == SF_REPLICATED) {
+            m0 = y0 == 0 ? dc : mw[y0 / REP];
+            m1 = mw[y1 / REP];
         }
+        if (!SLOW) p[0][s] = pack_sat(dequant_fast(l0, m0, t), dequant_fast(l1, m1, t));
+        else p[0][s] = pack_sat(dequant(l0, m0, t), dequant(l1, m1, t));
     }
+    int e[1][N];
+    if (N == 4 && dst_flag) {
+        int p4[1][2] = {{p[0][0], p[0][1]}};
+        int e4[1][4];
+        dst4<1>(p4, 64, e4);
+        P265_UNROLL
+        for (int i = 0; i < 4; i++) e[0][i] = e4[0][i];
+    } else {
+        Idct<N, 1>::run(p, 64, e);
+    }
+    // g[y][slot tl].half = clip16((e[y] + 64) >> 7); chunk index XOR-swizzled per row
+    unsigned char *base[4];
+    P265_UNROLL
+    for (int q = 0; q < 4; q++) base[q] = g + ((((tl >> 2) ^ q) << 4) | ((tl & 3) << 2) | (half << 1));
+    P265_UNROLL
+    for (int y = 0; y < N; y++)
+        *reinterpret_cast<uint16_t *>(base[L::swz(y)] + y * L::ROW_BYTES) = sat_s16(e[0][y] >> 7);
 }
 
-// ------------------------------------------- phase 1b: column transforms -> g (smem)
+// ------------------------------------------------- stage 2: ONE row of one TB
+// Horizontal pass (8.6.4.2) over row `row` of g, final bdShift rounding (8.6.2), int16
+// saturation and the 2N-byte row store into the residual plane.
 template <int LOG2N>
-P265_HD void phase_stage1(int lane, const TbParams &t, unsigned char *wsmem, const int (&p)[2][(1 << LOG2N) / 2]) {
+P265_HD void stage2_row(const unsigned char *g, int row, int16_t *dst, int rnd2, int sh2, int dst_flag) {
     using L = Layout<LOG2N>;
     constexpr int N = L::N;
-    const int tb = lane / L::TPB, tl = lane % L::TPB;
-    uint32_t *g = reinterpret_cast<uint32_t *>(wsmem + tb * L::TB_BYTES);
-    int e[2][N];
-    if (N == 4 && (t.flags & P265_TU_DST)) {
-        int p4[2][2] = {{p[0][0], p[0][1]}, {p[1][0], p[1][1]}};
-        int e4[2][4];
-        dst4<2>(p4, 64, e4);
+    const unsigned char *grow = g + row * L::ROW_BYTES;
+    const int sw = N == 32 ? ((row >> 1) & 3) : (N == 16 ? ((row >> 2) & 1) : 0);
+    int p[1][N / 2];
+    if (N >= 8) {
         P265_UNROLL
-        for (int i = 0; i < 4; i++) {
-            e[0][i] = e4[0][i];
-            e[1][i] = e4[1][i];
+        for (int q = 0; q < N / 8; q++) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(grow + ((q ^ sw) << 4));
+            p[0][4 * q + 0] = (int)v.x;
+            p[0][4 * q + 1] = (int)v.y;
+            p[0][4 * q + 2] = (int)v.z;
+            p[0][4 * q + 3] = (int)v.w;
         }
     } else {
-        Idct<N, 2>::run(p, 64, e);
+        const uint2 v = *reinterpret_cast<const uint2 *>(grow);
+        p[0][0] = (int)v.x;
+        p[0][1] = (int)v.y;
     }
-    // g[y][slot tl] = (clip16((e[x_lo][y] + 64) >> 7), clip16((e[x_hi][y] + 64) >> 7))
-    P265_UNROLL
-    for (int y = 0; y < N; y++) g[y * L::G_ROW + tl] = (uint32_t)pack_sat(e[0][y] >> 7, e[1][y] >> 7);
-}
-
-// ------------------------------------------- phase 2: row transforms -> residual plane
-template <int LOG2N>
-P265_HD void phase_stage2(int lane, const TbParams &t, const unsigned char *wsmem) {
-    using L = Layout<LOG2N>;
-    constexpr int N = L::N;
-    const int tb = lane / L::TPB, tl = lane % L::TPB;
-    if (!t.valid || (t.flags & (P265_TU_SKIP | P265_TU_BYPASS))) return;
-    const uint32_t *g = reinterpret_cast<const uint32_t *>(wsmem + tb * L::TB_BYTES);
-    int p[2][N / 2];
-    P265_UNROLL
-    for (int c = 0; c < 2; c++) {
-        const uint32_t *row = g + (tl + c * L::TPB) * L::G_ROW;
-        if (N >= 8) {
-            P265_UNROLL
-            for (int q = 0; q < N / 8; q++) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(row + 4 * q);
-                p[c][4 * q + 0] = (int)v.x;
-                p[c][4 * q + 1] = (int)v.y;
-                p[c][4 * q + 2] = (int)v.z;
-                p[c][4 * q + 3] = (int)v.w;
-            }
-        } else {
-            const uint2 v = *reinterpret_cast<const uint2 *>(row);
-            p[c][0] = (int)v.x;
-            p[c][1] = (int)v.y;
-        }
-    }
-    int r[2][N];
-    if (N == 4 && (t.flags & P265_TU_DST)) {
-        int p4[2][2] = {{p[0][0], p[0][1]}, {p[1][0], p[1][1]}};
-        int r4[2][4];
-        dst4<2>(p4, t.rnd2, r4);
+    int r[1][N];
+    if (N == 4 && dst_flag) {
+        int p4[1][2] = {{p[0][0], p[0][1]}};
+        int r4[1][4];
+        dst4<1>(p4, rnd2, r4);
         P265_UNROLL
-        for (int i = 0; i < 4; i++) {
-            r[0][i] = r4[0][i];
-            r[1][i] = r4[1][i];
-        }
+        for (int i = 0; i < 4; i++) r[0][i] = r4[0][i];
     } else {
-        Idct<N, 2>::run(p, t.rnd2, r);
+        Idct<N, 1>::run(p, rnd2, r);
     }
+    uint32_t w[N / 2];
     P265_UNROLL
-    for (int c = 0; c < 2; c++) {
-        int16_t *dst = t.dst + (size_t)(tl + c * L::TPB) * t.stride;
-        uint32_t w[N / 2];
+    for (int i = 0; i < N / 2; i++) w[i] = (uint32_t)pack_sat(r[0][2 * i] >> sh2, r[0][2 * i + 1] >> sh2);
+    if (N >= 8) {
         P265_UNROLL
-        for (int i = 0; i < N / 2; i++) w[i] = (uint32_t)pack_sat(r[c][2 * i] >> t.sh2, r[c][2 * i + 1] >> t.sh2);
-        if (N >= 8) {
-            P265_UNROLL
-            for (int q = 0; q < N / 8; q++)
-                *reinterpret_cast<uint4 *>(dst + 8 * q) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-        } else {
-            *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
-        }
+        for (int q = 0; q < N / 8; q++)
+            *reinterpret_cast<uint4 *>(dst + 8 * q) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    } else {
+        *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
     }
 }
 

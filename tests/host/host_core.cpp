@@ -10,33 +10,52 @@
 
 using namespace p265;
 
-template <int LOG2N>
-static void run_item(const KernelArgs &a, int item) {
+template <int LOG2N, int SF>
+static void run_item_sf(const KernelArgs &a, int item) {
     using L = Layout<LOG2N>;
-    alignas(16) unsigned char smem[kWarpSmemBytes];
-    std::memset(smem, 0xA5, sizeof smem);
+    constexpr int N = L::N;
+    alignas(16) unsigned char in_buf[kWarpSmemBytes], g_buf[kWarpSmemBytes];
+    std::memset(in_buf, 0xA5, sizeof in_buf);
+    std::memset(g_buf, 0x5A, sizeof g_buf);
     TbParams t[32];
+    bool slow = false;
     for (int lane = 0; lane < 32; lane++) {
         bool valid;
         int tb = lane_tb<LOG2N>(a, item, lane, valid);
         t[lane] = make_params(a, tb, valid);
+        slow |= t[lane].lsh != 0;
+        tile_issue<LOG2N>(lane, t[lane].src, valid, in_buf);
     }
-    for (int lane = 0; lane < 32; lane++) tile_issue<LOG2N>(lane, t[lane], smem);
-    for (int lane = 0; lane < 32; lane++) phase_special<LOG2N>(lane, t[lane], smem);
-    static int p[32][2][L::N / 2];
-    bool slow = false;
-    for (int lane = 0; lane < 32; lane++) slow |= t[lane].lsh != 0;
-    const int sf = !a.sf ? SF_NONE : (a.sf_replicated ? SF_REPLICATED : SF_GENERAL);
+    for (int lane = 0; lane < 32; lane++) phase_special<LOG2N>(lane, t[lane], in_buf);
     for (int lane = 0; lane < 32; lane++) {
-        if (sf == SF_NONE && slow) phase_gather<LOG2N, SF_NONE, true>(lane, t[lane], smem, p[lane]);
-        else if (sf == SF_NONE) phase_gather<LOG2N, SF_NONE, false>(lane, t[lane], smem, p[lane]);
-        else if (sf == SF_GENERAL && slow) phase_gather<LOG2N, SF_GENERAL, true>(lane, t[lane], smem, p[lane]);
-        else if (sf == SF_GENERAL) phase_gather<LOG2N, SF_GENERAL, false>(lane, t[lane], smem, p[lane]);
-        else if (slow) phase_gather<LOG2N, SF_REPLICATED, true>(lane, t[lane], smem, p[lane]);
-        else phase_gather<LOG2N, SF_REPLICATED, false>(lane, t[lane], smem, p[lane]);
+        const int tb_l = lane / L::TPB, tl = lane % L::TPB;
+        const unsigned char *in = in_buf + tb_l * L::TB_BYTES;
+        unsigned char *g = g_buf + tb_l * L::TB_BYTES;
+        const TbParams &q = t[lane];
+        for (int half = 0; half < 2; half++) {
+            const int x = slot_index_rt(N, tl, half);
+            const int dstf = q.flags & P265_TU_DST;
+            if (slow) stage1_column<LOG2N, SF, true>(in, g, x, tl, half, q.sf, q.w, q.rnd, q.sh, q.lsh, dstf);
+            else stage1_column<LOG2N, SF, false>(in, g, x, tl, half, q.sf, q.w, q.rnd, q.sh, 0, dstf);
+        }
     }
-    for (int lane = 0; lane < 32; lane++) phase_stage1<LOG2N>(lane, t[lane], smem, p[lane]);
-    for (int lane = 0; lane < 32; lane++) phase_stage2<LOG2N>(lane, t[lane], smem);
+    for (int lane = 0; lane < 32; lane++) {
+        const int tb_l = lane / L::TPB, tl = lane % L::TPB;
+        const unsigned char *g = g_buf + tb_l * L::TB_BYTES;
+        const TbParams &q = t[lane];
+        if (!q.valid || (q.flags & (P265_TU_SKIP | P265_TU_BYPASS))) continue;
+        for (int c = 0; c < 2; c++) {
+            const int row = tl + c * L::TPB;
+            stage2_row<LOG2N>(g, row, q.dst + (size_t)row * q.stride, q.rnd2, q.sh2, q.flags & P265_TU_DST);
+        }
+    }
+}
+
+template <int LOG2N>
+static void run_item(const KernelArgs &a, int item) {
+    if (!a.sf) run_item_sf<LOG2N, SF_NONE>(a, item);
+    else if (a.sf_replicated) run_item_sf<LOG2N, SF_REPLICATED>(a, item);
+    else run_item_sf<LOG2N, SF_GENERAL>(a, item);
 }
 
 extern "C" int host_residual_batch(const p265_tu_desc *tus, const int32_t bin_counts[4], const int16_t *coeffs,

@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""Kernel-only timing of the residual / SAO kernels on device-resident synthetic inputs.
+Quick A/B tool for tuning runs (not the contract benchmark -- that is bench.py).
+
+    python tools/kbench.py [--pics 8] [--reps 20]
+"""
+import argparse, os, sys, json
+import numpy as np
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+import torch
+from p265_b200 import synth
+from p265_b200.engine import Engine
+from p265_b200.picture import ResidualBatch
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--pics", type=int, default=8)
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--tag", default="")
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    eng = Engine(0, stream.cuda_stream)
+
+    def to_dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+
+    def time_residual(batch, label, force_general=False):
+        d_tus, d_co = to_dev(batch.tus), to_dev(batch.coeffs)
+        d_sf = to_dev(batch.scaling_factor) if batch.scaling_factor is not None else None
+        d_out = torch.empty(batch.geom.total_elems() * 2, dtype=torch.uint8, device=dev)
+        bins = batch.bin_counts()
+        rep = bool(batch.sf_replicated) and not force_general
+
+        def run():
+            eng.residual_dev(d_tus.data_ptr(), bins, d_co.data_ptr(), d_sf.data_ptr() if d_sf is not None else None,
+                             batch.geom, d_out.data_ptr(), zero_fill=False, sf_replicated=rep)
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(args.reps):
+                run()
+            e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / args.reps
+        samples = batch.samples()
+        gbs = (4 * samples + 16 * len(batch.tus)) / (ms * 1e-3) / 1e9
+        print("%-34s %8.4f ms  %7.1f GB/s alg (%.3f of 6555)  %6.2f Gsample/s" %
+              (label, ms, gbs, gbs / 6554.9, samples / (ms * 1e-3) / 1e9), flush=True)
+        return ms
+
+    full = synth.residual_batch("4k10", n_pics=args.pics, n_unique=min(2, args.pics))
+    time_residual(full, "4k10 mix, SF replicated")
+    time_residual(full, "4k10 mix, SF general", force_general=True)
+    flat = ResidualBatch(full.geom, full.tus, full.coeffs, None, covers_all=True)
+    time_residual(flat, "4k10 mix, flat lists")
+    for l2 in (5, 4, 3, 2):
+        sel = full.tus[full.tus["log2n"] == l2]
+        for sf, name in ((full.scaling_factor, "SF repl"), (None, "flat")):
+            b = ResidualBatch(full.geom, np.ascontiguousarray(sel), full.coeffs, sf, covers_all=True)
+            time_residual(b, "only %2dx%-2d (%7d TBs) %s" % (1 << l2, 1 << l2, len(sel), name))
+
+    geom, rec, params = synth.sao_batch(3840, 2160, 10, n_pics=args.pics, n_unique=min(2, args.pics))
+    d_rec, d_par = to_dev(rec), to_dev(params)
+    d_o = torch.empty_like(d_rec)
+    for label, mod in (("SAO config 4 mix", None), ("SAO all off (copy)", 0), ("SAO all band", 1), ("SAO all edge", 2)):
+        p = params.copy()
+        if mod is not None:
+            p["type"][:] = mod
+            if mod:
+                p["offset_val"][:] = (3, 1, -1, -3)
+        d_par = to_dev(p)
+        for _ in range(3):
+            eng.sao_dev(d_rec.data_ptr(), d_o.data_ptr(), geom, 6, d_par.data_ptr())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(args.reps):
+                eng.sao_dev(d_rec.data_ptr(), d_o.data_ptr(), geom, 6, d_par.data_ptr())
+            e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / args.reps
+        b = 4 * geom.n_pics * (geom.width * geom.height * 3 // 2)
+        print("%-34s %8.4f ms  %7.1f GB/s alg (%.3f of 6555)" % (label, ms, b / (ms * 1e-3) / 1e9,
+                                                                 b / (ms * 1e-3) / 1e9 / 6554.9), flush=True)
+
+
+if __name__ == "__main__":
+    main()
