@@ -3,10 +3,13 @@
 // parameters sao.Sao.parse() produces (sao.py:15-136).  The reference has no SAO filter
 // at all; parity is against the spec oracle.
 //
-// One warp per (picture, component, CTB).  A lane owns an 8-sample-wide strip of R rows
-// and walks it with a three-row window kept in registers: 16-byte (10-bit) / 8-byte
-// (8-bit) coalesced loads and stores, horizontal neighbours through warp shuffles, no
-// shared memory.  All arithmetic is packed 2 x 16 bit in one 32-bit register:
+// One warp per tile of (up to) 1024 samples of one CTB: 64x16 for a 64x64 luma CTB (four
+// tiles per CTB), the whole CTB for 32x32 and smaller.  A lane owns an 8-sample-wide,
+// R <= 4 rows tall strip; all R + 2 row loads of the strip (16 bytes at 10 bits, 8 bytes
+// at 8 bits, coalesced) are issued before the first use, so every warp keeps six
+// independent loads in flight -- the kernel is bandwidth-, not latency-limited.
+// Horizontal neighbours come through warp shuffles, vertical ones from the lane's own
+// registers; no shared memory.  All arithmetic is packed 2 x 16 bit in one 32-bit register:
 //   sign(c - n)      : (c + 0x4000_4000 - n) clamped to [0x3fff, 0x4001] per half-word
 //                      (VIMNMX.S16x2 twice)
 //   SaoOffsetVal[..] : byte-permute LUT (PRMT with sign replication) over the CTB's four
@@ -32,8 +35,8 @@ struct SaoArgs {
     int32_t bit_depth_y, bit_depth_c;
     int32_t ctb_log2, ctbs_w, ctbs_h, n_pics;
     int32_t ctbs;        // ctbs_w * ctbs_h
-    int32_t luma_items;  // n_pics * ctbs
-    int32_t items;       // 3 * luma_items
+    int32_t tiles_y, tiles_c;  // 1024-sample tiles per luma / chroma CTB
+    int32_t items;       // n_pics * ctbs * (tiles_y + 2 * tiles_c)
 };
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
@@ -189,8 +192,9 @@ __device__ __forceinline__ void edge_row(const Row &P, const Row &C, const Row &
     }
 }
 
+constexpr int kMaxRows = 4;  // rows per lane
 struct Geo {
-    int y0, vh, row0, rows;  // CTB top row, valid rows, lane's first local row, rows per lane
+    int y0, vh, row0, rows;  // CTB top row, valid rows, lane's first row inside the CTB, rows per lane
     int h;                   // plane height
     int64_t stride;
     bool active;             // lane covers valid columns
@@ -201,56 +205,48 @@ __device__ __forceinline__ void edge_strip(const T *in, T *out, const Geo &g, co
                                            const ItemConst &k, const uint8_t *nf_row, int nf_stride, int nf_shift) {
     // `in` / `out` point at (row y0, lane's first column)
     constexpr bool HALO = CLS != 1;
-    constexpr int CH = 4;  // rows fetched per batch: CH independent 16-byte loads in flight per lane
-    Row P, C;
     auto rowptr = [&](int ly) {
         int y = g.y0 + ly;
         y = y < 0 ? 0 : (y >= g.h ? g.h - 1 : y);
         return in + (int64_t)(y - g.y0) * g.stride;
     };
-    row_issue<T, HALO>(P, rowptr(g.row0 - 1), s);
-    row_issue<T, HALO>(C, rowptr(g.row0), s);
-    Row Nn[CH];
+    // rows row0-1 .. row0+rows of the CTB: every load is issued before the first use
+    Row rw[kMaxRows + 2];
 #pragma unroll
-    for (int j = 0; j < CH; j++) row_issue<T, HALO>(Nn[j], rowptr(g.row0 + 1 + j), s);
-    row_finish<HALO>(P, s);
-    row_finish<HALO>(C, s);
+    for (int j = 0; j < kMaxRows + 2; j++)
+        if (j < g.rows + 2) row_issue<T, HALO>(rw[j], rowptr(g.row0 - 1 + j), s);
+#pragma unroll
+    for (int j = 0; j < kMaxRows + 2; j++)
+        if (j < g.rows + 2) row_finish<HALO>(rw[j], s);
     uint32_t mid[4];
     row_mask<CLS>(m, false, false, mid);
-    for (int r = 0; r < g.rows; r += CH) {
 #pragma unroll
-        for (int j = 0; j < CH; j++) {
-            if (r + j >= g.rows) break;  // warp-uniform
-            row_finish<HALO>(Nn[j], s);
-            const int ly = g.row0 + r + j;
-            const bool top = ly == 0, bot = ly == g.vh - 1;
-            uint32_t keep[4], o[4];
-            if (top || bot) row_mask<CLS>(m, top, bot, keep);
-            else {
+    for (int j = 0; j < kMaxRows; j++) {
+        if (j >= g.rows) break;  // warp-uniform
+        const int ly = g.row0 + j;
+        const bool top = ly == 0, bot = ly == g.vh - 1;
+        uint32_t keep[4], o[4];
+        if (top || bot) row_mask<CLS>(m, top, bot, keep);
+        else {
 #pragma unroll
-                for (int i = 0; i < 4; i++) keep[i] = mid[i];
-            }
-            if (NOFILT) {
-                const uint8_t *f = nf_row + (int64_t)(min(ly, g.vh - 1) >> nf_shift) * nf_stride;
-                if (nf_shift == 3) {
-                    if (f[0]) keep[0] = keep[1] = keep[2] = keep[3] = 0xffffffffu;
-                } else {
-                    if (f[0]) keep[0] = keep[1] = 0xffffffffu;
-                    if (f[1]) keep[2] = keep[3] = 0xffffffffu;
-                }
-            }
-            edge_row<CLS>(P, C, Nn[j], k, keep, o);
-            if (g.active && ly < g.vh) store8<T>(out + (int64_t)ly * g.stride, o);
-            P = C;
-            C = Nn[j];
-            // refill this slot with the row CH ahead (consumed in the next batch)
-            if (r + j + CH < g.rows) row_issue<T, HALO>(Nn[j], rowptr(ly + 1 + CH), s);
+            for (int i = 0; i < 4; i++) keep[i] = mid[i];
         }
+        if (NOFILT) {
+            const uint8_t *f = nf_row + (int64_t)(min(ly, g.vh - 1) >> nf_shift) * nf_stride;
+            if (nf_shift == 3) {
+                if (f[0]) keep[0] = keep[1] = keep[2] = keep[3] = 0xffffffffu;
+            } else {
+                if (f[0]) keep[0] = keep[1] = 0xffffffffu;
+                if (f[1]) keep[2] = keep[3] = 0xffffffffu;
+            }
+        }
+        edge_row<CLS>(rw[j], rw[j + 1], rw[j + 2], k, keep, o);
+        if (g.active && ly < g.vh) store8<T>(out + (int64_t)ly * g.stride, o);
     }
 }
 
 template <typename T, bool NOFILT>
-__device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int rx, int ry, int lane) {
+__device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int rx, int ry, int tile, int lane) {
     // field-by-field reads (a by-value copy indexed by `c` would live in local memory)
     const p265_sao_ctb *qp = &a.params[((int64_t)pic * a.ctbs_h + ry) * a.ctbs_w + rx];
     struct {
@@ -274,16 +270,18 @@ __device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int r
     const int vw = min(cs, w - x0);
     g.vh = min(cs, h - g.y0);
 
+    // tile = th rows of the CTB starting at row tile * th; lanes_w x lane_rows lanes, R rows each
     Strip s;
     s.lanes_w = max(cs >> 3, 1);
     const int lane_rows = 32 / s.lanes_w;
-    g.rows = max(1, cs / lane_rows);
+    const int th = min(cs, 1024 / cs);              // 16 (cs 64), 32, 16, 8
+    g.rows = max(1, th / lane_rows);                // 4, 4, 1, 1
     s.lx = lane % s.lanes_w;
     const int ly = lane / s.lanes_w;
-    g.row0 = ly * g.rows;
-    g.active = s.lx * 8 < vw && g.row0 < g.vh;
-    if (g.row0 >= cs) {  // lane has no rows at all (chroma of 16x16 CTBs): park it on row 0
-        g.row0 = 0;
+    g.row0 = tile * th + ly * g.rows;
+    g.active = s.lx * 8 < vw && g.row0 < g.vh && ly * g.rows < th;
+    if (ly * g.rows >= th) {  // lane has no rows at all (8x8 chroma CTBs): park it on the tile's first row
+        g.row0 = tile * th;
         g.active = false;
     }
     s.first_col = s.lx == 0;
@@ -318,29 +316,26 @@ __device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int r
         // off: copy; band: bandTable lookup (pool index = band - band_position, 4 = none)
         k.pool_lo = o1 | (o2 << 8) | (o3 << 16) | (o4 << 24);
         k.pool_hi = 0;
-        constexpr int CH = 4;
-        for (int r = 0; r < g.rows; r += CH) {
-            uint32_t wv[CH][4];
+        uint32_t wv[kMaxRows][4];
 #pragma unroll
-            for (int j = 0; j < CH; j++) {
-                const int lyr = g.row0 + r + j;
-                if (r + j < g.rows && g.active && lyr < g.vh) load8<T>(in + (int64_t)lyr * g.stride, wv[j]);
+        for (int j = 0; j < kMaxRows; j++) {
+            const int lyr = g.row0 + j;
+            if (j < g.rows && g.active && lyr < g.vh) load8<T>(in + (int64_t)lyr * g.stride, wv[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < kMaxRows; j++) {
+            const int lyr = g.row0 + j;
+            if (!(j < g.rows && g.active && lyr < g.vh)) continue;
+            uint32_t o[4];
+            bool skip[2] = {false, false};
+            if (NOFILT) {
+                const uint8_t *f = nf_row + (int64_t)(lyr >> nf_shift) * nf_stride;
+                skip[0] = f[0] != 0;
+                skip[1] = nf_shift == 3 ? skip[0] : (f[1] != 0);
             }
 #pragma unroll
-            for (int j = 0; j < CH; j++) {
-                const int lyr = g.row0 + r + j;
-                if (!(r + j < g.rows && g.active && lyr < g.vh)) continue;
-                uint32_t o[4];
-                bool skip[2] = {false, false};
-                if (NOFILT) {
-                    const uint8_t *f = nf_row + (int64_t)(lyr >> nf_shift) * nf_stride;
-                    skip[0] = f[0] != 0;
-                    skip[1] = nf_shift == 3 ? skip[0] : (f[1] != 0);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; i++) o[i] = (type == 1 && !skip[i >> 1]) ? band_word(wv[j][i], k) : wv[j][i];
-                store8<T>(out + (int64_t)lyr * g.stride, o);
-            }
+            for (int i = 0; i < 4; i++) o[i] = (type == 1 && !skip[i >> 1]) ? band_word(wv[j][i], k) : wv[j][i];
+            store8<T>(out + (int64_t)lyr * g.stride, o);
         }
         return;
     }
@@ -380,24 +375,27 @@ __device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int r
     }
 }
 
+// Work items: for every (picture, CTB) first the luma tiles (tiles_y of them), then one
+// Cb and one Cr item; all items cover (up to) 1024 samples, so warps are balanced.
 template <typename T, bool NOFILT>
 __global__ void __launch_bounds__(kSaoWarpsPerCta * 32) sao_kernel(const __grid_constant__ SaoArgs a) {
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * kSaoWarpsPerCta + (threadIdx.x >> 5);
     if (item >= a.items) return;
-    // luma CTBs first (4x the work of a chroma CTB) so the tail is made of small items
-    int c, rest;
-    if (item < a.luma_items) {
+    const int per_ctb = a.tiles_y + a.tiles_c * 2;
+    const int cb = item / per_ctb, sub = item - cb * per_ctb;
+    int c, tile;
+    if (sub < a.tiles_y) {
         c = 0;
-        rest = item;
+        tile = sub;
     } else {
-        const int j = item - a.luma_items;
-        c = 1 + (j & 1);
-        rest = j >> 1;
+        const int j = sub - a.tiles_y;
+        c = 1 + j / a.tiles_c;
+        tile = j - (c - 1) * a.tiles_c;
     }
-    const int pic = rest / a.ctbs, ctb = rest - pic * a.ctbs;
+    const int pic = cb / a.ctbs, ctb = cb - pic * a.ctbs;
     const int ry = ctb / a.ctbs_w, rx = ctb - ry * a.ctbs_w;
-    sao_item<T, NOFILT>(a, pic, c, rx, ry, lane);
+    sao_item<T, NOFILT>(a, pic, c, rx, ry, tile, lane);
 }
 
 int launch_sao(p265_ctx *ctx, const void *d_rec, void *d_out, const p265_pic_geom *g, int ctb_log2,
@@ -421,10 +419,12 @@ int launch_sao(p265_ctx *ctx, const void *d_rec, void *d_out, const p265_pic_geo
     a.ctbs_h = (g->height + ctb - 1) / ctb;
     a.n_pics = g->n_pics;
     a.ctbs = a.ctbs_w * a.ctbs_h;
-    const int64_t luma = (int64_t)a.ctbs * g->n_pics;
-    if (luma * 3 > INT32_MAX) return set_error(P265_EINVAL, "too many CTBs in one SAO batch");
-    a.luma_items = (int32_t)luma;
-    a.items = (int32_t)(luma * 3);
+    const int cs_c = ctb >> 1;
+    a.tiles_y = ctb / (ctb < 1024 / ctb ? ctb : 1024 / ctb);
+    a.tiles_c = cs_c / (cs_c < 1024 / cs_c ? cs_c : 1024 / cs_c);
+    const int64_t items = (int64_t)a.ctbs * g->n_pics * (a.tiles_y + 2 * a.tiles_c);
+    if (items > INT32_MAX) return set_error(P265_EINVAL, "too many CTBs in one SAO batch");
+    a.items = (int32_t)items;
     if (a.items == 0) return P265_OK;
     const int grid = (a.items + kSaoWarpsPerCta - 1) / kSaoWarpsPerCta;
     const bool wide = g->bit_depth_y > 8 || g->bit_depth_c > 8;

@@ -32,3 +32,18 @@ for i, r in enumerate(data):
     r.append(i)
 for r in sorted(data, key=lambda r: -int(r[idx["# Samples"]]))[:n]:
     print("%5s smp %8s exe  #%5d  %s" % (r[idx["# Samples"]], r[idx["Instructions Executed"]], r[-1], r[idx["Source"]][:90]))
+
+# per-stall-reason hot spots (optional 4th arg: stall column, e.g. stall_no_inst)
+if len(sys.argv) > 4:
+    col = sys.argv[4]
+    tot_c = sum(int(r[idx[col]] or 0) for r in data)
+    print("\n== %s: %d samples ==" % (col, tot_c))
+    # cluster by 64-instruction windows to see where in the code they sit
+    win = Counter()
+    for r in data:
+        win[r[-1] // 64] += int(r[idx[col]] or 0)
+    for w_, c in sorted(win.items()):
+        if c:
+            print("  sass #%5d-%5d : %5d  %s" % (w_ * 64, w_ * 64 + 63, c, "#" * (c * 200 // max(tot_c, 1))))
+    for r in sorted(data, key=lambda r: -int(r[idx[col]] or 0))[:15]:
+        print("%5s  #%5d  %s" % (r[idx[col]], r[-1], r[idx["Source"]][:80]))
