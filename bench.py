@@ -159,8 +159,11 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    # stream s -> GPU s mod G; each rank owns the streams 26510 + rank
-    res, sgeom, rec, params = make_workload(args.pics, 26510 + rank)
+    # stream s -> GPU s mod G: with G streams on G GPUs every rank owns
+    # exactly one synthetic stream (seed 26510 + s); per-GPU work is fixed -> weak scaling
+    from p265_b200 import partition
+    stream_id = partition.streams_of_rank(world, rank, world)[0]
+    res, sgeom, rec, params = make_workload(args.pics, 26510 + stream_id)
     stream = torch.cuda.Stream(device=dev)
     eng = Engine(local, stream.cuda_stream)
 
@@ -217,17 +220,14 @@ def run_gpu(args):
     ms_sao = timed(sao, args.steps) / args.steps
     clocks = sampler.stop()
 
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total_max = float(t.item())
+    ms_total_max = partition.max_over_ranks(ms_total, dev)
     pixels_step = PIC_W * PIC_H * args.pics * world
     value = pixels_step * args.steps / (ms_total_max * 1e-3) / 1e6
 
     # ---- end to end through the host API (pinned host buffers, copies timed) ----
     e2e_pics = min(args.pics, args.e2e_pics)
     res_h, sgeom_h, rec_h, params_h = (res, sgeom, rec, params) if e2e_pics == args.pics else \
-        make_workload(e2e_pics, 26510 + rank)
+        make_workload(e2e_pics, 26510 + stream_id)
     eng2 = Engine(local)
 
     def pin(a):
@@ -262,10 +262,7 @@ def run_gpu(args):
         e2e_step()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = PIC_W * PIC_H * e2e_pics * world * e2e_steps / float(t.item()) / 1e6
+    e2e_value = PIC_W * PIC_H * e2e_pics * world * e2e_steps / partition.max_over_ranks(dt, dev) / 1e6
     h2d = res_h.tus.nbytes + res_h.coeffs.nbytes + rec_h.nbytes + params_h.nbytes + \
         (res_h.scaling_factor.nbytes if res_h.scaling_factor is not None else 0)
     d2h = h_ro.nbytes + h_so.nbytes
