@@ -588,6 +588,182 @@ P265_HD void stage2_row(const unsigned char *g, int row, int16_t *dst, int rnd2,
     }
 }
 
+// ======================================================================================
+// Small TBs: one lane = one TB, everything in registers.
+// For 4x4 and 8x8 blocks the shared-memory choreography above costs more than the
+// arithmetic (per-item overhead is amortised over only 8 / 16 samples per lane).  Here a
+// work item is 32 TBs, one per lane: the lane reads its TB, dequantises, runs both
+// transform stages and writes its rows without ever leaving its registers -- no
+// transposes through shared memory, no warp synchronisation.
+// ======================================================================================
+P265_HD int sx_lo(uint32_t w) { return (int)(int16_t)(w & 0xffff); }
+P265_HD int sx_hi(uint32_t w) { return (int)w >> 16; }
+
+// transform-skip / bypass of a TB held as packed rows (N*N/2 words, row-major)
+template <int N>
+P265_HD void lane_special(const TbParams &t, const uint32_t *w, const uint8_t *sfm) {
+    P265_UNROLL
+    for (int y = 0; y < N; y++) {
+        uint32_t o[N / 2];
+        P265_UNROLL
+        for (int k = 0; k < N / 2; k++) {
+            int r[2];
+            P265_UNROLL
+            for (int h = 0; h < 2; h++) {
+                const int lv = h ? sx_hi(w[y * (N / 2) + k]) : sx_lo(w[y * (N / 2) + k]);
+                if (t.flags & P265_TU_BYPASS) {
+                    r[h] = lv;
+                } else {
+                    const int m = sfm ? (int)sfm[y * N + 2 * k + h] * t.w : t.w;
+                    int d = dequant(lv, m, t);
+                    d = d < -32768 ? -32768 : (d > 32767 ? 32767 : d);
+                    r[h] = (d * 128 + t.rnd2) >> t.sh2;
+                }
+            }
+            o[k] = (uint32_t)pack_sat(r[0], r[1]);
+        }
+        int16_t *dst = t.dst + (size_t)y * t.stride;
+        if (N == 4) *reinterpret_cast<uint2 *>(dst) = make_uint2(o[0], o[1]);
+        else *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[N / 2 - 2], o[N / 2 - 1]);
+    }
+}
+
+// 4x4: `w` = the TB's 8 packed words (rows 0..3, two words per row)
+template <int SF, bool SLOW>
+P265_HD void tb4_lane(const TbParams &t, const uint32_t (&w)[8]) {
+    if (!t.valid) return;
+    const uint8_t *sfm = (SF != SF_NONE) ? t.sf : nullptr;
+    if (t.flags & (P265_TU_SKIP | P265_TU_BYPASS)) {
+        lane_special<4>(t, w, sfm);
+        return;
+    }
+    uint32_t mrow[4] = {0, 0, 0, 0};  // ScalingFactor bytes, one word per row
+    if (SF != SF_NONE && sfm) {
+        const uint4 mv = *reinterpret_cast<const uint4 *>(sfm);
+        mrow[0] = mv.x; mrow[1] = mv.y; mrow[2] = mv.z; mrow[3] = mv.w;
+    }
+    int d[4][4];  // [y][x]
+    P265_UNROLL
+    for (int y = 0; y < 4; y++) {
+        P265_UNROLL
+        for (int x = 0; x < 4; x++) {
+            const uint32_t ww = w[y * 2 + (x >> 1)];
+            const int lv = (x & 1) ? sx_hi(ww) : sx_lo(ww);
+            int m = t.w;
+            if (SF != SF_NONE && sfm) m *= (int)((mrow[y] >> (8 * x)) & 0xff);
+            d[y][x] = SLOW ? dequant(lv, m, t) : dequant_fast(lv, m, t);
+        }
+    }
+    // stage 1: four columns in lock step; slot 0 = rows (0,2), slot 1 = rows (1,3)
+    int p[4][2], e[4][4];
+    P265_UNROLL
+    for (int x = 0; x < 4; x++) {
+        p[x][0] = pack_sat(d[0][x], d[2][x]);
+        p[x][1] = pack_sat(d[1][x], d[3][x]);
+    }
+    if (t.flags & P265_TU_DST) dst4<4>(p, 64, e);
+    else Idct<4, 4>::run(p, 64, e);
+    // stage 2: four rows in lock step; slot 0 = columns (0,2), slot 1 = columns (1,3)
+    int q[4][2], r[4][4];
+    P265_UNROLL
+    for (int y = 0; y < 4; y++) {
+        q[y][0] = pack_sat(e[0][y] >> 7, e[2][y] >> 7);
+        q[y][1] = pack_sat(e[1][y] >> 7, e[3][y] >> 7);
+    }
+    if (t.flags & P265_TU_DST) dst4<4>(q, t.rnd2, r);
+    else Idct<4, 4>::run(q, t.rnd2, r);
+    P265_UNROLL
+    for (int y = 0; y < 4; y++) {
+        const uint32_t o0 = (uint32_t)pack_sat(r[y][0] >> t.sh2, r[y][1] >> t.sh2);
+        const uint32_t o1 = (uint32_t)pack_sat(r[y][2] >> t.sh2, r[y][3] >> t.sh2);
+        *reinterpret_cast<uint2 *>(t.dst + (size_t)y * t.stride) = make_uint2(o0, o1);
+    }
+}
+
+// 8x8: the TB sits in shared memory (lane-private 128 bytes, 16-byte chunks XOR-swizzled
+// by the lane index so that the 128-bit row loads of a quarter-warp hit distinct banks).
+P265_HD int tb8_chunk_off(int lane, int row) { return lane * 128 + ((row ^ (lane & 7)) << 4); }
+
+template <int SF, bool SLOW>
+P265_HD void tb8_lane(const TbParams &t, const unsigned char *tile, int lane) {
+    if (!t.valid) return;
+    const uint8_t *sfm = (SF != SF_NONE) ? t.sf : nullptr;
+    if (t.flags & P265_TU_BYPASS) {
+        uint32_t w[32];
+        P265_UNROLL
+        for (int y = 0; y < 8; y++) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(tile + tb8_chunk_off(lane, y));
+            w[4 * y] = v.x; w[4 * y + 1] = v.y; w[4 * y + 2] = v.z; w[4 * y + 3] = v.w;
+        }
+        lane_special<8>(t, w, sfm);
+        return;
+    }
+    // dequantise row pairs (0,4), (2,6), (1,3), (5,7) into packed stage-1 operands P[x][s]
+    int P[8][4];
+    P265_UNROLL
+    for (int s = 0; s < 4; s++) {
+        const int y0 = slot_index(8, s, 0), y1 = slot_index(8, s, 1);
+        const uint4 a = *reinterpret_cast<const uint4 *>(tile + tb8_chunk_off(lane, y0));
+        const uint4 b = *reinterpret_cast<const uint4 *>(tile + tb8_chunk_off(lane, y1));
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+        uint32_t ma[2] = {0, 0}, mb[2] = {0, 0};
+        if (SF != SF_NONE && sfm) {
+            const uint2 va = *reinterpret_cast<const uint2 *>(sfm + y0 * 8);
+            const uint2 vb = *reinterpret_cast<const uint2 *>(sfm + y1 * 8);
+            ma[0] = va.x; ma[1] = va.y; mb[0] = vb.x; mb[1] = vb.y;
+        }
+        P265_UNROLL
+        for (int x = 0; x < 8; x++) {
+            const int la = (x & 1) ? sx_hi(aw[x >> 1]) : sx_lo(aw[x >> 1]);
+            const int lb = (x & 1) ? sx_hi(bw[x >> 1]) : sx_lo(bw[x >> 1]);
+            int m0 = t.w, m1 = t.w;
+            if (SF != SF_NONE && sfm) {
+                m0 *= (int)((ma[x >> 2] >> (8 * (x & 3))) & 0xff);
+                m1 *= (int)((mb[x >> 2] >> (8 * (x & 3))) & 0xff);
+            }
+            if (!SLOW) P[x][s] = pack_sat(dequant_fast(la, m0, t), dequant_fast(lb, m1, t));
+            else P[x][s] = pack_sat(dequant(la, m0, t), dequant(lb, m1, t));
+        }
+    }
+    // stage 1: column pairs = stage-2 slots (0,4), (2,6), (1,3), (5,7)
+    int G[8][4];
+    P265_UNROLL
+    for (int sl = 0; sl < 4; sl++) {
+        const int x0 = slot_index(8, sl, 0), x1 = slot_index(8, sl, 1);
+        int pp[2][4], e[2][8];
+        P265_UNROLL
+        for (int k = 0; k < 4; k++) {
+            pp[0][k] = P[x0][k];
+            pp[1][k] = P[x1][k];
+        }
+        Idct<8, 2>::run(pp, 64, e);
+        P265_UNROLL
+        for (int y = 0; y < 8; y++) G[y][sl] = pack_sat(e[0][y] >> 7, e[1][y] >> 7);
+    }
+    // stage 2: two rows at a time
+    P265_UNROLL
+    for (int y = 0; y < 8; y += 2) {
+        int pp[2][4], r[2][8];
+        P265_UNROLL
+        for (int k = 0; k < 4; k++) {
+            pp[0][k] = G[y][k];
+            pp[1][k] = G[y + 1][k];
+        }
+        Idct<8, 2>::run(pp, t.rnd2, r);
+        P265_UNROLL
+        for (int c = 0; c < 2; c++) {
+            uint32_t o[4];
+            P265_UNROLL
+            for (int k = 0; k < 4; k++) o[k] = (uint32_t)pack_sat(r[c][2 * k] >> t.sh2, r[c][2 * k + 1] >> t.sh2);
+            *reinterpret_cast<uint4 *>(t.dst + (size_t)(y + c) * t.stride) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+// TBs per warp work item, by bin (32x32, 16x16, 8x8, 4x4): the two big sizes use the
+// shared-memory column/row scheme (64 columns per item), the two small ones one lane per TB.
+P265_HD constexpr int tbs_per_item(int bin) { return bin == 0 ? 2 : (bin == 1 ? 4 : 32); }
+
 // TB index handled by `lane` of warp item `item` in bin LOG2N (bins: 0 -> 32x32 ...)
 template <int LOG2N>
 P265_HD int lane_tb(const KernelArgs &a, int item, int lane, bool &valid) {

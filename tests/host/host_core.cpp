@@ -51,8 +51,43 @@ static void run_item_sf(const KernelArgs &a, int item) {
     }
 }
 
+template <int SF>
+static void run_small_item(const KernelArgs &a, int bin, int item) {
+    // one lane = one TB (tb8_lane / tb4_lane), 32 TBs per item
+    alignas(16) unsigned char tile[kWarpSmemBytes];
+    std::memset(tile, 0xA5, sizeof tile);
+    TbParams t[32];
+    bool slow = false;
+    for (int lane = 0; lane < 32; lane++) {
+        const int local = item * 32 + lane;
+        const bool valid = local < a.n_tb[bin];
+        t[lane] = make_params(a, a.first_tb[bin] + local, valid);
+        slow |= valid && t[lane].lsh != 0;
+    }
+    for (int lane = 0; lane < 32; lane++) {
+        const TbParams &q = t[lane];
+        if (!q.valid) continue;
+        if (bin == 2) {
+            for (int r = 0; r < 8; r++) copy16_async(tile + tb8_chunk_off(lane, r), q.src + r * 8);
+            if (slow) tb8_lane<SF, true>(q, tile, lane);
+            else tb8_lane<SF, false>(q, tile, lane);
+        } else {
+            uint32_t w[8];
+            std::memcpy(w, q.src, 32);
+            if (slow) tb4_lane<SF, true>(q, w);
+            else tb4_lane<SF, false>(q, w);
+        }
+    }
+}
+
 template <int LOG2N>
 static void run_item(const KernelArgs &a, int item) {
+    if (LOG2N <= 3) {
+        const int bin = 5 - LOG2N;
+        if (!a.sf) run_small_item<SF_NONE>(a, bin, item);
+        else run_small_item<SF_GENERAL>(a, bin, item);
+        return;
+    }
     if (!a.sf) run_item_sf<LOG2N, SF_NONE>(a, item);
     else if (a.sf_replicated) run_item_sf<LOG2N, SF_REPLICATED>(a, item);
     else run_item_sf<LOG2N, SF_GENERAL>(a, item);
@@ -71,7 +106,7 @@ extern "C" int host_residual_batch(const p265_tu_desc *tus, const int32_t bin_co
         a.first_tb[b] = first; a.n_tb[b] = bin_counts[b];
         first += bin_counts[b];
         a.first_item[b] = items;
-        const int per = 2 << b;  // 2, 4, 8, 16 TBs per warp item
+        const int per = tbs_per_item(b);
         items += (bin_counts[b] + per - 1) / per;
     }
     a.first_item[4] = items;
