@@ -259,7 +259,8 @@ __device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int r
     q.avail = qp->avail;
 #pragma unroll
     for (int i = 0; i < 4; i++) q.offset_val[i] = qp->offset_val[c][i];
-    const int cs = (1 << a.ctb_log2) >> (c ? 1 : 0);
+    const int cs_log2 = a.ctb_log2 - (c ? 1 : 0);
+    const int cs = 1 << cs_log2;
     const int w = c ? a.width >> 1 : a.width, h = c ? a.height >> 1 : a.height;
     const int bd = c ? a.bit_depth_c : a.bit_depth_y;
     Geo g;
@@ -271,13 +272,14 @@ __device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int r
     g.vh = min(cs, h - g.y0);
 
     // tile = th rows of the CTB starting at row tile * th; lanes_w x lane_rows lanes, R rows each
+    // (all sizes are powers of two: shifts, no integer divisions)
     Strip s;
-    s.lanes_w = max(cs >> 3, 1);
-    const int lane_rows = 32 / s.lanes_w;
-    const int th = min(cs, 1024 / cs);              // 16 (cs 64), 32, 16, 8
-    g.rows = max(1, th / lane_rows);                // 4, 4, 1, 1
-    s.lx = lane % s.lanes_w;
-    const int ly = lane / s.lanes_w;
+    const int lw_log2 = max(cs_log2 - 3, 0);
+    s.lanes_w = 1 << lw_log2;
+    const int th = min(cs, 1024 >> cs_log2);        // 16 (cs 64), 32, 16, 8
+    g.rows = max(1, (th << lw_log2) >> 5);          // 4, 4, 1, 1
+    s.lx = lane & (s.lanes_w - 1);
+    const int ly = lane >> lw_log2;
     g.row0 = tile * th + ly * g.rows;
     g.active = s.lx * 8 < vw && g.row0 < g.vh && ly * g.rows < th;
     if (ly * g.rows >= th) {  // lane has no rows at all (8x8 chroma CTBs): park it on the tile's first row
@@ -354,18 +356,16 @@ __device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int r
     m.aDL = has_d && has_l && (av >> 6 & 1);
     m.aD = has_d && (av >> 7 & 1);
     m.aDR = has_d && has_r && (av >> 8 & 1);
+    // first / last valid column of the CTB and columns beyond the picture, as half-word
+    // masks of this lane's four words (vw is a multiple of 4: 8 for luma, 4 for chroma)
+    {
+        const int xr = vw - 1 - s.lx * 8;  // position of the last valid column inside the strip
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        uint32_t cl = 0, cr = 0, be = 0;
-#pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-            const int xl = s.lx * 8 + 2 * i + hh;
-            const uint32_t bit = 0xffffu << (16 * hh);
-            if (xl == 0) cl |= bit;
-            if (xl == vw - 1) cr |= bit;
-            if (xl >= vw) be |= bit;
+        for (int i = 0; i < 4; i++) {
+            m.col_l[i] = (i == 0 && s.lx == 0) ? 0x0000ffffu : 0u;
+            m.col_r[i] = (xr >> 1) == i ? ((xr & 1) ? 0xffff0000u : 0x0000ffffu) : 0u;
+            m.beyond[i] = (2 * i > xr) ? 0xffffffffu : ((2 * i + 1 > xr) ? 0xffff0000u : 0u);
         }
-        m.col_l[i] = cl; m.col_r[i] = cr; m.beyond[i] = be;
     }
     switch (q.eo_class) {
         case 0: edge_strip<T, 0, NOFILT>(in, out, g, s, m, k, nf_row, nf_stride, nf_shift); break;
@@ -375,27 +375,31 @@ __device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int r
     }
 }
 
-// Work items: for every (picture, CTB) first the luma tiles (tiles_y of them), then one
-// Cb and one Cr item; all items cover (up to) 1024 samples, so warps are balanced.
-template <typename T, bool NOFILT>
+// Grid = (tiles of a CTB row / 4, CTB row, picture), 4 warps per CTA, one warp per tile.
+// Tiles of a CTB: the luma tiles first (PER_CTB - 2 of them), then Cb, then Cr; all cover
+// (up to) 1024 samples.  PER_CTB is a template constant so that no run-time division is
+// left in the per-warp setup.
+template <typename T, bool NOFILT, int PER_CTB>
 __global__ void __launch_bounds__(kSaoWarpsPerCta * 32) sao_kernel(const __grid_constant__ SaoArgs a) {
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * kSaoWarpsPerCta + (threadIdx.x >> 5);
-    if (item >= a.items) return;
-    const int per_ctb = a.tiles_y + a.tiles_c * 2;
-    const int cb = item / per_ctb, sub = item - cb * per_ctb;
-    int c, tile;
-    if (sub < a.tiles_y) {
-        c = 0;
-        tile = sub;
-    } else {
-        const int j = sub - a.tiles_y;
-        c = 1 + j / a.tiles_c;
-        tile = j - (c - 1) * a.tiles_c;
-    }
-    const int pic = cb / a.ctbs, ctb = cb - pic * a.ctbs;
-    const int ry = ctb / a.ctbs_w, rx = ctb - ry * a.ctbs_w;
-    sao_item<T, NOFILT>(a, pic, c, rx, ry, tile, lane);
+    const int rx = item / PER_CTB, sub = item - rx * PER_CTB;
+    if (rx >= a.ctbs_w) return;
+    const int c = sub < PER_CTB - 2 ? 0 : sub - (PER_CTB - 3);
+    const int tile = c ? 0 : sub;
+    sao_item<T, NOFILT>(a, blockIdx.z, c, rx, blockIdx.y, tile, lane);
+}
+
+template <typename T, bool NOFILT>
+static int launch_sao_t(p265_ctx *ctx, const SaoArgs &a, int n_pics) {
+    const int per_ctb = a.tiles_y + 2 * a.tiles_c;  // 6 for 64x64 CTBs, 3 otherwise
+    const dim3 grid((a.ctbs_w * per_ctb + kSaoWarpsPerCta - 1) / kSaoWarpsPerCta, a.ctbs_h, n_pics);
+    const int threads = kSaoWarpsPerCta * 32;
+    if (per_ctb == 6) sao_kernel<T, NOFILT, 6><<<grid, threads, 0, ctx->stream>>>(a);
+    else sao_kernel<T, NOFILT, 3><<<grid, threads, 0, ctx->stream>>>(a);
+    P265_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return P265_OK;
 }
 
 int launch_sao(p265_ctx *ctx, const void *d_rec, void *d_out, const p265_pic_geom *g, int ctb_log2,
@@ -422,23 +426,11 @@ int launch_sao(p265_ctx *ctx, const void *d_rec, void *d_out, const p265_pic_geo
     const int cs_c = ctb >> 1;
     a.tiles_y = ctb / (ctb < 1024 / ctb ? ctb : 1024 / ctb);
     a.tiles_c = cs_c / (cs_c < 1024 / cs_c ? cs_c : 1024 / cs_c);
-    const int64_t items = (int64_t)a.ctbs * g->n_pics * (a.tiles_y + 2 * a.tiles_c);
-    if (items > INT32_MAX) return set_error(P265_EINVAL, "too many CTBs in one SAO batch");
-    a.items = (int32_t)items;
-    if (a.items == 0) return P265_OK;
-    const int grid = (a.items + kSaoWarpsPerCta - 1) / kSaoWarpsPerCta;
+    a.items = 0;
+    if (a.ctbs_h > 65535 || g->n_pics > 65535) return set_error(P265_EINVAL, "too many CTB rows / pictures in one SAO batch");
     const bool wide = g->bit_depth_y > 8 || g->bit_depth_c > 8;
-    const int threads = kSaoWarpsPerCta * 32;
-    if (wide) {
-        if (d_no_filter) sao_kernel<uint16_t, true><<<grid, threads, 0, ctx->stream>>>(a);
-        else sao_kernel<uint16_t, false><<<grid, threads, 0, ctx->stream>>>(a);
-    } else {
-        if (d_no_filter) sao_kernel<uint8_t, true><<<grid, threads, 0, ctx->stream>>>(a);
-        else sao_kernel<uint8_t, false><<<grid, threads, 0, ctx->stream>>>(a);
-    }
-    P265_CUDA(cudaGetLastError());
-    ctx->launches++;
-    return P265_OK;
+    if (wide) return d_no_filter ? launch_sao_t<uint16_t, true>(ctx, a, g->n_pics) : launch_sao_t<uint16_t, false>(ctx, a, g->n_pics);
+    return d_no_filter ? launch_sao_t<uint8_t, true>(ctx, a, g->n_pics) : launch_sao_t<uint8_t, false>(ctx, a, g->n_pics);
 }
 
 }  // namespace p265
