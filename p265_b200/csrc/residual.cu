@@ -61,8 +61,8 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
     constexpr int N = L::N, bin = 5 - LOG2N;
     const int n_items = a.first_item[bin + 1] - a.first_item[bin];
     if (gw >= n_items) return;
-    unsigned char *in_base = wbase, *g_base = wbase + kWarpSmemBytes;
-    uint4 *ring = reinterpret_cast<uint4 *>(wbase + 2 * kWarpSmemBytes) + lane;  // slot s at ring[32 * s]
+    unsigned char *in_base = wbase, *g_base = wbase + L::WARP_BYTES;
+    uint4 *ring = reinterpret_cast<uint4 *>(wbase + 2 * L::WARP_BYTES) + lane;  // slot s at ring[32 * s]
     const int tb_l = lane / L::TPB, tl = lane % L::TPB;
     const unsigned char *in = in_base + tb_l * L::TB_BYTES;
     unsigned char *g = g_base + tb_l * L::TB_BYTES;
@@ -223,13 +223,30 @@ __device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride
 // reach the bin boundaries at different times, several size paths are then hot at once
 // and the per-SM instruction cache (hit rate 87 % vs 98-99 % per size) becomes the
 // bottleneck.  Persistent warps: warp w handles items w, w + W, w + 2W, ... of its bin.
+// CTAs per SM per bin: 32x32 is shared-memory limited (9.25 KB per warp); 16x16 needs only
+// 5.25 KB per warp and fits 64 registers; 8x8 keeps 64 packed words live per lane; 4x4 is
+// register-only.
+#ifndef P265_CTAS_BIN1
+#define P265_CTAS_BIN1 16
+#endif
+#ifndef P265_CTAS_BIN3
+#define P265_CTAS_BIN3 16
+#endif
+template <int BIN>
+struct BinCfg {
+    static constexpr int ctas = BIN == 1 ? P265_CTAS_BIN1 : (BIN == 3 ? P265_CTAS_BIN3 : kCtasPerSm);
+    static constexpr int smem =
+        BIN == 3 ? 0 : (BIN == 1 ? kWarpsPerCta * (2 * Layout<4>::WARP_BYTES + kDescRingBytes) : kCtaSmemBytes);
+};
+
 template <int BIN, int SF>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) residual_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, BinCfg<BIN>::ctas) residual_kernel(const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stride = gridDim.x * kWarpsPerCta;
     const int gw = blockIdx.x * kWarpsPerCta + warp;
-    unsigned char *wbase = smem + warp * kWarpBytes;
+    constexpr int warp_bytes = BinCfg<BIN>::smem / kWarpsPerCta;
+    unsigned char *wbase = smem + warp * warp_bytes;
     if (BIN == 0) run_bin<5, SF>(a, gw, stride, lane, wbase);
     else if (BIN == 1) run_bin<4, SF>(a, gw, stride, lane, wbase);
     else if (BIN == 2) run_bin8<SF>(a, gw, stride, lane, wbase);
@@ -345,7 +362,7 @@ template <int BIN, int SF>
 static int launch_bin(p265_ctx *ctx, const KernelArgs &a) {
     const int items = a.first_item[BIN + 1] - a.first_item[BIN];
     if (items == 0) return P265_OK;
-    constexpr int smem = BIN == 3 ? 0 : kCtaSmemBytes;  // the 4x4 path lives in registers
+    constexpr int smem = BinCfg<BIN>::smem;
     static int occ = 0;  // CTAs per SM the kernel really gets (same for every device of a box)
     if (!occ) {
         P265_CUDA(cudaFuncSetAttribute(residual_kernel<BIN, SF>, cudaFuncAttributePreferredSharedMemoryCarveout,
