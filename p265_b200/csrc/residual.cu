@@ -242,6 +242,10 @@ struct BinCfg {
 template <int BIN, int SF>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, BinCfg<BIN>::ctas) residual_kernel(const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
+    // The four bin kernels are independent (disjoint TBs): let the next one be scheduled
+    // as soon as CTAs of this one retire (programmatic dependent launch) so the tail of a
+    // bin overlaps the head of the next instead of idling SMs.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stride = gridDim.x * kWarpsPerCta;
     const int gw = blockIdx.x * kWarpsPerCta + warp;
@@ -359,7 +363,7 @@ static int fill_args(KernelArgs &a, const p265_tu_desc *d_tus, const int32_t bin
 }
 
 template <int BIN, int SF>
-static int launch_bin(p265_ctx *ctx, const KernelArgs &a) {
+static int launch_bin(p265_ctx *ctx, const KernelArgs &a, bool overlap_previous) {
     const int items = a.first_item[BIN + 1] - a.first_item[BIN];
     if (items == 0) return P265_OK;
     constexpr int smem = BinCfg<BIN>::smem;
@@ -376,19 +380,32 @@ static int launch_bin(p265_ctx *ctx, const KernelArgs &a) {
     const int rounds = (items + max_warps - 1) / max_warps;
     const int warps = (items + rounds - 1) / rounds;
     const int grid = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
-    residual_kernel<BIN, SF><<<grid, kWarpsPerCta * 32, smem, ctx->stream>>>(a);
-    P265_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kWarpsPerCta * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = overlap_previous ? 1 : 0;
+    P265_CUDA(cudaLaunchKernelEx(&cfg, residual_kernel<BIN, SF>, a));
     ctx->launches++;
     return P265_OK;
 }
 
 template <int SF>
 static int launch_residual_sf(p265_ctx *ctx, const KernelArgs &a) {
+    // the first kernel of the batch is ordered normally behind whatever precedes it on the
+    // stream (zero fill, copies); the following bins may overlap their predecessor
     int rc;
-    if ((rc = launch_bin<0, SF>(ctx, a))) return rc;
-    if ((rc = launch_bin<1, SF>(ctx, a))) return rc;
-    if ((rc = launch_bin<2, SF>(ctx, a))) return rc;
-    return launch_bin<3, SF>(ctx, a);
+    bool first = true;
+    if (a.n_tb[0]) { if ((rc = launch_bin<0, SF>(ctx, a, !first))) return rc; first = false; }
+    if (a.n_tb[1]) { if ((rc = launch_bin<1, SF>(ctx, a, !first))) return rc; first = false; }
+    if (a.n_tb[2]) { if ((rc = launch_bin<2, SF>(ctx, a, !first))) return rc; first = false; }
+    if (a.n_tb[3]) { if ((rc = launch_bin<3, SF>(ctx, a, !first))) return rc; first = false; }
+    return P265_OK;
 }
 
 int launch_residual(p265_ctx *ctx, const p265_tu_desc *d_tus, const int32_t bin_counts[4], const int16_t *d_coeffs,
