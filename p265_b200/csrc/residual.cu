@@ -410,6 +410,8 @@ static int launch_residual_sf(p265_ctx *ctx, const KernelArgs &a) {
 
 int launch_residual(p265_ctx *ctx, const p265_tu_desc *d_tus, const int32_t bin_counts[4], const int16_t *d_coeffs,
                     const uint8_t *d_sf, const p265_pic_geom *g, int16_t *d_out, int flags) {
+    if ((uint64_t)g->pic_stride * (uint64_t)g->n_pics > 0xffffffffull)
+        return set_error(P265_EINVAL, "residual planes of one batch must stay below 2^32 elements: split the batch");
     KernelArgs a;
     int rc = fill_args(a, d_tus, bin_counts, d_coeffs, d_sf, g, d_out);
     if (rc) return rc;

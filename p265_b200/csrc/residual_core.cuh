@@ -288,11 +288,23 @@ struct KernelArgs {
 };
 
 P265_HD int sf_matrix_offset(int log2n, int c_idx, int intra) {
-    // [sizeId][matrixId][y][x]; matrixId per scaling.py:33-42
-    const int n2 = 1 << (2 * log2n);
-    const int base = log2n == 2 ? 0 : (log2n == 3 ? 96 : (log2n == 4 ? 480 : 2016));
-    const int mid = log2n == 5 ? (intra ? 0 : 1) : (intra ? c_idx : c_idx + 3);
-    return base + mid * n2;
+    // [sizeId][matrixId][y][x]; matrixId per scaling.py:33-42.  Branch-free: the four
+    // sizeId bases {0, 96, 480, 2016} sit in one 64-bit constant (16 bits each).
+    const int size_id = log2n - 2;
+    const int base = (int)((0x07e001e000600000ull >> (16 * size_id)) & 0xffff);
+    const int not_intra = intra ? 0 : 1;
+    const int mid = log2n == 5 ? not_intra : c_idx + 3 * not_intra;
+    return base + (mid << (2 * log2n));
+}
+
+// levelScale[rem] = {40,45,51,57,64,72} (scaling.py:28) as a byte LUT
+P265_HD int level_scale(int rem) {
+#if defined(__CUDA_ARCH__)
+    return (int)(__byte_perm(0x39332d28u, 0x00004840u, (unsigned)rem | 0x7770u));  // bytes 1-3 <- pool byte 7 = 0
+#else
+    const uint64_t lut = 0x0000484039332d28ull;
+    return (int)((lut >> (8 * rem)) & 0xff);
+#endif
 }
 
 P265_HD uint4 load_desc(const KernelArgs &a, int tb_index, bool valid) {
@@ -321,11 +333,14 @@ P265_HD TbParams make_params(const KernelArgs &a, const uint4 d, bool valid) {
     const int bit_depth = c_idx ? a.bit_depth_c : a.bit_depth_y;
     t.stride = c_idx ? a.stride_c : a.stride_y;
     t.src = a.coeffs + (size_t)coeff_off * 16;
-    t.dst = a.out + (size_t)pic * a.pic_stride + a.plane_off[c_idx] + (size_t)y * t.stride + x;
+    // element offset inside the residual buffer in 32 bits (the launcher rejects batches
+    // whose planes exceed 2^32 elements)
+    const uint32_t off = (uint32_t)pic * (uint32_t)a.pic_stride + (uint32_t)a.plane_off[c_idx] +
+                         (uint32_t)y * (uint32_t)t.stride + (uint32_t)x;
+    t.dst = a.out + off;
     const int per = (qp * 43) >> 8;  // qp / 6 for qp < 128
     const int rem = qp - per * 6;
-    // levelScale = {40,45,51,57,64,72} (scaling.py:28)
-    const int ls = rem == 0 ? 40 : rem == 1 ? 45 : rem == 2 ? 51 : rem == 3 ? 57 : rem == 4 ? 64 : 72;
+    const int ls = level_scale(rem);
     const int bd_shift = bit_depth + log2n - 5;
     if (a.sf) {
         t.sf = a.sf + sf_matrix_offset(log2n, c_idx, (t.flags & P265_TU_INTRA) != 0);
@@ -334,15 +349,10 @@ P265_HD TbParams make_params(const KernelArgs &a, const uint4 d, bool valid) {
         t.sf = nullptr;
         t.w = ls * 16;
     }
-    if (per < bd_shift) {
-        t.sh = bd_shift - per;
-        t.rnd = 1 << (t.sh - 1);
-        t.lsh = 0;
-    } else {
-        t.sh = 0;
-        t.rnd = 0;
-        t.lsh = per - bd_shift;
-    }
+    const int ds = bd_shift - per;  // > 0: right shift with rounding; <= 0: clip, left shift
+    t.sh = ds > 0 ? ds : 0;
+    t.rnd = ds > 0 ? (1 << (ds - 1)) : 0;
+    t.lsh = ds > 0 ? 0 : -ds;
     if (t.flags & P265_TU_PRESCALED) {  // arena holds d[] already: identity "dequantisation"
         t.sf = nullptr;
         t.w = 1;
