@@ -56,7 +56,8 @@ __device__ __noinline__ void stage2_call(const unsigned char *g, int row, int16_
 //     stage 2 of item k       ->  overlaps the tile copy
 // so both dependent global-memory latencies of an item hide behind arithmetic.
 template <int LOG2N, int SF>
-__device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride, int lane, unsigned char *wbase) {
+__device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride, int lane, unsigned char *wbase,
+                                        const uint8_t *sfc) {
     using L = Layout<LOG2N>;
     constexpr int N = L::N, bin = 5 - LOG2N;
     const int n_items = a.first_item[bin + 1] - a.first_item[bin];
@@ -90,12 +91,16 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
         const bool slow = __any_sync(0xffffffffu, t.lsh != 0);
         if (__any_sync(0xffffffffu, t.valid && is_special)) phase_special<LOG2N>(lane, t, in_base);
         const int dstf = t.flags & P265_TU_DST;
+        // SF_REPLICATED: stage 1 reads the CTA's compact copy of this TB's matrix
+        const uint8_t *sf1 = t.sf;
+        if (SF == SF_REPLICATED && t.sf)
+            sf1 = sfc + sf_matrix_id(LOG2N, (int)((ring[32 * k].y >> 8) & 0xff), t.flags) * kSfcStride;
         if (!slow) {
-            stage1_call<LOG2N, SF, false>(in, g, x0, tl, 0, t.sf, t.w, t.rnd, t.sh, 0, dstf);
-            stage1_call<LOG2N, SF, false>(in, g, x1, tl, 1, t.sf, t.w, t.rnd, t.sh, 0, dstf);
+            stage1_call<LOG2N, SF, false>(in, g, x0, tl, 0, sf1, t.w, t.rnd, t.sh, 0, dstf);
+            stage1_call<LOG2N, SF, false>(in, g, x1, tl, 1, sf1, t.w, t.rnd, t.sh, 0, dstf);
         } else {  // rare
-            stage1_call<LOG2N, SF, true>(in, g, x0, tl, 0, t.sf, t.w, t.rnd, t.sh, t.lsh, dstf);
-            stage1_call<LOG2N, SF, true>(in, g, x1, tl, 1, t.sf, t.w, t.rnd, t.sh, t.lsh, dstf);
+            stage1_call<LOG2N, SF, true>(in, g, x0, tl, 0, sf1, t.w, t.rnd, t.sh, t.lsh, dstf);
+            stage1_call<LOG2N, SF, true>(in, g, x1, tl, 1, sf1, t.w, t.rnd, t.sh, t.lsh, dstf);
         }
         __syncwarp();  // `in` is consumed, g is complete
         if (it + stride < n_items) {
@@ -232,11 +237,13 @@ __device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride
 #ifndef P265_CTAS_BIN3
 #define P265_CTAS_BIN3 16
 #endif
+constexpr int kSfcBytes = 512;  // compact ScalingFactor copy at the start of a CTA's shared memory (6 x 80 B)
 template <int BIN>
 struct BinCfg {
     static constexpr int ctas = BIN == 1 ? P265_CTAS_BIN1 : (BIN == 3 ? P265_CTAS_BIN3 : kCtasPerSm);
     static constexpr int smem =
-        BIN == 3 ? 0 : (BIN == 1 ? kWarpsPerCta * (2 * Layout<4>::WARP_BYTES + kDescRingBytes) : kCtaSmemBytes);
+        BIN == 3 ? 0
+                 : kSfcBytes + (BIN == 1 ? kWarpsPerCta * (2 * Layout<4>::WARP_BYTES + kDescRingBytes) : kCtaSmemBytes);
 };
 
 template <int BIN, int SF>
@@ -249,10 +256,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, BinCfg<BIN>::ctas) residual
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stride = gridDim.x * kWarpsPerCta;
     const int gw = blockIdx.x * kWarpsPerCta + warp;
-    constexpr int warp_bytes = BinCfg<BIN>::smem / kWarpsPerCta;
-    unsigned char *wbase = smem + warp * warp_bytes;
-    if (BIN == 0) run_bin<5, SF>(a, gw, stride, lane, wbase);
-    else if (BIN == 1) run_bin<4, SF>(a, gw, stride, lane, wbase);
+    constexpr int warp_bytes = (BinCfg<BIN>::smem - kSfcBytes) / kWarpsPerCta;
+    unsigned char *wbase = smem + kSfcBytes + warp * warp_bytes;
+    if (SF == SF_REPLICATED && BIN <= 1) {
+        if (BIN == 0) build_sf_compact<5>(a.sf, smem, threadIdx.x, blockDim.x);
+        else build_sf_compact<4>(a.sf, smem, threadIdx.x, blockDim.x);
+        __syncthreads();  // the only block-wide barrier: once per persistent CTA
+    }
+    if (BIN == 0) run_bin<5, SF>(a, gw, stride, lane, wbase, smem);
+    else if (BIN == 1) run_bin<4, SF>(a, gw, stride, lane, wbase, smem);
     else if (BIN == 2) run_bin8<SF>(a, gw, stride, lane, wbase);
     else run_bin4<SF>(a, gw, stride, lane);
 }

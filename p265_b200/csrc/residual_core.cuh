@@ -491,6 +491,31 @@ P265_HD void phase_special(int lane, const TbParams &t, const unsigned char *in_
 //                  levelScale -- no per-coefficient load or multiply is left.
 enum { SF_NONE = 0, SF_GENERAL = 1, SF_REPLICATED = 2 };
 
+// SF_REPLICATED: compact, transposed copy of the ScalingFactor matrices of one size,
+// built once per CTA in shared memory: matrix m occupies kSfcStride bytes --
+// [x8][y8] (the 8x8 list, column-major: the 8 factors of a column are 8 contiguous
+// bytes) followed by the DC value at byte 64.
+constexpr int kSfcStride = 80;
+template <int LOG2N>
+P265_HD void build_sf_compact(const uint8_t *table, uint8_t *out, int tid, int nthreads) {
+    constexpr int N = 1 << LOG2N, REP = N / 8, NM = LOG2N == 5 ? 2 : 6;
+    const uint8_t *base = table + sf_matrix_offset(LOG2N, 0, 1);  // matrixId 0 of this size
+    for (int i = tid; i < NM * 65; i += nthreads) {
+        const int m = i / 65, e = i - m * 65;
+        const uint8_t *mat = base + m * N * N;
+        if (e == 64) {
+            out[m * kSfcStride + 64] = mat[0];
+        } else {
+            const int x8 = e >> 3, y8 = e & 7;
+            out[m * kSfcStride + e] = mat[(y8 * REP + (REP > 1 ? 1 : 0)) * N + x8 * REP + (REP - 1)];
+        }
+    }
+}
+P265_HD int sf_matrix_id(int log2n, int c_idx, int flags) {
+    const int not_intra = (flags & P265_TU_INTRA) ? 0 : 1;
+    return log2n == 5 ? not_intra : c_idx + 3 * not_intra;
+}
+
 // ------------------------------------------------- stage 1: ONE column of one TB
 // Dequantise column x of the tile (8.6.3), inverse-transform it (8.6.4.2, vertical pass),
 // clip16((e + 64) >> 7) and store the N results as the `half`-th 16-bit half of slot
@@ -512,9 +537,11 @@ P265_HD void stage1_column(const unsigned char *in, unsigned char *g, int x, int
     int mw[K];
     int dc = 0;
     if (SF == SF_REPLICATED) {
+        // `sf` = this TB's compact matrix (build_sf_compact): one 8-byte load per column
+        const uint2 v = *reinterpret_cast<const uint2 *>(sf + (x / REP) * 8);
         P265_UNROLL
-        for (int k = 0; k < K; k++) mw[k] = (int)sf[(k * REP + (REP > 1 ? 1 : 0)) * N + x] * w;
-        dc = (REP > 1 && x == 0) ? (int)sf[0] * w : mw[0];
+        for (int k = 0; k < K; k++) mw[k] = (int)(((k < 4 ? v.x : v.y) >> (8 * (k & 3))) & 0xff) * w;
+        dc = (x == 0) ? (int)sf[64] * w : mw[0];
     }
     int p[1][N / 2];
     P265_UNROLL

@@ -18,25 +18,35 @@ static void run_item_sf(const KernelArgs &a, int item) {
     std::memset(in_buf, 0xA5, sizeof in_buf);
     std::memset(g_buf, 0x5A, sizeof g_buf);
     TbParams t[32];
+    int lane_tb_index[32];
     bool slow = false;
     for (int lane = 0; lane < 32; lane++) {
         bool valid;
         int tb = lane_tb<LOG2N>(a, item, lane, valid);
+        lane_tb_index[lane] = valid ? tb : 0;
         t[lane] = make_params(a, tb, valid);
         slow |= t[lane].lsh != 0;
         tile_issue<LOG2N>(lane, t[lane].src, valid, in_buf);
     }
     for (int lane = 0; lane < 32; lane++) phase_special<LOG2N>(lane, t[lane], in_buf);
+    alignas(16) uint8_t sfc[512];
+    if (SF == SF_REPLICATED)
+        for (int tid = 0; tid < 64; tid++) build_sf_compact<LOG2N>(a.sf, sfc, tid, 64);
     for (int lane = 0; lane < 32; lane++) {
         const int tb_l = lane / L::TPB, tl = lane % L::TPB;
         const unsigned char *in = in_buf + tb_l * L::TB_BYTES;
         unsigned char *g = g_buf + tb_l * L::TB_BYTES;
         const TbParams &q = t[lane];
+        const uint8_t *sf1 = q.sf;
+        if (SF == SF_REPLICATED && q.sf) {
+            const p265_tu_desc &d = a.tus[lane_tb_index[lane]];
+            sf1 = sfc + sf_matrix_id(LOG2N, d.c_idx, q.flags) * kSfcStride;
+        }
         for (int half = 0; half < 2; half++) {
             const int x = slot_index_rt(N, tl, half);
             const int dstf = q.flags & P265_TU_DST;
-            if (slow) stage1_column<LOG2N, SF, true>(in, g, x, tl, half, q.sf, q.w, q.rnd, q.sh, q.lsh, dstf);
-            else stage1_column<LOG2N, SF, false>(in, g, x, tl, half, q.sf, q.w, q.rnd, q.sh, 0, dstf);
+            if (slow) stage1_column<LOG2N, SF, true>(in, g, x, tl, half, sf1, q.w, q.rnd, q.sh, q.lsh, dstf);
+            else stage1_column<LOG2N, SF, false>(in, g, x, tl, half, sf1, q.w, q.rnd, q.sh, 0, dstf);
         }
     }
     for (int lane = 0; lane < 32; lane++) {
