@@ -469,7 +469,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pics", type=int, default=8, help="4K pictures per step per GPU")
+    ap.add_argument("--pics", type=int, default=16, help="4K pictures per step per GPU")
     ap.add_argument("--e2e-pics", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

@@ -23,6 +23,9 @@
 namespace p265 {
 
 constexpr int kSaoWarpsPerCta = 4;
+#ifndef P265_SAO_CTAS
+#define P265_SAO_CTAS 8  // 64 registers -> 32 warps per SM
+#endif
 
 struct SaoArgs {
     const void *rec;
@@ -380,7 +383,7 @@ __device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int r
 // (up to) 1024 samples.  PER_CTB is a template constant so that no run-time division is
 // left in the per-warp setup.
 template <typename T, bool NOFILT, int PER_CTB>
-__global__ void __launch_bounds__(kSaoWarpsPerCta * 32) sao_kernel(const __grid_constant__ SaoArgs a) {
+__global__ void __launch_bounds__(kSaoWarpsPerCta * 32, P265_SAO_CTAS) sao_kernel(const __grid_constant__ SaoArgs a) {
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * kSaoWarpsPerCta + (threadIdx.x >> 5);
     const int rx = item / PER_CTB, sub = item - rx * PER_CTB;
