@@ -284,11 +284,14 @@ def run_gpu(args):
     kernels = {"residual_kernel": (b_res, ms_res), "sao_kernel": (b_sao, ms_sao)}
     dom = max(kernels, key=lambda k: kernels[k][1])
     ach = kernels[dom][0] / (kernels[dom][1] * 1e-3) / 1e9
+    # DRAM traffic of the dominant kernel from the committed ncu capture (profiles/), scaled
+    # from the capture's batch size to this run's (bytes per picture x pictures per launch)
     traffic = None
     tp = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(dom, {}).get("dram_bytes_per_launch")
+            per_pic = json.load(open(tp)).get(dom, {}).get("dram_bytes_per_picture")
+            traffic = int(per_pic * args.pics) if per_pic else None
         except Exception:
             traffic = None
     int_peak = {}
@@ -299,6 +302,11 @@ def run_gpu(args):
             int_peak[name] = str(e)
     best_int = max(v for v in int_peak.values() if isinstance(v, float))
     ops = alg_int_ops(res)
+    # roofline time of the residual launch = the slower of dense algorithmic
+    # INT32 ops at the measured dual-issue peak and algorithmic bytes at the measured HBM copy
+    # bandwidth; SAO is HBM-bound
+    t_res_roof = max(b_res / (peaks["hbm_gbs"] * 1e9), ops / (best_int * 1e12))
+    t_sao_roof = b_sao / (peaks["hbm_gbs"] * 1e9)
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -315,6 +323,7 @@ def run_gpu(args):
                 "how": "Engine.residual and Engine.sao (C-ABI host entry points) on two contexts from two host "
                        "threads, pinned host buffers, every copy inside the timed region"},
         "gpu_launches": int(launches),
+        "gpu_launches_per_step": {"residual_kernel<bin 32/16/8/4>": 4, "sao_kernel": 1},
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1),
                      "peak": peaks["hbm_gbs"], "peak_source": peak_kind, "unit": "GB/s",
@@ -325,6 +334,14 @@ def run_gpu(args):
                                  for k, v in kernels.items()},
                      "combined_frac_hbm": round((b_res + b_sao) / ((ms_res + ms_sao) * 1e-3) / 1e9
                                                 / peaks["hbm_gbs"], 4),
+                     "slower_of_int32_and_hbm": {
+                         "definition": "SURVEY 8(d): max(alg bytes / measured HBM, dense alg int ops / measured "
+                                       "INT32 dual-issue peak) / measured time",
+                         "residual_bound": "int32" if ops / (best_int * 1e12) > b_res / (peaks["hbm_gbs"] * 1e9)
+                         else "hbm",
+                         "residual_frac": round(t_res_roof / (ms_res * 1e-3), 4),
+                         "sao_frac": round(t_sao_roof / (ms_sao * 1e-3), 4),
+                         "combined_frac": round((t_res_roof + t_sao_roof) / ((ms_res + ms_sao) * 1e-3), 4)},
                      "int32": {"peak_tops_measured": int_peak,
                                "residual_alg_gops_per_launch": round(ops / 1e9, 2),
                                "residual_alg_tops": round(ops / (ms_res * 1e-3) / 1e12, 2),
