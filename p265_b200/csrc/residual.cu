@@ -379,13 +379,17 @@ static int launch_bin(p265_ctx *ctx, const KernelArgs &a, bool overlap_previous)
     const int items = a.first_item[BIN + 1] - a.first_item[BIN];
     if (items == 0) return P265_OK;
     constexpr int smem = BinCfg<BIN>::smem;
-    static int occ = 0;  // CTAs per SM the kernel really gets (same for every device of a box)
+    // CTAs per SM the kernel really gets; function attributes are per device, so the
+    // carve-out hint is set once for every device this process uses
+    static int occ_dev[64] = {0};
+    int &occ = occ_dev[ctx->device & 63];
     if (!occ) {
+        int o = 0;
         P265_CUDA(cudaFuncSetAttribute(residual_kernel<BIN, SF>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        cudaSharedmemCarveoutMaxShared));
-        P265_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, residual_kernel<BIN, SF>, kWarpsPerCta * 32,
+        P265_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, residual_kernel<BIN, SF>, kWarpsPerCta * 32,
                                                                 smem));
-        if (occ < 1) occ = 1;
+        occ = o < 1 ? 1 : o;
     }
     // persistent grid, trimmed so that every warp gets the same number of items
     const int max_warps = ctx->sm_count * occ * kWarpsPerCta;
