@@ -146,6 +146,16 @@ int p265_sao_batch_dev(p265_ctx *ctx, const void *d_rec, void *d_out,
                        const p265_pic_geom *geom, int ctb_log2, const p265_sao_ctb *d_params,
                        const uint8_t *d_no_filter);
 
+/* ---- reconstruction (reconstruction.py:4-27) ------------- */
+/* rec = Clip1(pred + residual) over whole planes: pred / rec are sample planes (uint8 or
+ * uint16 like the SAO planes), residual the int16 planes p265_residual_batch produced;
+ * all three share `geom`.  rec may alias pred.                                        */
+int p265_reconstruct_batch(p265_ctx *ctx, const void *pred /* host in */,
+                           const int16_t *residual /* host in */, void *rec /* host out */,
+                           const p265_pic_geom *geom);
+int p265_reconstruct_batch_dev(p265_ctx *ctx, const void *d_pred, const int16_t *d_residual,
+                               void *d_rec, const p265_pic_geom *geom);
+
 /* ---- measurement helpers ------------------------------------------------------- */
 /* Register-resident integer-pipe microbenchmark; kind: 0 IMAD, 1 IADD3, 2 IMAD+IADD3
  * interleaved, 3 DP2A, 4 SHF, 5 DP2A+IADD3.  Returns lane-ops per second.           */

@@ -386,3 +386,11 @@ def inverse_transform_xy(d_xy, log2size, tr_type, bit_depth):
     d = np.asarray(d_xy, dtype=I64)
     return np.swapaxes(inverse_transform_yx(np.swapaxes(d, -1, -2), log2size, tr_type,
                                             bit_depth), -1, -2)
+
+
+# ------------------------------------------------------------------ reconstruction
+def reconstruct(pred, res, bit_depth):
+    """8.6.7 picture construction prior to in-loop filtering == reconstruction.py:23-25:
+    Clip1(predSamples + resSamples).  PINNED against the reference's own
+    reconstruction.reconstruction (tests/test_oracle.py, through the shim)."""
+    return np.clip(np.asarray(pred, dtype=I64) + np.asarray(res, dtype=I64), 0, (1 << bit_depth) - 1)

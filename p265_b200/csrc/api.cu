@@ -360,6 +360,36 @@ int p265_sao_batch(p265_ctx *ctx, const void *rec, void *out, const p265_pic_geo
     return P265_OK;
 }
 
+int p265_reconstruct_batch_dev(p265_ctx *ctx, const void *d_pred, const int16_t *d_residual, void *d_rec,
+                               const p265_pic_geom *geom) {
+    if (!ctx || !d_pred || !d_residual || !d_rec) return set_error(P265_EINVAL, "p265_reconstruct_batch_dev: NULL argument");
+    int rc = check_geom(geom, 16);  // 16-byte rows for both the uint8 and the int16 planes
+    if (rc) return rc;
+    P265_CUDA(cudaSetDevice(ctx->device));
+    return launch_recon(ctx, d_pred, d_residual, d_rec, geom);
+}
+
+int p265_reconstruct_batch(p265_ctx *ctx, const void *pred, const int16_t *residual, void *rec,
+                           const p265_pic_geom *geom) {
+    if (!ctx || !pred || !residual || !rec) return set_error(P265_EINVAL, "p265_reconstruct_batch: NULL argument");
+    int rc = check_geom(geom, 16);
+    if (rc) return rc;
+    P265_CUDA(cudaSetDevice(ctx->device));
+    const int bytes = (geom->bit_depth_y > 8 || geom->bit_depth_c > 8) ? 2 : 1;
+    const size_t elems = (size_t)geom->pic_stride * geom->n_pics;
+    void *d_pred, *d_res, *d_rec;
+    if ((rc = ensure(ctx, 2, elems * bytes, &d_pred))) return rc;
+    if ((rc = ensure(ctx, 4, elems * 2, &d_res))) return rc;
+    if ((rc = ensure(ctx, 6, elems * bytes, &d_rec))) return rc;
+    P265_CUDA(cudaMemcpyAsync(d_pred, pred, elems * bytes, cudaMemcpyHostToDevice, ctx->stream));
+    P265_CUDA(cudaMemcpyAsync(d_res, residual, elems * 2, cudaMemcpyHostToDevice, ctx->stream));
+    P265_CUDA(cudaMemcpyAsync(d_rec, d_pred, elems * bytes, cudaMemcpyDeviceToDevice, ctx->stream));  // padding
+    if ((rc = launch_recon(ctx, d_pred, (const int16_t *)d_res, d_rec, geom))) return rc;
+    P265_CUDA(cudaMemcpyAsync(rec, d_rec, elems * bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    P265_CUDA(cudaStreamSynchronize(ctx->stream));
+    return P265_OK;
+}
+
 int p265_int_peak(p265_ctx *ctx, int kind, double *ops_per_s, double *ms) {
     if (!ctx || !ops_per_s || !ms) return set_error(P265_EINVAL, "p265_int_peak: NULL argument");
     P265_CUDA(cudaSetDevice(ctx->device));

@@ -38,6 +38,7 @@ int launch_ref_literal(p265_ctx *ctx, const p265_tu_desc *d_tus, int n_tus, cons
 int launch_idct1d(p265_ctx *ctx, const int32_t *d_x, int log2size, int tr_type, int mode, int32_t *d_y);
 int launch_sao(p265_ctx *ctx, const void *d_rec, void *d_out, const p265_pic_geom *g, int ctb_log2,
                const p265_sao_ctb *d_params, const uint8_t *d_no_filter);
+int launch_recon(p265_ctx *ctx, const void *d_pred, const int16_t *d_res, void *d_rec, const p265_pic_geom *g);
 int run_int_peak(p265_ctx *ctx, int kind, double *ops_per_s, double *ms);
 
 }  // namespace p265

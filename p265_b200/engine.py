@@ -144,6 +144,27 @@ class Engine:
             self._ctx, C.c_void_p(d_rec), C.c_void_p(d_out), C.byref(gs), int(ctb_log2),
             C.c_void_p(d_params), C.c_void_p(d_no_filter) if d_no_filter else None))
 
+    # ------------------------------------------------------------- reconstruction
+    def reconstruct(self, pred: np.ndarray, residual: np.ndarray, geom: PicGeom,
+                    out: np.ndarray | None = None) -> np.ndarray:
+        """rec = Clip1(pred + residual) over whole planes (reconstruction.py:4-27)."""
+        dtype = np.uint8 if max(geom.bit_depth_y, geom.bit_depth_c) <= 8 else np.uint16
+        pred = _lib.as_array(pred, dtype).reshape(-1)
+        res = _lib.as_array(residual, np.int16).reshape(-1)
+        if pred.size < geom.total_elems() or res.size < geom.total_elems():
+            raise ValueError("pred / residual buffers smaller than the geometry")
+        if out is None:
+            out = np.empty_like(pred)
+        gs = _lib.geom_struct(geom)
+        _lib.check(self._lib.p265_reconstruct_batch(self._ctx, _lib.ptr(pred), _lib.ptr(res), _lib.ptr(out),
+                                                    C.byref(gs)))
+        return out
+
+    def reconstruct_dev(self, d_pred: int, d_residual: int, d_rec: int, geom: PicGeom):
+        gs = _lib.geom_struct(geom)
+        _lib.check(self._lib.p265_reconstruct_batch_dev(self._ctx, C.c_void_p(d_pred), C.c_void_p(d_residual),
+                                                        C.c_void_p(d_rec), C.byref(gs)))
+
     # ---------------------------------------------------------------- measurement
     def int_peak(self, kind: int):
         ops, ms = C.c_double(), C.c_double()

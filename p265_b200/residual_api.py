@@ -229,3 +229,30 @@ def inverse_transform_1d(x, log2size, tr_type):
     """One-dimensional transform (8.6.4.2): y[i] = sum_j transMatrix[j][i] * x[j]; in
     MODE "ref_literal" the reference's transposed indexing (transform.py:81,85)."""
     return get_engine().idct_1d(x, log2size, tr_type, as_written=(MODE == "ref_literal")).astype(np.int64)
+
+
+def reconstruction(pu, x0, y0, log2size):
+    """reconstruction.reconstruction(pu, x0, y0, log2size) (reconstruction.py:4-27):
+    reconstructed = Clip1(predicted + transformed) on the TB window of the PU arrays, in
+    place; returns the window like the reference.  One small GPU call per TB; whole
+    pictures go through Engine.reconstruct (p265_reconstruct_batch)."""
+    if not 2 <= int(log2size) <= 5:
+        raise ValueError("log2size must be in 2..5")
+    n = 1 << log2size
+    sx, sy = x0 - pu.origin_x, y0 - pu.origin_y
+    pred = pu.predicted_samples[sx:sx + n, sy:sy + n]
+    res = pu.transformed_samples[sx:sx + n, sy:sy + n]
+    rec = pu.reconstructed_samples[sx:sx + n, sy:sy + n]
+    bdy, bdc = _bit_depths(pu)
+    geom = _GEOM.get((bdy, bdc))
+    if geom is None:
+        geom = _GEOM[(bdy, bdc)] = PicGeom(64, 64, 1, bdy, bdc)
+    dtype = np.uint8 if max(bdy, bdc) <= 8 else np.uint16
+    bd = bdy if pu.c_idx == 0 else bdc
+    pbuf = np.zeros(geom.total_elems(), dtype=dtype)
+    rbuf = np.zeros(geom.total_elems(), dtype=np.int16)
+    geom.plane_view(pbuf, 0, pu.c_idx)[:n, :n] = np.clip(np.asarray(pred).T, 0, (1 << bd) - 1)
+    geom.plane_view(rbuf, 0, pu.c_idx)[:n, :n] = np.clip(np.asarray(res).T, -32768, 32767)
+    out = get_engine().reconstruct(pbuf, rbuf, geom)
+    rec[...] = geom.plane_view(out, 0, pu.c_idx)[:n, :n].T
+    return rec

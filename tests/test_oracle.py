@@ -304,3 +304,22 @@ def test_c_sao_no_filter_equals_numpy(c_oracle):
                                    p["band_pos"][..., c], p["eo_class"][..., c], p["offset_val"][..., c, :],
                                    ctb_avail=p["avail"], no_filter=nf[0], no_filter_log2=2 if c else 3)
         assert np.array_equal(geom.plane_view(out, 0, c), want), c
+
+
+@pytest.mark.skipif(not refshim.reference_available(), reason="/root/reference not mounted")
+def test_reconstruct_pinned_by_reference_function():
+    """oracle.reconstruct == the reference's own reconstruction.reconstruction."""
+    import types
+    ns = refshim.load()
+    rng = np.random.default_rng(17)
+    for bd, c_idx in ((8, 0), (10, 1), (8, 2)):
+        n = 8
+        pred = rng.integers(0, 1 << bd, (n, n))
+        res = rng.integers(-1500, 1500, (n, n))
+        sps = types.SimpleNamespace(bit_depth_y=bd, bit_depth_c=bd)
+        pu = types.SimpleNamespace(c_idx=c_idx, origin_x=0, origin_y=0,
+                                   cu=types.SimpleNamespace(ctx=types.SimpleNamespace(sps=sps)),
+                                   predicted_samples=pred.copy(), transformed_samples=res.copy(),
+                                   reconstructed_samples=np.zeros((n, n), np.int64))
+        ns.reconstruction.reconstruction(pu=pu, x0=0, y0=0, log2size=3)
+        assert np.array_equal(pu.reconstructed_samples, so.reconstruct(pred, res, bd))

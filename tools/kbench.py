@@ -91,5 +91,25 @@ def main():
                                                                  b / (ms * 1e-3) / 1e9 / 6554.9), flush=True)
 
 
+    # reconstruction: 6 B/sample at 10 bits (pred 2 + residual 2 in, rec 2 out)
+    d_pred = to_dev(rec)
+    d_res = torch.zeros(geom.total_elems() * 2, dtype=torch.uint8, device=dev)
+    d_out = torch.empty_like(d_pred)
+    for _ in range(3):
+        eng.reconstruct_dev(d_pred.data_ptr(), d_res.data_ptr(), d_out.data_ptr(), geom)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.reps):
+            eng.reconstruct_dev(d_pred.data_ptr(), d_res.data_ptr(), d_out.data_ptr(), geom)
+        e1.record(stream)
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / args.reps
+    b = 6 * geom.n_pics * (geom.width * geom.height * 3 // 2)
+    print("%-34s %8.4f ms  %7.1f GB/s alg (%.3f of 6555)" % ("reconstruct (pred + residual)", ms,
+                                                             b / (ms * 1e-3) / 1e9, b / (ms * 1e-3) / 1e9 / 6554.9))
+
+
 if __name__ == "__main__":
     main()
