@@ -179,55 +179,77 @@ __device__ __forceinline__ void run_bin8(const KernelArgs &a, int gw, int stride
     cp_async_wait<0>();
 }
 
-// 4x4 bin: 32 TBs per item, the lane's 32 bytes go straight to registers; descriptor and
-// coefficients of the next item are loaded before the current one is transformed.
+// 4x4 bin: 32 TBs per item, one per lane.  Three-stage cp.async pipeline in lane-private
+// shared memory: the 32 bytes of coefficients of item k+2 and the descriptor of item k+3
+// are in flight while item k is transformed in registers (the bin is latency-bound: every
+// TB is only 32 + 16 bytes of input).
+constexpr int kBin4Stages = 3;
+constexpr int kBin4WarpBytes = kBin4Stages * 32 * 32 + 4 * 32 * 16;  // tiles + 4-slot descriptor ring = 5120
+
+__device__ __forceinline__ int tb4_slot_off(int lane, int half) {
+    // 32-byte lane slots; the two 16-byte halves are swapped for odd lane quads so that a
+    // quarter-warp's 128-bit reads hit distinct banks
+    return lane * 32 + ((half ^ ((lane >> 2) & 1)) << 4);
+}
+
 template <int SF>
-__device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride, int lane) {
+__device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride, int lane, unsigned char *wbase) {
     const int n_tb = a.n_tb[3], first = a.first_tb[3];
     const int n_items = (n_tb + 31) >> 5;
     if (gw >= n_items) return;
-    auto load_w = [&](const uint4 d, bool valid, uint32_t (&w)[8]) {
-        if (!valid) return;
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.coeffs + (size_t)d.z * 16);
-        const uint4 v0 = src[0], v1 = src[1];
-        w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w;
-        w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+    unsigned char *tiles = wbase;                                                     // [stage][lane][32 B]
+    uint4 *ring = reinterpret_cast<uint4 *>(wbase + kBin4Stages * 1024) + lane;      // slot s at ring[32 * s]
+    auto desc_async = [&](int item, int slot) {
+        const int i = item * 32 + lane;
+        if (item < n_items && i < n_tb) copy16_async(&ring[32 * slot], &a.tus[first + i]);
     };
-    bool v_cur = gw * 32 + lane < n_tb, v_next = false;
-    uint4 d_cur = load_desc(a, first + gw * 32 + lane, v_cur), d_next = make_uint4(0, 0, 0, 0);
-    uint32_t w_cur[8] = {0, 0, 0, 0, 0, 0, 0, 0}, w_next[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    load_w(d_cur, v_cur, w_cur);
-    if (gw + stride < n_items) {
-        v_next = (gw + stride) * 32 + lane < n_tb;
-        d_next = load_desc(a, first + (gw + stride) * 32 + lane, v_next);
-    }
-#pragma unroll 1
-    for (int it = gw; it < n_items; it += stride) {
-        bool v_nn = false;
-        uint4 d_nn = make_uint4(0, 0, 0, 0);
-        if (it + stride < n_items) {
-            load_w(d_next, v_next, w_next);  // descriptor arrived during the previous item
-            if (it + 2 * stride < n_items) {
-                v_nn = (it + 2 * stride) * 32 + lane < n_tb;
-                d_nn = load_desc(a, first + (it + 2 * stride) * 32 + lane, v_nn);
-            }
+    auto tile_async = [&](int item, const uint4 d, int stage) {
+        const int i = item * 32 + lane;
+        if (item < n_items && i < n_tb) {
+            const int16_t *src = a.coeffs + (size_t)d.z * 16;
+            unsigned char *dst = tiles + stage * 1024;
+            copy16_async(dst + tb4_slot_off(lane, 0), src);
+            copy16_async(dst + tb4_slot_off(lane, 1), src + 8);
         }
-        const TbParams t = make_params(a, d_cur, v_cur);
-        const bool slow = __any_sync(0xffffffffu, t.lsh != 0);
-        if (slow) tb4_lane<SF, true>(t, w_cur);
-        else tb4_lane<SF, false>(t, w_cur);
-        d_cur = d_next; v_cur = v_next;
-        d_next = d_nn; v_next = v_nn;
-#pragma unroll
-        for (int i = 0; i < 8; i++) w_cur[i] = w_next[i];
+    };
+    // cp.async groups: G0 = {tile 0}, G_j = {tile j, descriptor j+2} for j >= 1.  At item k
+    // all groups but the newest (G_{k+1}) are complete: tile k and descriptors <= k+2.
+    {   // prologue: descriptors 0..2 by plain loads (paid once per warp and bin)
+        for (int j = 0; j < 3; j++) {
+            const int i = (gw + j * stride) * 32 + lane;
+            ring[32 * j] = load_desc(a, first + i, gw + j * stride < n_items && i < n_tb);
+        }
+        tile_async(gw, ring[0], 0);
+        cp_async_commit();
+        tile_async(gw + stride, ring[32], 1);
+        desc_async(gw + 3 * stride, 3);
+        cp_async_commit();
     }
+    int k = 0;  // item counter: tile stage k % 3, descriptor slot k % 4
+#pragma unroll 1
+    for (int it = gw; it < n_items; it += stride, k++) {
+        cp_async_wait<1>();
+        const bool valid = it * 32 + lane < n_tb;
+        const int st = k % kBin4Stages;
+        const uint4 d_cur = ring[32 * (k & 3)];  // read before its slot is refilled below
+        tile_async(it + 2 * stride, ring[32 * ((k + 2) & 3)], (k + 2) % kBin4Stages);
+        desc_async(it + 4 * stride, k & 3);
+        cp_async_commit();
+        const TbParams t = make_params(a, d_cur, valid);
+        uint32_t w[8];
+        {
+            const uint4 v0 = *reinterpret_cast<const uint4 *>(tiles + st * 1024 + tb4_slot_off(lane, 0));
+            const uint4 v1 = *reinterpret_cast<const uint4 *>(tiles + st * 1024 + tb4_slot_off(lane, 1));
+            w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w;
+            w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+        }
+        const bool slow = __any_sync(0xffffffffu, t.lsh != 0);
+        if (slow) tb4_lane<SF, true>(t, w);
+        else tb4_lane<SF, false>(t, w);
+    }
+    cp_async_wait<0>();
 }
 
-// One kernel instance per size bin (32x32, 16x16, 8x8, 4x4), launched back to back on the
-// context's stream.  A single launch walking all four bins was measured slower: warps
-// reach the bin boundaries at different times, several size paths are then hot at once
-// and the per-SM instruction cache (hit rate 87 % vs 98-99 % per size) becomes the
-// bottleneck.  Persistent warps: warp w handles items w, w + W, w + 2W, ... of its bin.
 // CTAs per SM per bin: 32x32 is shared-memory limited (9.25 KB per warp); 16x16 needs only
 // 5.25 KB per warp and fits 64 registers; 8x8 keeps 64 packed words live per lane; 4x4 is
 // register-only.
@@ -242,7 +264,7 @@ template <int BIN>
 struct BinCfg {
     static constexpr int ctas = BIN == 1 ? P265_CTAS_BIN1 : (BIN == 3 ? P265_CTAS_BIN3 : kCtasPerSm);
     static constexpr int smem =
-        BIN == 3 ? 0
+        BIN == 3 ? kSfcBytes + kWarpsPerCta * kBin4WarpBytes
                  : kSfcBytes + (BIN == 1 ? kWarpsPerCta * (2 * Layout<4>::WARP_BYTES + kDescRingBytes) : kCtaSmemBytes);
 };
 
@@ -266,7 +288,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, BinCfg<BIN>::ctas) residual
     if (BIN == 0) run_bin<5, SF>(a, gw, stride, lane, wbase, smem);
     else if (BIN == 1) run_bin<4, SF>(a, gw, stride, lane, wbase, smem);
     else if (BIN == 2) run_bin8<SF>(a, gw, stride, lane, wbase);
-    else run_bin4<SF>(a, gw, stride, lane);
+    else run_bin4<SF>(a, gw, stride, lane, wbase);
 }
 
 // ---- auxiliary, non-hot kernels ------------------------------------------------------
