@@ -87,6 +87,24 @@ typedef struct p265_sao_ctb {
     uint16_t avail;           /* bit (dy+1)*3+(dx+1): neighbour CTB usable (8.7.3)   */
 } p265_sao_ctb;
 
+/* Deblocking edge map (8.7.2; the reference only parses the control flags, pps.py:121-131,
+ * slice.py:170-179): one uint16 per 8x8 luma block, raster order, (height/8) x (width/8)
+ * per picture.  Bs values are final (filterEdgeFlag, slice_deblocking_filter_disabled_flag
+ * and the picture / slice / tile boundary rules are already folded in by the host).    */
+typedef uint16_t p265_dbk_blk;
+#define P265_DBK_BS_V0 0       /* bits 0-1: Bs of the vertical edge x = 8*bx, rows 8*by .. +3   */
+#define P265_DBK_BS_V1 2       /* bits 2-3: same edge, rows 8*by+4 .. +7                        */
+#define P265_DBK_BS_H0 4       /* bits 4-5: Bs of the horizontal edge y = 8*by, cols 8*bx .. +3 */
+#define P265_DBK_BS_H1 6       /* bits 6-7: same edge, cols 8*bx+4 .. +7                        */
+#define P265_DBK_QP_SHIFT 8    /* bits 8-14: QpY of the CU (cu.py:566), 7-bit two's complement  */
+#define P265_DBK_NO_FILTER 0x8000u /* pcm + pcm_loop_filter_disabled / cu_transquant_bypass     */
+
+/* Per-CTB deblocking parameters: the offsets of the slice the CTB belongs to
+ * (slice_beta_offset_div2, slice_tc_offset_div2) and the PPS chroma QP offsets (cQpPicOffset). */
+typedef struct p265_dbk_ctb {
+    int8_t beta_offset_div2, tc_offset_div2, cb_qp_offset, cr_qp_offset;
+} p265_dbk_ctb;
+
 #define P265_SF_BYTES 4064 /* ScalingFactor table: [sizeId][matrixId][y][x] uint8    */
 
 #define P265_RES_ZERO_FILL 1 /* clear the planes first (TBs do not cover them)       */
@@ -155,6 +173,15 @@ int p265_reconstruct_batch(p265_ctx *ctx, const void *pred /* host in */,
                            const p265_pic_geom *geom);
 int p265_reconstruct_batch_dev(p265_ctx *ctx, const void *d_pred, const int16_t *d_residual,
                                void *d_rec, const p265_pic_geom *geom);
+
+/* ---- deblocking (8.7.2) ----------------------------------- */
+/* In place on reconstructed sample planes (same element type rule as SAO).  blk: n_pics *
+ * (height/8) * (width/8) edge-map entries; ctb: n_pics * ctbs_h * ctbs_w records.
+ * width and height must be multiples of 8.                                              */
+int p265_deblock_batch(p265_ctx *ctx, void *planes /* host in/out */, const p265_pic_geom *geom,
+                       int ctb_log2, const p265_dbk_blk *blk, const p265_dbk_ctb *ctb);
+int p265_deblock_batch_dev(p265_ctx *ctx, void *d_planes, const p265_pic_geom *geom, int ctb_log2,
+                           const p265_dbk_blk *d_blk, const p265_dbk_ctb *d_ctb);
 
 /* ---- measurement helpers ------------------------------------------------------- */
 /* Register-resident integer-pipe microbenchmark; kind: 0 IMAD, 1 IADD3, 2 IMAD+IADD3

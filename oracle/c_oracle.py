@@ -93,3 +93,14 @@ def sao_batch(rec, geom, ctb_log2, params, no_filter=None) -> np.ndarray:
     gs = geom_struct(geom)
     lib().oracle_sao_batch(_p(rec), _p(out), C.byref(gs), C.c_int(ctb_log2), _p(params), _p(nf))
     return out
+
+
+def deblock_batch(planes, geom, ctb_log2, blk, ctb) -> np.ndarray:
+    """8.7.2 on a batch (returns a filtered copy of the flat plane buffer)."""
+    out = np.ascontiguousarray(planes).copy()
+    blk = np.ascontiguousarray(blk, dtype=np.uint16)
+    ctb = np.ascontiguousarray(ctb)
+    gs = geom_struct(geom)
+    if lib().oracle_deblock_batch(_p(out), C.byref(gs), C.c_int(ctb_log2), _p(blk), _p(ctb)) != 0:
+        raise ValueError("oracle_deblock_batch: bad geometry")
+    return out

@@ -285,3 +285,140 @@ int oracle_sao_batch(const void *rec, void *out, const p265_pic_geom *g, int ctb
         }
     return 0;
 }
+
+/* --------------------------------------------------------------------- deblocking */
+/* H.265 8.7.2 restated from the standard (the reference has no deblocking filter; only its
+ * control flags are parsed, pps.py:121-131, slice.py:170-179).  Classic two passes over the
+ * whole picture: every vertical edge, then every horizontal edge on the result.  Pinned by
+ * the libavcodec decode of sanity.bin (tests/test_decode_sanity.py).                       */
+static const uint8_t k_beta[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15,
+                                   16, 17, 18, 20, 22, 24, 26, 28, 30, 32, 34, 36, 38, 40, 42, 44, 46, 48, 50, 52,
+                                   54, 56, 58, 60, 62, 64};
+static const uint8_t k_tc[54] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2,
+                                 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 5, 5, 6, 6, 7, 8, 9, 10, 11, 13, 14, 16, 18, 20, 22, 24};
+static int qpc_of(int qpi) {
+    static const int t[14] = {29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37, 37};
+    return qpi < 30 ? qpi : (qpi >= 44 ? qpi - 6 : t[qpi - 30]);
+}
+
+typedef struct {
+    void *pix; const p265_pic_geom *g; int ctb_log2; const p265_dbk_blk *blk; const p265_dbk_ctb *ctb;
+    int p, c, vertical;
+} dbk_job;
+
+static inline int blk_qp(uint16_t e) { int q = (e >> P265_DBK_QP_SHIFT) & 0x7f; return q >= 64 ? q - 128 : q; }
+
+/* one 4-sample segment; (x, y) first q0 sample in the plane of component c */
+static void dbk_segment(const dbk_job *j, int x, int y) {
+    const p265_pic_geom *g = j->g;
+    int c = j->c, v = j->vertical;
+    int bytes = (g->bit_depth_y > 8 || g->bit_depth_c > 8) ? 2 : 1;
+    int w8 = g->width / 8, h8 = g->height / 8;
+    int ctb = 1 << j->ctb_log2;
+    int ctbs_w = (g->width + ctb - 1) / ctb, ctbs_h = (g->height + ctb - 1) / ctb;
+    int xl = c ? x * 2 : x, yl = c ? y * 2 : y;             /* luma position of q0 */
+    int xp = v ? xl - 1 : xl, yp = v ? yl : yl - 1;         /* luma position of p0 */
+    const p265_dbk_blk *bp = j->blk + (size_t)j->p * w8 * h8;
+    uint16_t eq = bp[(yl >> 3) * w8 + (xl >> 3)], ep = bp[(yp >> 3) * w8 + (xp >> 3)];
+    int bs = v ? (eq >> ((yl & 4) ? P265_DBK_BS_V1 : P265_DBK_BS_V0)) & 3
+               : (eq >> ((xl & 4) ? P265_DBK_BS_H1 : P265_DBK_BS_H0)) & 3;
+    if (bs == 0 || (c && bs != 2)) return;
+    const p265_dbk_ctb *par = &j->ctb[((size_t)j->p * ctbs_h + (yl >> j->ctb_log2)) * ctbs_w + (xl >> j->ctb_log2)];
+    int no_p = (ep & P265_DBK_NO_FILTER) != 0, no_q = (eq & P265_DBK_NO_FILTER) != 0;
+    int qpl = (blk_qp(eq) + blk_qp(ep) + 1) >> 1;
+    int stride = c ? g->stride_c : g->stride_y;
+    int bd = c ? g->bit_depth_c : g->bit_depth_y;
+    int maxv = (1 << bd) - 1;
+    size_t base = (size_t)j->p * g->pic_stride + g->plane_off[c];
+    ptrdiff_t across = v ? 1 : stride, along = v ? stride : 1;
+    size_t q0 = base + (size_t)y * stride + x;
+#define PX(side, i, k) sample_at(j->pix, bytes, (size_t)((ptrdiff_t)q0 + (side) * across * ((i) + ((side) < 0)) + (k) * along))
+#define P(i, k) PX(-1, i, k)
+#define Q(i, k) PX(1, i, k)
+#define PUTP(i, k, val) sample_put(j->pix, bytes, (size_t)((ptrdiff_t)q0 - across * ((i) + 1) + (k) * along), (int)(val))
+#define PUTQ(i, k, val) sample_put(j->pix, bytes, (size_t)((ptrdiff_t)q0 + across * (i) + (k) * along), (int)(val))
+    if (c) {
+        int qpc = qpc_of(qpl + (c == 1 ? par->cb_qp_offset : par->cr_qp_offset));
+        int tc = k_tc[clip3(0, 53, qpc + 2 + (par->tc_offset_div2 * 2))] << (bd - 8);
+        for (int k = 0; k < 4; k++) {
+            int p0 = P(0, k), p1 = P(1, k), q0v = Q(0, k), q1 = Q(1, k);
+            int d = (int)clip3(-tc, tc, ((((q0v - p0) * 4) + p1 - q1 + 4) >> 3));
+            if (!no_p) PUTP(0, k, clip3(0, maxv, p0 + d));
+            if (!no_q) PUTQ(0, k, clip3(0, maxv, q0v - d));
+        }
+        return;
+    }
+    int beta = k_beta[clip3(0, 51, qpl + par->beta_offset_div2 * 2)] << (bd - 8);
+    int tc = k_tc[clip3(0, 53, qpl + 2 * (bs - 1) + par->tc_offset_div2 * 2)] << (bd - 8);
+    int dp0 = abs(P(2, 0) - 2 * P(1, 0) + P(0, 0)), dp3 = abs(P(2, 3) - 2 * P(1, 3) + P(0, 3));
+    int dq0 = abs(Q(2, 0) - 2 * Q(1, 0) + Q(0, 0)), dq3 = abs(Q(2, 3) - 2 * Q(1, 3) + Q(0, 3));
+    int dpq0 = dp0 + dq0, dpq3 = dp3 + dq3, dp = dp0 + dp3, dq = dq0 + dq3;
+    if (dpq0 + dpq3 >= beta) return;
+    int s0 = 2 * dpq0 < (beta >> 2) && abs(P(3, 0) - P(0, 0)) + abs(Q(0, 0) - Q(3, 0)) < (beta >> 3) &&
+             abs(P(0, 0) - Q(0, 0)) < ((5 * tc + 1) >> 1);
+    int s3 = 2 * dpq3 < (beta >> 2) && abs(P(3, 3) - P(0, 3)) + abs(Q(0, 3) - Q(3, 3)) < (beta >> 3) &&
+             abs(P(0, 3) - Q(0, 3)) < ((5 * tc + 1) >> 1);
+    int side = (beta + (beta >> 1)) >> 3;
+    int dep = dp < side, deq = dq < side;
+    for (int k = 0; k < 4; k++) {
+        int p0 = P(0, k), p1 = P(1, k), p2 = P(2, k), p3 = P(3, k);
+        int q0v = Q(0, k), q1 = Q(1, k), q2 = Q(2, k), q3 = Q(3, k);
+        if (s0 && s3) {
+            if (!no_p) {
+                PUTP(0, k, clip3(p0 - 2 * tc, p0 + 2 * tc, (p2 + 2 * p1 + 2 * p0 + 2 * q0v + q1 + 4) >> 3));
+                PUTP(1, k, clip3(p1 - 2 * tc, p1 + 2 * tc, (p2 + p1 + p0 + q0v + 2) >> 2));
+                PUTP(2, k, clip3(p2 - 2 * tc, p2 + 2 * tc, (2 * p3 + 3 * p2 + p1 + p0 + q0v + 4) >> 3));
+            }
+            if (!no_q) {
+                PUTQ(0, k, clip3(q0v - 2 * tc, q0v + 2 * tc, (p1 + 2 * p0 + 2 * q0v + 2 * q1 + q2 + 4) >> 3));
+                PUTQ(1, k, clip3(q1 - 2 * tc, q1 + 2 * tc, (p0 + q0v + q1 + q2 + 2) >> 2));
+                PUTQ(2, k, clip3(q2 - 2 * tc, q2 + 2 * tc, (p0 + q0v + q1 + 3 * q2 + 2 * q3 + 4) >> 3));
+            }
+        } else {
+            int d = (9 * (q0v - p0) - 3 * (q1 - p1) + 8) >> 4;
+            if (abs(d) >= tc * 10) continue;
+            d = (int)clip3(-tc, tc, d);
+            if (!no_p) {
+                PUTP(0, k, clip3(0, maxv, p0 + d));
+                if (dep) PUTP(1, k, clip3(0, maxv, p1 + clip3(-(tc >> 1), tc >> 1, (((p2 + p0 + 1) >> 1) - p1 + d) >> 1)));
+            }
+            if (!no_q) {
+                PUTQ(0, k, clip3(0, maxv, q0v - d));
+                if (deq) PUTQ(1, k, clip3(0, maxv, q1 + clip3(-(tc >> 1), tc >> 1, (((q2 + q0v + 1) >> 1) - q1 - d) >> 1)));
+            }
+        }
+    }
+#undef PX
+#undef P
+#undef Q
+#undef PUTP
+#undef PUTQ
+}
+
+/* unit u = one row of 4-sample segments (vertical pass) or one edge row (horizontal pass) */
+static void dbk_units(int64_t lo, int64_t hi, void *arg) {
+    const dbk_job *j = (const dbk_job *)arg;
+    int w = j->c ? j->g->width / 2 : j->g->width, h = j->c ? j->g->height / 2 : j->g->height;
+    for (int64_t u = lo; u < hi; u++) {
+        if (j->vertical) {
+            for (int x = 8; x < w; x += 8) dbk_segment(j, x, (int)u * 4);
+        } else {
+            int y = ((int)u + 1) * 8;
+            if (y >= h) continue;
+            for (int x = 0; x < w; x += 4) dbk_segment(j, x, y);
+        }
+    }
+}
+
+int oracle_deblock_batch(void *planes, const p265_pic_geom *g, int ctb_log2, const p265_dbk_blk *blk,
+                         const p265_dbk_ctb *ctb) {
+    if (g->width % 8 || g->height % 8) return -1;
+    for (int p = 0; p < g->n_pics; p++)
+        for (int vertical = 1; vertical >= 0; vertical--)
+            for (int c = 0; c < 3; c++) {
+                dbk_job j = {planes, g, ctb_log2, blk, ctb, p, c, vertical};
+                int h = c ? g->height / 2 : g->height;
+                parallel_for(vertical ? h / 4 : h / 8, dbk_units, &j);
+            }
+    return 0;
+}

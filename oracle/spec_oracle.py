@@ -394,3 +394,171 @@ def reconstruct(pred, res, bit_depth):
     Clip1(predSamples + resSamples).  PINNED against the reference's own
     reconstruction.reconstruction (tests/test_oracle.py, through the shim)."""
     return np.clip(np.asarray(pred, dtype=I64) + np.asarray(res, dtype=I64), 0, (1 << bit_depth) - 1)
+
+
+# --------------------------------------------------------------------------- deblocking
+# H.265 (04/2013) 8.7.2.  The reference has no deblocking filter (only the control flags
+# are parsed, pps.py:121-131, slice.py:170-179; SURVEY.md 8(f) rank 3).  Inputs are the
+# packed edge map the product's host side builds (picture.py DBK_*): per 8x8 luma block
+# the Bs of the two edges starting in it, the CU's QpY and the no-filter bit; per CTB the
+# slice's beta / tc offsets and the PPS chroma QP offsets.  Pinned end to end by the
+# libavcodec decode of sanity.bin (tests/golden/sanity_ffmpeg.npz).
+BETA_TABLE = np.array([0] * 16 + list(range(6, 19)) + list(range(20, 66, 2)), dtype=I64)     # Table 8-11
+TC_TABLE = np.array([0] * 18 + [1] * 9 + [2] * 4 + [3] * 4 + [4] * 3 + [5, 5, 6, 6, 7, 8, 9, 10, 11, 13,
+                    14, 16, 18, 20, 22, 24], dtype=I64)
+assert BETA_TABLE.size == 52 and TC_TABLE.size == 54
+_QPC_TABLE = [29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37, 37]                         # Table 8-10
+
+
+def chroma_qp(qpi: int) -> int:
+    """QpC as a function of qPi for ChromaArrayType == 1 (Table 8-10)."""
+    if qpi < 30:
+        return qpi
+    if qpi >= 44:
+        return qpi - 6
+    return _QPC_TABLE[qpi - 30]
+
+
+def _blk_bs(blk, vertical, x, y):
+    """Bs of the edge segment whose first q sample is luma (x, y)."""
+    e = int(blk[y >> 3, x >> 3])
+    if vertical:
+        return (e >> (2 if (y & 4) else 0)) & 3
+    return (e >> (6 if (x & 4) else 4)) & 3
+
+
+def _blk_qp(blk, x, y):
+    q = (int(blk[y >> 3, x >> 3]) >> 8) & 0x7F
+    return q - 128 if q >= 64 else q
+
+
+def _blk_nofilter(blk, x, y):
+    return bool(int(blk[y >> 3, x >> 3]) & 0x8000)
+
+
+def _deblock_luma_segment(pix, blk, ctb, ctb_log2, bit_depth, vertical, x0, y0):
+    """One 4-sample luma edge segment (8.7.2.5.3, .6, .7).  pix: int64 [row][col], in place.
+    (x0, y0) = first q0 sample; p samples lie to the left (vertical edge) or above."""
+    bs = _blk_bs(blk, vertical, x0, y0)
+    if bs == 0:
+        return
+    dx, dy = (1, 0) if vertical else (0, 1)          # across the edge
+    sx, sy = (0, 1) if vertical else (1, 0)          # along the edge
+
+    def P(i, k):
+        return int(pix[y0 - (i + 1) * dy + k * sy, x0 - (i + 1) * dx + k * sx])
+
+    def Q(i, k):
+        return int(pix[y0 + i * dy + k * sy, x0 + i * dx + k * sx])
+
+    qp_q, qp_p = _blk_qp(blk, x0, y0), _blk_qp(blk, x0 - dx, y0 - dy)
+    qpl = (qp_q + qp_p + 1) >> 1
+    par = ctb[y0 >> ctb_log2, x0 >> ctb_log2]
+    beta = int(BETA_TABLE[min(max(qpl + (int(par["beta_offset_div2"]) << 1), 0), 51)]) << (bit_depth - 8)
+    tc = int(TC_TABLE[min(max(qpl + 2 * (bs - 1) + (int(par["tc_offset_div2"]) << 1), 0), 53)]) << (bit_depth - 8)
+    dp0 = abs(P(2, 0) - 2 * P(1, 0) + P(0, 0))
+    dp3 = abs(P(2, 3) - 2 * P(1, 3) + P(0, 3))
+    dq0 = abs(Q(2, 0) - 2 * Q(1, 0) + Q(0, 0))
+    dq3 = abs(Q(2, 3) - 2 * Q(1, 3) + Q(0, 3))
+    dpq0, dpq3, dp, dq = dp0 + dq0, dp3 + dq3, dp0 + dp3, dq0 + dq3
+    d = dpq0 + dpq3
+    if d >= beta:
+        return
+
+    def d_sam(dpq, k):
+        return (dpq < (beta >> 2) and abs(P(3, k) - P(0, k)) + abs(Q(0, k) - Q(3, k)) < (beta >> 3)
+                and abs(P(0, k) - Q(0, k)) < ((5 * tc + 1) >> 1))
+
+    strong = d_sam(2 * dpq0, 0) and d_sam(2 * dpq3, 3)
+    d_ep = dp < ((beta + (beta >> 1)) >> 3)
+    d_eq = dq < ((beta + (beta >> 1)) >> 3)
+    no_p = _blk_nofilter(blk, x0 - dx, y0 - dy)
+    no_q = _blk_nofilter(blk, x0, y0)
+    mx = (1 << bit_depth) - 1
+
+    def clip3(lo, hi, v):
+        return lo if v < lo else (hi if v > hi else v)
+
+    for k in range(4):
+        p = [P(i, k) for i in range(4)]
+        q = [Q(i, k) for i in range(4)]
+        np_, nq_ = {}, {}
+        if strong:
+            np_[0] = clip3(p[0] - 2 * tc, p[0] + 2 * tc, (p[2] + 2 * p[1] + 2 * p[0] + 2 * q[0] + q[1] + 4) >> 3)
+            np_[1] = clip3(p[1] - 2 * tc, p[1] + 2 * tc, (p[2] + p[1] + p[0] + q[0] + 2) >> 2)
+            np_[2] = clip3(p[2] - 2 * tc, p[2] + 2 * tc, (2 * p[3] + 3 * p[2] + p[1] + p[0] + q[0] + 4) >> 3)
+            nq_[0] = clip3(q[0] - 2 * tc, q[0] + 2 * tc, (p[1] + 2 * p[0] + 2 * q[0] + 2 * q[1] + q[2] + 4) >> 3)
+            nq_[1] = clip3(q[1] - 2 * tc, q[1] + 2 * tc, (p[0] + q[0] + q[1] + q[2] + 2) >> 2)
+            nq_[2] = clip3(q[2] - 2 * tc, q[2] + 2 * tc, (p[0] + q[0] + q[1] + 3 * q[2] + 2 * q[3] + 4) >> 3)
+        else:
+            delta = (9 * (q[0] - p[0]) - 3 * (q[1] - p[1]) + 8) >> 4
+            if abs(delta) < tc * 10:
+                delta = clip3(-tc, tc, delta)
+                np_[0] = clip3(0, mx, p[0] + delta)
+                nq_[0] = clip3(0, mx, q[0] - delta)
+                if d_ep:
+                    dl = clip3(-(tc >> 1), tc >> 1, (((p[2] + p[0] + 1) >> 1) - p[1] + delta) >> 1)
+                    np_[1] = clip3(0, mx, p[1] + dl)
+                if d_eq:
+                    dl = clip3(-(tc >> 1), tc >> 1, (((q[2] + q[0] + 1) >> 1) - q[1] - delta) >> 1)
+                    nq_[1] = clip3(0, mx, q[1] + dl)
+        if not no_p:
+            for i, v in np_.items():
+                pix[y0 - (i + 1) * dy + k * sy, x0 - (i + 1) * dx + k * sx] = v
+        if not no_q:
+            for i, v in nq_.items():
+                pix[y0 + i * dy + k * sy, x0 + i * dx + k * sx] = v
+
+
+def _deblock_chroma_segment(pix, blk, ctb, ctb_log2, bit_depth, vertical, xc, yc, c_idx):
+    """One 4-sample chroma edge segment (8.7.2.5.5, .8); (xc, yc) = first q0 sample in chroma
+    coordinates (4:2:0), edges on the 8-sample chroma grid, only Bs == 2."""
+    xl, yl = xc << 1, yc << 1
+    if _blk_bs(blk, vertical, xl, yl) != 2:
+        return
+    dx, dy = (1, 0) if vertical else (0, 1)
+    sx, sy = (0, 1) if vertical else (1, 0)
+    qp_q, qp_p = _blk_qp(blk, xl, yl), _blk_qp(blk, xl - dx, yl - dy)
+    par = ctb[yl >> ctb_log2, xl >> ctb_log2]
+    off = int(par["cb_qp_offset"] if c_idx == 1 else par["cr_qp_offset"])
+    qpc = chroma_qp(((qp_q + qp_p + 1) >> 1) + off)
+    tc = int(TC_TABLE[min(max(qpc + 2 + (int(par["tc_offset_div2"]) << 1), 0), 53)]) << (bit_depth - 8)
+    no_p = _blk_nofilter(blk, xl - dx, yl - dy)
+    no_q = _blk_nofilter(blk, xl, yl)
+    mx = (1 << bit_depth) - 1
+    for k in range(4):
+        yy, xx = yc + k * sy, xc + k * sx
+        p0, p1 = int(pix[yy - dy, xx - dx]), int(pix[yy - 2 * dy, xx - 2 * dx])
+        q0, q1 = int(pix[yy, xx]), int(pix[yy + dy, xx + dx])
+        delta = min(max((((q0 - p0) << 2) + p1 - q1 + 4) >> 3, -tc), tc)
+        if not no_p:
+            pix[yy - dy, xx - dx] = min(max(p0 + delta, 0), mx)
+        if not no_q:
+            pix[yy, xx] = min(max(q0 - delta, 0), mx)
+
+
+def deblock_picture(planes, blk, ctb, ctb_log2, bit_depth_y, bit_depth_c):
+    """8.7.2 on one 4:2:0 picture: all vertical edges of the picture first, then all
+    horizontal edges with the vertically filtered samples as input.  Returns new planes."""
+    out = [np.asarray(p).astype(I64).copy() for p in planes]
+    h, w = out[0].shape
+    for vertical in (True, False):
+        if vertical:
+            for x in range(8, w, 8):
+                for y in range(0, h, 4):
+                    _deblock_luma_segment(out[0], blk, ctb, ctb_log2, bit_depth_y, True, x, y)
+        else:
+            for y in range(8, h, 8):
+                for x in range(0, w, 4):
+                    _deblock_luma_segment(out[0], blk, ctb, ctb_log2, bit_depth_y, False, x, y)
+        hc, wc = out[1].shape
+        for c in (1, 2):
+            if vertical:
+                for x in range(8, wc, 8):
+                    for y in range(0, hc, 4):
+                        _deblock_chroma_segment(out[c], blk, ctb, ctb_log2, bit_depth_c, True, x, y, c)
+            else:
+                for y in range(8, hc, 8):
+                    for x in range(0, wc, 4):
+                        _deblock_chroma_segment(out[c], blk, ctb, ctb_log2, bit_depth_c, False, x, y, c)
+    return [o.astype(np.asarray(p).dtype) for o, p in zip(out, planes)]

@@ -32,6 +32,17 @@ SAO_CTB = np.dtype([("type", "u1", 3), ("band_pos", "u1", 3), ("eo_class", "u1",
                     ("offset_val", "i1", (3, 4)), ("pad", "u1"), ("avail", "<u2")])
 assert SAO_CTB.itemsize == 24
 
+#: mirrors `p265_dbk_ctb` (4 bytes): deblocking parameters of the slice / PPS a CTB belongs to
+DBK_CTB = np.dtype([("beta_offset_div2", "i1"), ("tc_offset_div2", "i1"),
+                    ("cb_qp_offset", "i1"), ("cr_qp_offset", "i1")])
+assert DBK_CTB.itemsize == 4
+
+# Deblocking edge map: one uint16 per 8x8 luma block (`p265_dbk_blk`, raster order)
+DBK_BS_V0, DBK_BS_V1 = 0, 2      # bits 0-1 / 2-3: Bs of the vertical edge x = 8*bx, rows 0-3 / 4-7
+DBK_BS_H0, DBK_BS_H1 = 4, 6      # bits 4-5 / 6-7: Bs of the horizontal edge y = 8*by, cols 0-3 / 4-7
+DBK_QP_SHIFT = 8                 # bits 8-14: QpY of the CU, 7-bit two's complement
+DBK_NO_FILTER = 0x8000           # bit 15: pcm + pcm_loop_filter_disabled / cu_transquant_bypass
+
 #: all eight neighbouring CTBs usable (bit (dy+1)*3+(dx+1), centre bit unused)
 AVAIL_ALL = 0x1FF
 

@@ -116,29 +116,6 @@ def test_inverse_transform_1d_and_tables(dropin):
     dropin.transform.set_mode("spec")
 
 
-@pytest.fixture(scope="module")
-def parsed_sanity():
-    """sanity.bin parsed by the reference's own parser through the shim that travels to
-    the GPU box (baseline/_ref, generated by __graft_entry__.build())."""
-    if not refshim.shim_available():
-        pytest.skip("baseline/_ref shim not present")
-    wd = tempfile.mkdtemp(prefix="p265_sanity_")
-    ns = refshim.load(wd)
-    args = types.SimpleNamespace(bitstream=os.path.join(refshim.SHIM_DIR, "sanity.bin"),
-                                 skip_syntax_dump=1000, output=None, plot=None)
-    cwd = os.getcwd()
-    os.chdir(wd)
-    try:
-        d = ns.dec.Decoder(args)
-        try:
-            d.decode()
-        except SystemExit:
-            pass
-    finally:
-        os.chdir(cwd)
-    return d.ctx.dpb.images, d.ctx.sps, d.ctx.pps
-
-
 def test_batched_flush_of_parsed_pictures(engine, c_oracle, dropin, parsed_sanity, sanity_batch):
     """Two-pass driver: parse everything with the reference, then one residual launch per
     picture; the per-TB functions afterwards only copy out of the planes."""
