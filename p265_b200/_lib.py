@@ -24,7 +24,8 @@ SYMBOLS = (
     "p265_ctx_destroy", "p265_sync", "p265_sm_count", "p265_launch_count",
     "p265_residual_batch", "p265_residual_batch_dev", "p265_dequant_batch",
     "p265_ref_literal_batch", "p265_idct_1d", "p265_sao_batch", "p265_sao_batch_dev",
-    "p265_reconstruct_batch", "p265_reconstruct_batch_dev", "p265_int_peak",
+    "p265_reconstruct_batch", "p265_reconstruct_batch_dev", "p265_deblock_batch",
+    "p265_deblock_batch_dev", "p265_int_peak",
 )
 
 
@@ -73,6 +74,8 @@ def load():
     lib.p265_sao_batch_dev.argtypes = [vp, vp, vp, C.POINTER(Geom), C.c_int, vp, vp]
     lib.p265_reconstruct_batch.argtypes = [vp, vp, vp, vp, C.POINTER(Geom)]
     lib.p265_reconstruct_batch_dev.argtypes = [vp, vp, vp, vp, C.POINTER(Geom)]
+    lib.p265_deblock_batch.argtypes = [vp, vp, C.POINTER(Geom), C.c_int, vp, vp]
+    lib.p265_deblock_batch_dev.argtypes = [vp, vp, C.POINTER(Geom), C.c_int, vp, vp]
     lib.p265_int_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = lib
     return lib

@@ -390,6 +390,61 @@ int p265_reconstruct_batch(p265_ctx *ctx, const void *pred, const int16_t *resid
     return P265_OK;
 }
 
+static int check_deblock(const p265_pic_geom *geom, int ctb_log2, int *bytes) {
+    *bytes = (geom->bit_depth_y > 8 || geom->bit_depth_c > 8) ? 2 : 1;
+    int rc = check_geom(geom, 8 / *bytes);   // rows start on 8-byte boundaries (half-block loads)
+    if (rc) return rc;
+    if (ctb_log2 < 4 || ctb_log2 > 6) return set_error(P265_EINVAL, "ctb_log2 %d outside 4..6", ctb_log2);
+    if (geom->width % 8 || geom->height % 8)
+        return set_error(P265_EINVAL, "picture size must be a multiple of MinCbSize 8 (got %dx%d)", geom->width,
+                         geom->height);
+    return P265_OK;
+}
+
+int p265_deblock_batch_dev(p265_ctx *ctx, void *d_planes, const p265_pic_geom *geom, int ctb_log2,
+                           const p265_dbk_blk *d_blk, const p265_dbk_ctb *d_ctb) {
+    if (!ctx || !d_planes || !d_blk || !d_ctb || !geom)
+        return set_error(P265_EINVAL, "p265_deblock_batch_dev: NULL argument");
+    int bytes;
+    int rc = check_deblock(geom, ctb_log2, &bytes);
+    if (rc) return rc;
+    P265_CUDA(cudaSetDevice(ctx->device));
+    return launch_deblock(ctx, d_planes, geom, ctb_log2, d_blk, d_ctb);
+}
+
+int p265_deblock_batch(p265_ctx *ctx, void *planes, const p265_pic_geom *geom, int ctb_log2, const p265_dbk_blk *blk,
+                       const p265_dbk_ctb *ctb) {
+    if (!ctx || !planes || !blk || !ctb || !geom) return set_error(P265_EINVAL, "p265_deblock_batch: NULL argument");
+    int bytes;
+    int rc = check_deblock(geom, ctb_log2, &bytes);
+    if (rc) return rc;
+    const int cs = 1 << ctb_log2;
+    const size_t n_blk = (size_t)(geom->width / 8) * (geom->height / 8) * geom->n_pics;
+    const size_t n_ctb = (size_t)((geom->width + cs - 1) / cs) * ((geom->height + cs - 1) / cs) * geom->n_pics;
+    for (size_t i = 0; i < n_blk; i++)
+        if ((blk[i] & 3) == 3 || ((blk[i] >> 2) & 3) == 3 || ((blk[i] >> 4) & 3) == 3 || ((blk[i] >> 6) & 3) == 3)
+            return set_error(P265_EINVAL, "edge map entry %zu holds a boundary strength of 3", i);
+    for (size_t i = 0; i < n_ctb; i++)
+        if (ctb[i].beta_offset_div2 < -6 || ctb[i].beta_offset_div2 > 6 || ctb[i].tc_offset_div2 < -6 ||
+            ctb[i].tc_offset_div2 > 6 || ctb[i].cb_qp_offset < -12 || ctb[i].cb_qp_offset > 12 ||
+            ctb[i].cr_qp_offset < -12 || ctb[i].cr_qp_offset > 12)
+            return set_error(P265_EINVAL, "deblocking parameters of CTB %zu out of range", i);
+    P265_CUDA(cudaSetDevice(ctx->device));
+    const size_t plane_bytes = (size_t)bytes * geom->pic_stride * geom->n_pics;
+    void *d_pix, *d_blk, *d_ctb;
+    if ((rc = ensure(ctx, 2, plane_bytes, &d_pix))) return rc;
+    if ((rc = ensure(ctx, 0, sizeof(p265_dbk_blk) * n_blk, &d_blk))) return rc;
+    if ((rc = ensure(ctx, 7, sizeof(p265_dbk_ctb) * n_ctb, &d_ctb))) return rc;
+    P265_CUDA(cudaMemcpyAsync(d_pix, planes, plane_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    P265_CUDA(cudaMemcpyAsync(d_blk, blk, sizeof(p265_dbk_blk) * n_blk, cudaMemcpyHostToDevice, ctx->stream));
+    P265_CUDA(cudaMemcpyAsync(d_ctb, ctb, sizeof(p265_dbk_ctb) * n_ctb, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = launch_deblock(ctx, d_pix, geom, ctb_log2, (const p265_dbk_blk *)d_blk, (const p265_dbk_ctb *)d_ctb)))
+        return rc;
+    P265_CUDA(cudaMemcpyAsync(planes, d_pix, plane_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    P265_CUDA(cudaStreamSynchronize(ctx->stream));
+    return P265_OK;
+}
+
 int p265_int_peak(p265_ctx *ctx, int kind, double *ops_per_s, double *ms) {
     if (!ctx || !ops_per_s || !ms) return set_error(P265_EINVAL, "p265_int_peak: NULL argument");
     P265_CUDA(cudaSetDevice(ctx->device));

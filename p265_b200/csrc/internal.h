@@ -39,6 +39,8 @@ int launch_idct1d(p265_ctx *ctx, const int32_t *d_x, int log2size, int tr_type, 
 int launch_sao(p265_ctx *ctx, const void *d_rec, void *d_out, const p265_pic_geom *g, int ctb_log2,
                const p265_sao_ctb *d_params, const uint8_t *d_no_filter);
 int launch_recon(p265_ctx *ctx, const void *d_pred, const int16_t *d_res, void *d_rec, const p265_pic_geom *g);
+int launch_deblock(p265_ctx *ctx, void *d_pix, const p265_pic_geom *g, int ctb_log2, const p265_dbk_blk *d_blk,
+                   const p265_dbk_ctb *d_ctb);
 int run_int_peak(p265_ctx *ctx, int kind, double *ops_per_s, double *ms);
 
 }  // namespace p265

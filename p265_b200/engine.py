@@ -13,7 +13,7 @@ import threading
 import numpy as np
 
 from . import _lib
-from .picture import SAO_CTB, SF_BYTES, TU_DESC, PicGeom, ResidualBatch
+from .picture import DBK_CTB, SAO_CTB, SF_BYTES, TU_DESC, PicGeom, ResidualBatch
 
 
 class Engine:
@@ -164,6 +164,33 @@ class Engine:
         gs = _lib.geom_struct(geom)
         _lib.check(self._lib.p265_reconstruct_batch_dev(self._ctx, C.c_void_p(d_pred), C.c_void_p(d_residual),
                                                         C.c_void_p(d_rec), C.byref(gs)))
+
+    # ------------------------------------------------------------------ deblocking
+    def deblock(self, rec: np.ndarray, geom: PicGeom, ctb_log2: int, blk: np.ndarray,
+                ctb: np.ndarray) -> np.ndarray:
+        """Deblocked copy (8.7.2) of reconstructed planes; blk / ctb: the edge map and per-CTB
+        parameters of `deblock_api.edge_map_from_picture`, stacked per picture."""
+        dtype = np.uint8 if max(geom.bit_depth_y, geom.bit_depth_c) <= 8 else np.uint16
+        out = np.array(_lib.as_array(rec, dtype).reshape(-1), copy=True)
+        if out.size < geom.total_elems():
+            raise ValueError("rec buffer smaller than the geometry")
+        if geom.width % 8 or geom.height % 8:
+            raise ValueError("picture size must be a multiple of 8")
+        blk = _lib.as_array(blk, np.uint16).reshape(-1)
+        par = _lib.as_array(ctb, DBK_CTB).reshape(-1)
+        cs = 1 << ctb_log2
+        n_ctb = ((geom.width + cs - 1) // cs) * ((geom.height + cs - 1) // cs) * geom.n_pics
+        if blk.size != (geom.width // 8) * (geom.height // 8) * geom.n_pics or par.size != n_ctb:
+            raise ValueError("edge map / CTB parameter tables do not match the geometry")
+        gs = _lib.geom_struct(geom)
+        _lib.check(self._lib.p265_deblock_batch(self._ctx, _lib.ptr(out), C.byref(gs), int(ctb_log2),
+                                                _lib.ptr(blk), _lib.ptr(par)))
+        return out
+
+    def deblock_dev(self, d_planes: int, geom: PicGeom, ctb_log2: int, d_blk: int, d_ctb: int):
+        gs = _lib.geom_struct(geom)
+        _lib.check(self._lib.p265_deblock_batch_dev(self._ctx, C.c_void_p(d_planes), C.byref(gs), int(ctb_log2),
+                                                    C.c_void_p(d_blk), C.c_void_p(d_ctb)))
 
     # ---------------------------------------------------------------- measurement
     def int_peak(self, kind: int):

@@ -239,3 +239,80 @@ def sao_batch(width: int = 3840, height: int = 2160, bit_depth: int = 10, n_pics
                 buf[q * geom.pic_stride:(q + 1) * geom.pic_stride]
             params[p] = params[q]
     return geom, buf, params
+
+
+# ------------------------------------------------------------------------ deblocking
+def deblock_picture(bit_depth: int, rng, geom: PicGeom, buf: np.ndarray, pic: int) -> None:
+    """Blocky reconstructed picture: smooth gradient, a DC step per 8x8 block (so edges
+    exist), light noise -- strong, weak and "no filtering" decisions all occur."""
+    maxv = (1 << bit_depth) - 1
+    scale = maxv / 255.0
+    for c in range(3):
+        h, w = geom.plane_shape(c)
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+        base = (0.2 + 0.6 * (xx / w * 0.5 + yy / h * 0.5)) * maxv
+        step = rng.normal(0.0, 3.0 * scale, ((h + 7) // 8, (w + 7) // 8)).astype(np.float32)
+        step = np.kron(step, np.ones((8, 8), np.float32))[:h, :w]
+        noise = rng.normal(0.0, 0.8 * scale, (h, w)).astype(np.float32)
+        geom.plane_view(buf, pic, c)[:] = np.clip(np.rint(base + step + noise), 0, maxv).astype(buf.dtype)
+
+
+def deblock_edge_map(width: int, height: int, ctb_log2: int, rng, qp_lo: int = 22, qp_hi: int = 45,
+                     no_filter_frac: float = 0.02, dense: bool = False):
+    """Synthetic edge map + per-CTB parameters: an intra-like TU grid (every 8x8 edge is a
+    transform edge with probability depending on a random 8/16/32 block structure; `dense`
+    = every 8x8 edge), Bs 2 mostly, some Bs 1, QpY per 16x16 region, slice offsets per CTB."""
+    from .picture import DBK_BS_H0, DBK_BS_H1, DBK_BS_V0, DBK_BS_V1, DBK_CTB, DBK_NO_FILTER, DBK_QP_SHIFT
+    w8, h8 = width // 8, height // 8
+    # block structure: each 32x32 region is one 32x32, four 16x16 or sixteen 8x8 blocks
+    kind = rng.choice((8, 16, 32), size=((h8 + 3) // 4, (w8 + 3) // 4), p=(0.3, 0.3, 0.4))
+    kind = np.kron(kind, np.ones((4, 4), np.int64))[:h8, :w8]
+    if dense:
+        kind[:] = 8
+    by, bx = np.mgrid[0:h8, 0:w8]
+    v_on = (bx * 8) % kind == 0
+    h_on = (by * 8) % kind == 0
+    v_on[:, 0] = False
+    h_on[0, :] = False
+
+    def bs(on):
+        s = rng.choice((0, 1, 2), size=(2,) + on.shape, p=(0.05, 0.15, 0.8))
+        return np.where(on[None], s, 0).astype(np.uint16)
+    bv, bh = bs(v_on), bs(h_on)
+    qp = rng.integers(qp_lo, qp_hi + 1, ((h8 + 1) // 2, (w8 + 1) // 2))
+    qp = np.kron(qp, np.ones((2, 2), np.int64))[:h8, :w8]
+    blk = (bv[0] << DBK_BS_V0) | (bv[1] << DBK_BS_V1) | (bh[0] << DBK_BS_H0) | (bh[1] << DBK_BS_H1) | \
+        ((qp & 0x7F) << DBK_QP_SHIFT).astype(np.uint16)
+    blk = blk.astype(np.uint16)
+    blk[rng.random((h8, w8)) < no_filter_frac] |= DBK_NO_FILTER
+    cs = 1 << ctb_log2
+    ctb = np.zeros(((height + cs - 1) // cs, (width + cs - 1) // cs), dtype=DBK_CTB)
+    ctb["beta_offset_div2"] = rng.integers(-6, 7, ctb.shape)
+    ctb["tc_offset_div2"] = rng.integers(-6, 7, ctb.shape)
+    ctb["cb_qp_offset"] = rng.integers(-4, 5)
+    ctb["cr_qp_offset"] = rng.integers(-4, 5)
+    return blk, ctb
+
+
+def deblock_batch(width: int = 3840, height: int = 2160, bit_depth: int = 10, n_pics: int = 1,
+                  ctb_log2: int = 6, seed: int = 26506, dense: bool = False, n_unique=None):
+    """Returns (geom, rec_buffer, blk[n_pics, h/8, w/8], ctb[n_pics, ctbs_h, ctbs_w])."""
+    from .picture import DBK_CTB
+    rng = np.random.default_rng(seed)
+    geom = PicGeom(width, height, n_pics, bit_depth, bit_depth)
+    dtype = np.uint8 if bit_depth <= 8 else np.uint16
+    buf = np.zeros(geom.total_elems(), dtype=dtype)
+    cs = 1 << ctb_log2
+    qp_off = 6 * (bit_depth - 8) * 0       # QpY itself does not include QpBdOffset
+    blk = np.zeros((n_pics, height // 8, width // 8), np.uint16)
+    ctb = np.zeros((n_pics, (height + cs - 1) // cs, (width + cs - 1) // cs), DBK_CTB)
+    n_unique = n_pics if n_unique is None else min(n_unique, n_pics)
+    for p in range(n_pics):
+        if p < n_unique:
+            deblock_picture(bit_depth, rng, geom, buf, p)
+            blk[p], ctb[p] = deblock_edge_map(width, height, ctb_log2, rng, 22 + qp_off, 45 + qp_off, dense=dense)
+        else:
+            q = p % n_unique
+            buf[p * geom.pic_stride:(p + 1) * geom.pic_stride] = buf[q * geom.pic_stride:(q + 1) * geom.pic_stride]
+            blk[p], ctb[p] = blk[q], ctb[q]
+    return geom, buf, blk, ctb

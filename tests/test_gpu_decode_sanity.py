@@ -1,0 +1,33 @@
+"""sanity.bin decoded end to end with the GPU path and compared with libavcodec (the
+independent known answer, tests/golden/sanity_ffmpeg.npz):
+
+  reference parser (py3 shim, host) -> packer -> residual kernels (GPU) -> host intra
+  prediction + reconstruction -> deblocking kernel (GPU) -> SAO kernel (GPU)
+
+Y, Cb and Cr of all three pictures, before the loop filters and after them, bit for bit.
+The CPU twin (oracle instead of GPU) is tests/test_decode_sanity.py."""
+import numpy as np
+import pytest
+
+from p265_b200 import deblock_api, intra_host, packer, sao_api
+
+pytestmark = pytest.mark.gpu
+COMPS = ("y", "cb", "cr")
+
+
+def test_gpu_decode_of_sanity_bin_equals_libavcodec(engine, parsed_sanity, ffmpeg_sanity):
+    imgs, sps, pps = parsed_sanity
+    assert len(imgs) == 3
+    launches = engine.launch_count
+    for p, img in enumerate(imgs):
+        batch = packer.pack_pictures([img], sps)
+        res = engine.residual(batch)
+        planes = [batch.geom.plane_view(res, 0, c) for c in range(3)]
+        rec = intra_host.reconstruct_intra_picture(img, sps, pps, planes)
+        for c, n in enumerate(COMPS):
+            assert np.array_equal(rec[c], ffmpeg_sanity["rec%d_%s" % (p, n)]), ("rec", p, n)
+        dbk = deblock_api.filter_picture(rec, img, sps, pps)
+        out = sao_api.filter_picture(dbk, img, sps, pps)
+        for c, n in enumerate(COMPS):
+            assert np.array_equal(out[c], ffmpeg_sanity["out%d_%s" % (p, n)]), ("out", p, n)
+    assert engine.launch_count > launches

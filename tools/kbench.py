@@ -110,6 +110,28 @@ def main():
     print("%-34s %8.4f ms  %7.1f GB/s alg (%.3f of 6555)" % ("reconstruct (pred + residual)", ms,
                                                              b / (ms * 1e-3) / 1e9, b / (ms * 1e-3) / 1e9 / 6554.9))
 
+    # deblocking: in place, 4 B/sample at 10 bits when every block is touched
+    for label, dense in (("deblock, TU-grid edge map", False), ("deblock, every 8x8 edge", True)):
+        g2, rec2, blk, ctb = synth.deblock_batch(3840, 2160, 10, n_pics=args.pics, n_unique=min(2, args.pics),
+                                                 dense=dense)
+        d_pix, d_blk, d_ctb = to_dev(rec2), to_dev(blk), to_dev(ctb)
+        d_work = torch.empty_like(d_pix)
+        times = []
+        for _ in range(args.reps + 3):
+            d_work.copy_(d_pix)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                stream.wait_stream(torch.cuda.current_stream())
+                e0.record(stream)
+                eng.deblock_dev(d_work.data_ptr(), g2, 6, d_blk.data_ptr(), d_ctb.data_ptr())
+                e1.record(stream)
+            e1.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = float(np.median(times[3:]))
+        b = 4 * g2.n_pics * (g2.width * g2.height * 3 // 2)
+        print("%-34s %8.4f ms  %7.1f GB/s alg (%.3f of 6555)" % (label, ms, b / (ms * 1e-3) / 1e9,
+                                                                 b / (ms * 1e-3) / 1e9 / 6554.9), flush=True)
+
 
 if __name__ == "__main__":
     main()
