@@ -225,13 +225,17 @@ def run_gpu(args):
     value = pixels_step * args.steps / (ms_total_max * 1e-3) / 1e6
 
     # ---- end to end through the host API (pinned host buffers, copies timed) ----
-    e2e_pics = min(args.pics, args.e2e_pics)
-    res_h, sgeom_h, rec_h, params_h = (res, sgeom, rec, params) if e2e_pics == args.pics else \
-        make_workload(e2e_pics, 26510 + stream_id)
-    # two contexts (one stream each) driven from two host threads: the residual call of one
-    # batch overlaps the SAO call of another, as a decoder pipelining pictures would do, so
-    # H2D of one overlaps D2H of the other on the two copy engines
-    eng2, eng3 = Engine(local), Engine(local)
+    # A decoder hands pictures over one at a time, so every picture is its own host call:
+    # Engine.residual (H2D descriptors + coefficients -> residual kernels -> D2H planes) then
+    # Engine.sao (H2D reconstructed planes + parameters -> SAO kernel -> D2H planes).  The
+    # calls go round-robin to a few ASYNCHRONOUS contexts (p265_ctx_set_async: one stream
+    # each), so the H2D copy of one picture overlaps the D2H copy of another on the two copy
+    # engines; every context is synchronised before the step ends.
+    e2e_pics = max(1, args.e2e_pics)
+    n_ctx = max(1, min(args.e2e_ctx, e2e_pics))
+    engs = [Engine(local) for _ in range(n_ctx)]
+    for e in engs:
+        e.set_async(True)
 
     def pin(a):
         a = np.ascontiguousarray(a)
@@ -240,25 +244,31 @@ def run_gpu(args):
         v[...] = a
         return t_, v
 
-    keep = []
-    k_tus, h_tus = pin(res_h.tus)
-    k_co, h_co = pin(res_h.coeffs)
-    k_rec, h_rec = pin(rec_h)
-    k_ro = pinned(res_h.geom.total_elems() * 2)
-    h_ro = k_ro.numpy().view(np.int16)
-    k_so = pinned(rec_h.nbytes)
-    h_so = k_so.numpy().view(rec_h.dtype)
-    keep += [k_tus, k_co, k_rec, k_ro, k_so]
     from p265_b200.picture import ResidualBatch
-    hb = ResidualBatch(res_h.geom, h_tus, h_co, res_h.scaling_factor, res_h.covers_all)
-
-    from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=1)
+    keep, uniq = [], []
+    for u in range(min(2, e2e_pics)):           # two distinct pictures, inputs shared read-only
+        r1, g1, rec1, par1 = make_workload(1, 26510 + stream_id + 100 * (u + 1))
+        k_tus, h_tus = pin(r1.tus)
+        k_co, h_co = pin(r1.coeffs)
+        k_rec, h_rec = pin(rec1)
+        k_par, h_par = pin(par1)
+        keep += [k_tus, k_co, k_rec, k_par]
+        uniq.append((ResidualBatch(r1.geom, h_tus, h_co, r1.scaling_factor, r1.covers_all), g1, h_rec, h_par))
+    items = []
+    for p in range(e2e_pics):
+        hb, g1, h_rec, h_par = uniq[p % len(uniq)]
+        k_ro = pinned(hb.geom.total_elems() * 2)
+        k_so = pinned(h_rec.nbytes)
+        keep += [k_ro, k_so]
+        items.append((hb, g1, h_rec, h_par, k_ro.numpy().view(np.int16), k_so.numpy().view(h_rec.dtype)))
 
     def e2e_step():
-        fut = pool.submit(eng2.residual, hb, h_ro)
-        eng3.sao(h_rec, sgeom_h, 6, params_h, out=h_so)
-        fut.result()
+        for p, (hb, g1, h_rec, h_par, h_ro, h_so) in enumerate(items):
+            e = engs[p % n_ctx]
+            e.residual(hb, h_ro)
+            e.sao(h_rec, g1, 6, h_par, out=h_so)
+        for e in engs:
+            e.sync()
 
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
     for _ in range(2):
@@ -270,9 +280,15 @@ def run_gpu(args):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     e2e_value = PIC_W * PIC_H * e2e_pics * world * e2e_steps / partition.max_over_ranks(dt, dev) / 1e6
-    h2d = res_h.tus.nbytes + res_h.coeffs.nbytes + rec_h.nbytes + params_h.nbytes + \
-        (res_h.scaling_factor.nbytes if res_h.scaling_factor is not None else 0)
-    d2h = h_ro.nbytes + h_so.nbytes
+    h2d = sum(it[0].tus.nbytes + it[0].coeffs.nbytes + it[2].nbytes + it[3].nbytes +
+              (it[0].scaling_factor.nbytes if it[0].scaling_factor is not None else 0) for it in items)
+    d2h = sum(it[4].nbytes + it[5].nbytes for it in items)
+    # the pipelined outputs are the synchronous call's outputs (outside the timed region)
+    chk = Engine(local)
+    hb, g1, h_rec, h_par, h_ro, h_so = items[-1]
+    if not (np.array_equal(chk.residual(hb), h_ro) and np.array_equal(chk.sao(h_rec, g1, 6, h_par), h_so)):
+        raise SystemExit("bench.py: asynchronous end-to-end outputs differ from the synchronous call")
+    e2e_launches = sum(e.launch_count for e in engs) // (e2e_steps + 2)
 
     if rank != 0:
         if world > 1:
@@ -320,8 +336,11 @@ def run_gpu(args):
                    "l2": "inputs larger than L2 (%.0f MB touched per step)" % ((b_res + b_sao) / 1e6)},
         "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "pics_per_step_per_gpu": e2e_pics, "steps": e2e_steps,
-                "how": "Engine.residual and Engine.sao (C-ABI host entry points) on two contexts from two host "
-                       "threads, pinned host buffers, every copy inside the timed region"},
+                "contexts": n_ctx, "gpu_launches_per_step": int(e2e_launches),
+                "how": "one Engine.residual + one Engine.sao call per picture (C-ABI host entry points "
+                       "p265_residual_batch / p265_sao_batch), round-robin over asynchronous contexts "
+                       "(p265_ctx_set_async), pinned host buffers, every H2D / D2H copy inside the timed "
+                       "region, all contexts synchronised before the step ends"},
         "gpu_launches": int(launches),
         "gpu_launches_per_step": {"residual_kernel<bin 32/16/8/4>": 4, "sao_kernel": 1},
         "clocks": clocks,
@@ -487,7 +506,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pics", type=int, default=16, help="4K pictures per step per GPU")
-    ap.add_argument("--e2e-pics", type=int, default=4)
+    ap.add_argument("--e2e-pics", type=int, default=8)
+    ap.add_argument("--e2e-ctx", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -121,6 +121,12 @@ int p265_device_count(void);
 int p265_ctx_create(int device, void *stream, p265_ctx **out);
 int p265_ctx_destroy(p265_ctx *ctx);
 int p265_sync(p265_ctx *ctx);
+/* enable != 0: the host-buffer batch entry points (p265_residual_batch, p265_sao_batch,
+ * p265_reconstruct_batch, p265_deblock_batch) return as soon as their copies and kernels are
+ * queued on the context's stream; results are valid after p265_sync().  The caller keeps the
+ * host buffers alive (and, for real overlap, page-locked) until then.  Several asynchronous
+ * contexts let the H2D copy of one picture overlap the D2H copy of another.               */
+int p265_ctx_set_async(p265_ctx *ctx, int enable);
 int p265_sm_count(p265_ctx *ctx);
 /* kernels launched through this context so far (bench.py reports it as gpu_launches) */
 uint64_t p265_launch_count(p265_ctx *ctx);

@@ -21,7 +21,7 @@ RES_SF_REPLICATED = 2
 #: every symbol include/p265_b200.h declares (tests check the .so exports them all)
 SYMBOLS = (
     "p265_abi_version", "p265_last_error", "p265_device_count", "p265_ctx_create",
-    "p265_ctx_destroy", "p265_sync", "p265_sm_count", "p265_launch_count",
+    "p265_ctx_destroy", "p265_sync", "p265_ctx_set_async", "p265_sm_count", "p265_launch_count",
     "p265_residual_batch", "p265_residual_batch_dev", "p265_dequant_batch",
     "p265_ref_literal_batch", "p265_idct_1d", "p265_sao_batch", "p265_sao_batch_dev",
     "p265_reconstruct_batch", "p265_reconstruct_batch_dev", "p265_deblock_batch",
@@ -62,6 +62,7 @@ def load():
     lib.p265_ctx_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
     lib.p265_ctx_destroy.argtypes = [vp]
     lib.p265_sync.argtypes = [vp]
+    lib.p265_ctx_set_async.argtypes = [vp, C.c_int]
     lib.p265_sm_count.argtypes = [vp]
     lib.p265_launch_count.argtypes = [vp]
     lib.p265_launch_count.restype = C.c_uint64

@@ -165,6 +165,19 @@ int p265_sync(p265_ctx *ctx) {
     return P265_OK;
 }
 
+int p265_ctx_set_async(p265_ctx *ctx, int enable) {
+    if (!ctx) return set_error(P265_EINVAL, "ctx is NULL");
+    ctx->async_mode = enable != 0;
+    return P265_OK;
+}
+
+// end of a host-buffer entry point: wait for the result unless the context is asynchronous
+static int finish(p265_ctx *ctx) {
+    if (ctx->async_mode) return P265_OK;
+    P265_CUDA(cudaStreamSynchronize(ctx->stream));
+    return P265_OK;
+}
+
 int p265_sm_count(p265_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 
 uint64_t p265_launch_count(p265_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -217,8 +230,7 @@ int p265_residual_batch(p265_ctx *ctx, const p265_tu_desc *tus, const int32_t bi
                          geom, (int16_t *)d_out, flags);
     if (rc) return rc;
     P265_CUDA(cudaMemcpyAsync(residual, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    P265_CUDA(cudaStreamSynchronize(ctx->stream));
-    return P265_OK;
+    return finish(ctx);
 }
 
 int p265_dequant_batch(p265_ctx *ctx, const p265_tu_desc *tus, int32_t n_tus, const int16_t *coeffs, size_t n_coeffs,
@@ -356,8 +368,7 @@ int p265_sao_batch(p265_ctx *ctx, const void *rec, void *out, const p265_pic_geo
     if ((rc = launch_sao(ctx, d_rec, d_out, geom, ctb_log2, (const p265_sao_ctb *)d_par, (const uint8_t *)d_nf)))
         return rc;
     P265_CUDA(cudaMemcpyAsync(out, d_out, plane_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    P265_CUDA(cudaStreamSynchronize(ctx->stream));
-    return P265_OK;
+    return finish(ctx);
 }
 
 int p265_reconstruct_batch_dev(p265_ctx *ctx, const void *d_pred, const int16_t *d_residual, void *d_rec,
@@ -386,8 +397,7 @@ int p265_reconstruct_batch(p265_ctx *ctx, const void *pred, const int16_t *resid
     P265_CUDA(cudaMemcpyAsync(d_rec, d_pred, elems * bytes, cudaMemcpyDeviceToDevice, ctx->stream));  // padding
     if ((rc = launch_recon(ctx, d_pred, (const int16_t *)d_res, d_rec, geom))) return rc;
     P265_CUDA(cudaMemcpyAsync(rec, d_rec, elems * bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    P265_CUDA(cudaStreamSynchronize(ctx->stream));
-    return P265_OK;
+    return finish(ctx);
 }
 
 static int check_deblock(const p265_pic_geom *geom, int ctb_log2, int *bytes) {
@@ -441,8 +451,7 @@ int p265_deblock_batch(p265_ctx *ctx, void *planes, const p265_pic_geom *geom, i
     if ((rc = launch_deblock(ctx, d_pix, geom, ctb_log2, (const p265_dbk_blk *)d_blk, (const p265_dbk_ctb *)d_ctb)))
         return rc;
     P265_CUDA(cudaMemcpyAsync(planes, d_pix, plane_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    P265_CUDA(cudaStreamSynchronize(ctx->stream));
-    return P265_OK;
+    return finish(ctx);
 }
 
 int p265_int_peak(p265_ctx *ctx, int kind, double *ops_per_s, double *ms) {

@@ -13,6 +13,7 @@ struct p265_ctx {
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
     int sm_count = 0;
+    bool async_mode = false;  // host entry points return after enqueueing (p265_ctx_set_async)
     uint64_t launches = 0;  // kernels launched by this context (bench.py: gpu_launches)
     // grow-only device scratch for the host-buffer entry points
     void *scratch[8] = {nullptr};

@@ -25,6 +25,7 @@ class Engine:
         _lib.check(lib.p265_ctx_create(int(device), C.c_void_p(stream) if stream else None,
                                        C.byref(handle)))
         self._lib, self._ctx, self.device = lib, handle, int(device)
+        self._async, self._inflight = False, []
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -40,6 +41,18 @@ class Engine:
 
     def sync(self):
         _lib.check(self._lib.p265_sync(self._ctx))
+        self._inflight.clear()
+
+    def _hold(self, *arrays):
+        """Asynchronous mode: keep the host arrays of queued copies alive until sync()."""
+        if self._async:
+            self._inflight.extend(a for a in arrays if a is not None)
+
+    def set_async(self, enable: bool = True):
+        """Host-array methods return once their copies and kernels are queued; call sync()
+        before reading the outputs (keep inputs alive, ideally page-locked, until then)."""
+        _lib.check(self._lib.p265_ctx_set_async(self._ctx, 1 if enable else 0))
+        self._async = bool(enable)
 
     @property
     def sm_count(self) -> int:
@@ -71,6 +84,7 @@ class Engine:
         _lib.check(self._lib.p265_residual_batch(
             self._ctx, _lib.ptr(tus), _lib.bins(batch.bin_counts()), _lib.ptr(co), co.size,
             _lib.ptr(sf), C.byref(gs), _lib.ptr(out), flags))
+        self._hold(tus, co, sf, out)
         return out
 
     def residual_dev(self, d_tus: int, bin_counts, d_coeffs: int, d_sf: int | None, geom: PicGeom,
@@ -135,6 +149,7 @@ class Engine:
         gs = _lib.geom_struct(geom)
         _lib.check(self._lib.p265_sao_batch(self._ctx, _lib.ptr(rec), _lib.ptr(out), C.byref(gs),
                                             int(ctb_log2), _lib.ptr(par), _lib.ptr(nf)))
+        self._hold(rec, par, nf, out)
         return out
 
     def sao_dev(self, d_rec: int, d_out: int, geom: PicGeom, ctb_log2: int, d_params: int,
@@ -158,6 +173,7 @@ class Engine:
         gs = _lib.geom_struct(geom)
         _lib.check(self._lib.p265_reconstruct_batch(self._ctx, _lib.ptr(pred), _lib.ptr(res), _lib.ptr(out),
                                                     C.byref(gs)))
+        self._hold(pred, res, out)
         return out
 
     def reconstruct_dev(self, d_pred: int, d_residual: int, d_rec: int, geom: PicGeom):
@@ -185,6 +201,7 @@ class Engine:
         gs = _lib.geom_struct(geom)
         _lib.check(self._lib.p265_deblock_batch(self._ctx, _lib.ptr(out), C.byref(gs), int(ctb_log2),
                                                 _lib.ptr(blk), _lib.ptr(par)))
+        self._hold(blk, par, out)
         return out
 
     def deblock_dev(self, d_planes: int, geom: PicGeom, ctb_log2: int, d_blk: int, d_ctb: int):

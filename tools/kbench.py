@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--pics", type=int, default=8)
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--only", default="", help="comma list of sections: residual,sao,recon,deblock")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     stream = torch.cuda.Stream(device=dev)
@@ -54,6 +55,20 @@ def main():
               (label, ms, gbs, gbs / 6554.9, samples / (ms * 1e-3) / 1e9), flush=True)
         return ms
 
+    only = set(x for x in args.only.split(",") if x)
+
+    def want(name):
+        return not only or name in only
+
+    if want("residual"):
+        bench_residual(args, time_residual)
+    if want("sao") or want("recon"):
+        bench_sao_recon(args, eng, dev, stream, to_dev, want)
+    if want("deblock"):
+        bench_deblock(args, eng, dev, stream, to_dev)
+
+
+def bench_residual(args, time_residual):
     full = synth.residual_batch("4k10", n_pics=args.pics, n_unique=min(2, args.pics))
     time_residual(full, "4k10 mix, SF replicated")
     time_residual(full, "4k10 mix, SF general", force_general=True)
@@ -65,6 +80,9 @@ def main():
             b = ResidualBatch(full.geom, np.ascontiguousarray(sel), full.coeffs, sf, covers_all=True)
             time_residual(b, "only %2dx%-2d (%7d TBs) %s" % (1 << l2, 1 << l2, len(sel), name))
 
+
+
+def bench_sao_recon(args, eng, dev, stream, to_dev, want):
     geom, rec, params = synth.sao_batch(3840, 2160, 10, n_pics=args.pics, n_unique=min(2, args.pics))
     d_rec, d_par = to_dev(rec), to_dev(params)
     d_o = torch.empty_like(d_rec)
@@ -110,6 +128,9 @@ def main():
     print("%-34s %8.4f ms  %7.1f GB/s alg (%.3f of 6555)" % ("reconstruct (pred + residual)", ms,
                                                              b / (ms * 1e-3) / 1e9, b / (ms * 1e-3) / 1e9 / 6554.9))
 
+
+
+def bench_deblock(args, eng, dev, stream, to_dev):
     # deblocking: in place, 4 B/sample at 10 bits when every block is touched
     for label, dense in (("deblock, TU-grid edge map", False), ("deblock, every 8x8 edge", True)):
         g2, rec2, blk, ctb = synth.deblock_batch(3840, 2160, 10, n_pics=args.pics, n_unique=min(2, args.pics),
