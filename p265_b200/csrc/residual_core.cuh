@@ -70,6 +70,15 @@ P265_HD int pack_sat(int lo, int hi) {
     return (int)(((uint32_t)(uint16_t)(int16_t)h << 16) | (uint16_t)(int16_t)l);
 #endif
 }
+// 2e - s in one 3-input add (IADD3 e, e, -s): the mirrored butterfly output e - O from e and
+// s = e + O.  Wraps like the separate subtraction would (two's complement).
+P265_HD int mirror(int e, int s) {
+#if defined(__CUDA_ARCH__)
+    return e + e - s;
+#else
+    return (int)((uint32_t)e + (uint32_t)e - (uint32_t)s);
+#endif
+}
 P265_HD int ilog2(unsigned v) {
 #if defined(__CUDA_ARCH__)
     return 31 - __clz((int)v);
@@ -190,14 +199,25 @@ struct Idct<4, C> {
     static P265_HD void run(const int (&p)[C][2], int rnd, int (&out)[C][4]) {
         P265_UNROLL
         for (int c = 0; c < C; c++) {
-            int e0 = dp2a_lo(p[c][0], P265_K(e4), rnd);
-            int e1 = dp2a_hi(p[c][0], P265_K(e4), rnd);
-            int o0 = dp2a_lo(p[c][1], P265_K(o4), 0);
-            int o1 = dp2a_hi(p[c][1], P265_K(o4), 0);
-            out[c][0] = e0 + o0;
-            out[c][3] = e0 - o0;
-            out[c][1] = e1 + o1;
-            out[c][2] = e1 - o1;
+            // the odd chain accumulates on top of the even value (no separate add); the
+            // mirrored output is 2e - (e + o), one 3-input IADD3 on the ALU pipe -- the FMA
+            // pipe (IDP.2A / IMAD, one warp-instruction per 2 cycles) is the scarce one
+            const int e0 = dp2a_lo(p[c][0], P265_K(e4), rnd);
+            const int e1 = dp2a_hi(p[c][0], P265_K(e4), rnd);
+            if (C == 4) {
+                // one-lane-per-4x4-TB path: latency-bound, keep the even and odd products independent
+                const int o0 = dp2a_lo(p[c][1], P265_K(o4), 0);
+                const int o1 = dp2a_hi(p[c][1], P265_K(o4), 0);
+                out[c][0] = e0 + o0;
+                out[c][3] = e0 - o0;
+                out[c][1] = e1 + o1;
+                out[c][2] = e1 - o1;
+            } else {
+                out[c][0] = dp2a_lo(p[c][1], P265_K(o4), e0);
+                out[c][1] = dp2a_hi(p[c][1], P265_K(o4), e1);
+                out[c][3] = mirror(e0, out[c][0]);
+                out[c][2] = mirror(e1, out[c][1]);
+            }
         }
     }
 };
@@ -230,9 +250,9 @@ struct Idct {
         Idct<N / 2, C>::run(pe, rnd, e);
         P265_UNROLL
         for (int k = 0; k < N / 2; k++) {
-            int o[C];
+            int o[C];  // e + O[k]: the odd chain starts from the even value
             P265_UNROLL
-            for (int c = 0; c < C; c++) o[c] = 0;
+            for (int c = 0; c < C; c++) o[c] = e[c][k];
             P265_UNROLL
             for (int s = 0; s < N / 4; s++) {
                 const int w = OddK<N>::w(k, s >> 1);
@@ -242,8 +262,8 @@ struct Idct {
             }
             P265_UNROLL
             for (int c = 0; c < C; c++) {
-                out[c][k] = e[c][k] + o[c];
-                out[c][N - 1 - k] = e[c][k] - o[c];
+                out[c][k] = o[c];
+                out[c][N - 1 - k] = mirror(e[c][k], o[c]);
             }
         }
     }

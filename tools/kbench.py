@@ -66,6 +66,47 @@ def main():
         bench_sao_recon(args, eng, dev, stream, to_dev, want)
     if want("deblock"):
         bench_deblock(args, eng, dev, stream, to_dev)
+    if want("overlap"):
+        bench_overlap(args, eng, dev, stream, to_dev)
+
+
+def bench_overlap(args, eng, dev, stream, to_dev):
+    """Residual on one stream, SAO on another: issue-bound and bandwidth-bound work overlap."""
+    batch = synth.residual_batch("4k10", n_pics=args.pics, n_unique=min(2, args.pics))
+    d_tus, d_co, d_sf = to_dev(batch.tus), to_dev(batch.coeffs), to_dev(batch.scaling_factor)
+    d_out = torch.empty(batch.geom.total_elems() * 2, dtype=torch.uint8, device=dev)
+    bins = batch.bin_counts()
+    geom, rec, params = synth.sao_batch(3840, 2160, 10, n_pics=args.pics, n_unique=min(2, args.pics))
+    d_rec, d_par = to_dev(rec), to_dev(params)
+    d_o = torch.empty_like(d_rec)
+    for prio in (0, -1):
+        stream2 = torch.cuda.Stream(device=dev, priority=prio)
+        eng2 = Engine(0, stream2.cuda_stream)
+
+        def res():
+            eng.residual_dev(d_tus.data_ptr(), bins, d_co.data_ptr(), d_sf.data_ptr(), batch.geom, d_out.data_ptr(),
+                             zero_fill=False, sf_replicated=True)
+
+        def sao():
+            eng2.sao_dev(d_rec.data_ptr(), d_o.data_ptr(), geom, 6, d_par.data_ptr())
+        for order in ("res first", "sao first"):
+            for _ in range(3):
+                res(); sao()
+            torch.cuda.synchronize()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(stream)
+            stream2.wait_event(e0)
+            for _ in range(args.reps):
+                if order == "res first":
+                    res(); sao()
+                else:
+                    sao(); res()
+            e2.record(stream2)
+            stream.wait_event(e2)
+            e1.record(stream)
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / args.reps
+            print("overlap residual || SAO (%s, sao prio %d)   %8.4f ms per pair" % (order, prio, ms), flush=True)
 
 
 def bench_residual(args, time_residual):
