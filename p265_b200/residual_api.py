@@ -60,13 +60,20 @@ class PictureResidual:
         return d, r
 
 
-def sps_scaling_table(sps):
-    """Packed 4064-byte table from `sps.scaling_factor[size_id][matrix_id][x][y]`
-    (scaling.py:44) or None when scaling lists are off (scaling.py:32-33)."""
+def sps_scaling_table(sps, pps=None):
+    """Packed 4064-byte table or None when scaling lists are off (scaling.py:32-33).
+
+    `sps.scaling_factor[size_id][matrix_id][x][y]` (the attribute scaling.py:44 reads) wins
+    when a caller has set it; the reference itself never does, so otherwise
+    the table comes from the decoded scaling_list_data() of the PPS / SPS (p265_b200's `sld`
+    drop-in) or the default lists (`scaling_list.active_table`)."""
     if not getattr(sps, "scaling_list_enabled_flag", 0):
         return None
+    src = getattr(sps, "scaling_factor", None)
+    if src is None:
+        from . import scaling_list
+        return scaling_list.active_table(sps, pps)
     sf = {}
-    src = sps.scaling_factor
     for s in range(4):
         for m in range(2 if s == 3 else 6):
             f = src[s][m]
@@ -75,11 +82,11 @@ def sps_scaling_table(sps):
     return pack_scaling_factor(sf)
 
 
-def flush_picture(img, sps, device: int = 0) -> PictureResidual:
+def flush_picture(img, sps, device: int = 0, pps=None) -> PictureResidual:
     """Batched path: one residual launch (+ one dequant launch for `scaled_samples`) for
     all coded TBs of a parsed picture; the result is attached to `img`."""
     eng = get_engine(device)
-    batch = packer.pack_pictures([img], sps, sps_scaling_table(sps))
+    batch = packer.pack_pictures([img], sps, sps_scaling_table(sps, pps))
     planes = eng.residual(batch)
     scaled = eng.dequant(batch)
     img._p265_b200_residual = PictureResidual(batch, planes, scaled)
@@ -193,7 +200,7 @@ def inverse_scaling(pu, x0, y0, log2size):
         d[...] = levels_xy
         return
     batch = _tb_batch(pu, levels_xy.T, log2size, _flags(pu, x0, y0, log2size) & TU_INTRA, _qp(pu),
-                      sps_scaling_table(pu.cu.ctx.sps))
+                      sps_scaling_table(pu.cu.ctx.sps, getattr(pu.cu.ctx, "pps", None)))
     out = get_engine().dequant(batch)
     d[...] = out[:n * n].reshape(n, n).T
 

@@ -106,30 +106,108 @@ def parse_scaling_list_data(read_flag, read_ue, read_se):
     lists, dc = {}, {}
     for s in range(4):
         for m in range(num_matrices(s)):
-            coef_num = min(64, 1 << (4 + (s << 1)))
-            if not read_flag():                       # scaling_list_pred_mode_flag == 0
-                delta = read_ue()                     # scaling_list_pred_matrix_id_delta
-                if delta == 0:
-                    lists[(s, m)] = default_list(s, m)
-                    if s >= 2:
-                        dc[(s, m)] = 16
-                else:
-                    ref = m - delta
-                    if ref < 0:
-                        raise ValueError("scaling_list_pred_matrix_id_delta out of range")
-                    lists[(s, m)] = list(lists[(s, ref)])
-                    if s >= 2:
-                        dc[(s, m)] = dc[(s, ref)]
-            else:
-                next_coef = 8
-                if s >= 2:
-                    next_coef = read_se() + 8          # scaling_list_dc_coef_minus8
-                    if not 1 <= next_coef <= 255:
-                        raise ValueError("scaling_list_dc_coef_minus8 out of range")
-                    dc[(s, m)] = next_coef
-                lst = []
-                for _ in range(coef_num):
-                    next_coef = (next_coef + read_se() + 256) % 256   # scaling_list_delta_coef
-                    lst.append(next_coef)
-                lists[(s, m)] = lst
+            lists[(s, m)], one_dc = _parse_one(s, m, lists, dc, read_flag, read_ue, read_se)
+            if s >= 2:
+                dc[(s, m)] = one_dc
     return lists, dc
+
+class ScalingListData:
+    """Drop-in for the reference's `sld.ScalingListData(bs)` (sld.py:3, used by sps.py:18,90
+    and pps.py:11,135).  `decode()` reads scaling_list_data() with the reference's bit reader
+    (`bs.u(1, name)`, `bs.ue(name)`, `bs.se(name)`, bsb.py:143-168, logging the syntax
+    elements under the names sld.py:78-111 uses) and leaves
+
+        .scaling_list[size_id][matrix_id]          the coefficient lists (scan order)
+        .scaling_list_dc_coef_minus8[size_id-2][matrix_id]
+        .scaling_factor[size_id][matrix_id][x][y]  what scaling.inverse_scaling reads (scaling.py:44)
+        .table                                      the packed 4064-byte device table
+
+    The reference's own decode() cannot run (undefined names, sld.py:82-94)."""
+    default_scaling_list_4x4 = list(DEFAULT_4x4)
+    default_scaling_list_8x8_intra = list(DEFAULT_8x8_INTRA)
+    default_scaling_list_8x8_inter = list(DEFAULT_8x8_INTER)
+
+    def __init__(self, bs=None):
+        self.bs = bs
+        self.present = False
+        self._set(*default_lists())
+
+    def _set(self, lists, dc):
+        from .picture import pack_scaling_factor
+        self.lists, self.dc = lists, dc
+        self.scaling_list = [[lists.get((s, m)) for m in range(num_matrices(s))] for s in range(4)]
+        self.scaling_list_dc_coef_minus8 = [[dc[(s, m)] - 8 for m in range(num_matrices(s))] for s in (2, 3)]
+        sf = expand(lists, dc)
+        self.scaling_factor = as_reference_object(sf)
+        self.table = pack_scaling_factor(sf)
+
+    def decode(self):
+        bs = self.bs
+        pos = {"s": 0, "m": 0, "i": 0}
+
+        # the syntax element names carry their indices (sld.py:78-106); track them by call order
+        def read_flag():
+            return bs.u(1, "scaling_list_pred_mode_flag[%d][%d]" % (pos["s"], pos["m"]))
+
+        def read_ue():
+            return bs.ue("scaling_list_pred_matrix_id_delta[%d][%d]" % (pos["s"], pos["m"]))
+
+        def read_se():
+            if pos["i"] < 0:
+                pos["i"] = 0
+                return bs.se("scaling_list_dc_coef_minus8[%d][%d]" % (pos["s"] - 2, pos["m"]))
+            name = "scaling_list_delta_coef[%d][%d][%d]" % (pos["s"], pos["m"], pos["i"])
+            pos["i"] += 1
+            return bs.se(name)
+
+        lists, dc = {}, {}
+        for s in range(4):
+            for m in range(num_matrices(s)):
+                pos.update(s=s, m=m, i=-1 if s >= 2 else 0)
+                one, one_dc = _parse_one(s, m, lists, dc, read_flag, read_ue, read_se)
+                lists[(s, m)] = one
+                if s >= 2:
+                    dc[(s, m)] = one_dc
+        self.present = True
+        self._set(lists, dc)
+
+
+def _parse_one(s, m, lists, dc, read_flag, read_ue, read_se):
+    """One (sizeId, matrixId) entry of scaling_list_data() (7.3.4)."""
+    coef_num = min(64, 1 << (4 + (s << 1)))
+    if not read_flag():                               # scaling_list_pred_mode_flag == 0
+        delta = read_ue()                             # scaling_list_pred_matrix_id_delta
+        if delta == 0:
+            return default_list(s, m), 16
+        ref = m - delta
+        if ref < 0:
+            raise ValueError("scaling_list_pred_matrix_id_delta out of range")
+        return list(lists[(s, ref)]), dc.get((s, ref), 16)
+    next_coef, dc_val = 8, 16
+    if s >= 2:
+        next_coef = read_se() + 8                     # scaling_list_dc_coef_minus8
+        if not 1 <= next_coef <= 255:
+            raise ValueError("scaling_list_dc_coef_minus8 out of range")
+        dc_val = next_coef
+    lst = []
+    for _ in range(coef_num):
+        next_coef = (next_coef + read_se() + 256) % 256   # scaling_list_delta_coef
+        if next_coef == 0:
+            raise ValueError("ScalingList entries must be positive (7.4.5)")
+        lst.append(next_coef)
+    return lst, dc_val
+
+
+def active_table(sps, pps=None):
+    """The packed ScalingFactor table a picture uses (7.4.3.2.1 / 7.4.3.3.1) or None when
+    scaling lists are off: PPS lists when pps_scaling_list_data_present_flag, else SPS lists
+    when sps_scaling_list_data_present_flag, else the default lists (Tables 7-5 / 7-6)."""
+    if not getattr(sps, "scaling_list_enabled_flag", 0):
+        return None
+    for owner, flag in ((pps, "pps_scaling_list_data_present_flag"), (sps, "sps_scaling_list_data_present_flag")):
+        if owner is not None and getattr(owner, flag, 0):
+            data = getattr(owner, "scaling_list_data", None)
+            if isinstance(data, ScalingListData) and data.present:
+                return data.table
+            raise ValueError("%s is set but the scaling list data were not decoded by p265_b200's sld module" % flag)
+    return ScalingListData().table
