@@ -165,9 +165,127 @@ __device__ __forceinline__ void store4<uint8_t>(uint8_t *p, const int (&v)[8], i
                                        ((uint32_t)v[at + 3] << 24);
 }
 
+
+// ======================================================================================
+// Packed path (bit depths <= 11): two lines per instruction.  A "line pair" is eight 32-bit
+// registers l[0..7] = p3 p2 p1 p0 q0 q1 q2 q3, each holding the same tap of two adjacent lines
+// as 2 x 16 bit.  All quantities are kept non-negative per half-word (biases are multiples of
+// the following shift) so that plain 32-bit adds / subtracts / shifts never carry or borrow
+// between the halves; clips are VIMNMX.S16x2 / VIADDMNMX.S16x2(.RELU).
+// ======================================================================================
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ uint32_t rep2(int v) { return ((uint32_t)v & 0xffffu) * 0x00010001u; }
+__device__ __forceinline__ uint32_t sel2(uint32_t m, uint32_t a, uint32_t b) { return (a & m) | (b & ~m); }
+
+// 8.7.2.5.7 strong filter on a line pair
+__device__ __forceinline__ void strong_pair(uint32_t (&l)[8], int tc, bool no_p, bool no_q) {
+    const uint32_t p3 = l[0], p2 = l[1], p1 = l[2], p0 = l[3], q0 = l[4], q1 = l[5], q2 = l[6], q3 = l[7];
+    const uint32_t tp = rep2(2 * tc), tn = rep2(-2 * tc);
+    const uint32_t K4 = 0x00040004u, K2 = 0x00020002u;
+    const uint32_t s = p0 + q0, A = p1 + s, B = q1 + s;
+    auto clipd = [&](uint32_t r, uint32_t x) { return __viaddmax_s16x2(x, tn, __viaddmin_s16x2(x, tp, r)); };
+    if (!no_p) {
+        l[3] = clipd((((p2 + q1 + K4) + (A << 1)) >> 3) & 0x1fff1fffu, p0);
+        l[2] = clipd(((p2 + A + K2) >> 2) & 0x3fff3fffu, p1);
+        l[1] = clipd(((((p3 + p2) << 1) + p2 + A + K4) >> 3) & 0x1fff1fffu, p2);
+    }
+    if (!no_q) {
+        l[4] = clipd((((p1 + q2 + K4) + (B << 1)) >> 3) & 0x1fff1fffu, q0);
+        l[5] = clipd(((q2 + B + K2) >> 2) & 0x3fff3fffu, q1);
+        l[6] = clipd(((((q3 + q2) << 1) + q2 + B + K4) >> 3) & 0x1fff1fffu, q2);
+    }
+}
+
+// 8.7.2.5.7 weak filter on a line pair (per-line condition abs(delta) < 10 * tC)
+__device__ __forceinline__ void weak_pair(uint32_t (&l)[8], int tc, bool dep, bool deq, bool no_p, bool no_q,
+                                          uint32_t maxv2) {
+    const uint32_t p2 = l[1], p1 = l[2], p0 = l[3], q0 = l[4], q1 = l[5], q2 = l[6];
+    // D = 9*(q0 - p0) - 3*(q1 - p1) + 8 + 0x6000  (|.| <= 12 * 2047 < 0x6000)
+    const uint32_t X = (q0 << 3) + q0 + (p1 << 1) + p1, Y = (p0 << 3) + p0 + (q1 << 1) + q1;
+    const uint32_t D = X + 0x60086008u - Y;
+    const uint32_t db = (D >> 4) & 0x0fff0fffu;                            // delta + 0x600, in [1, 3071]
+    const uint32_t ad = __vmaxu2(db, 0x0c000c00u - db) - 0x06000600u;      // abs(delta)
+    const uint32_t t = ad + 0x80008000u - rep2(10 * tc);                   // bit 15 of a half: abs(delta) >= 10 tC
+    const uint32_t ok = ((~t >> 15) & 0x00010001u) * 0xffffu;
+    const uint32_t dc = __vminu2(__vmaxu2(db, 0x06000600u - rep2(tc)), 0x06000600u + rep2(tc));
+    const uint32_t n600 = rep2(-0x600), n800 = rep2(-0x800);
+    const uint32_t th = rep2(tc >> 1);
+    const uint32_t mp = no_p ? 0u : ok, mq = no_q ? 0u : ok;
+    l[3] = sel2(mp, __viaddmin_s16x2_relu(p0 + dc, n600, maxv2), p0);
+    l[4] = sel2(mq, __viaddmin_s16x2_relu(q0 + 0x0c000c00u - dc, n600, maxv2), q0);
+    if (dep) {
+        const uint32_t avg = ((p2 + p0 + 0x00010001u) >> 1) & 0x7fff7fffu;
+        const uint32_t E = avg + dc + 0x0a000a00u - p1;                    // (avg - p1 + delta) + 0x1000
+        uint32_t e2 = (E >> 1) & 0x7fff7fffu;                              // (.. >> 1) + 0x800
+        e2 = __vminu2(__vmaxu2(e2, 0x08000800u - th), 0x08000800u + th);
+        l[2] = sel2(mp, __viaddmin_s16x2_relu(p1 + e2, n800, maxv2), p1);
+    }
+    if (deq) {
+        const uint32_t avg = ((q2 + q0 + 0x00010001u) >> 1) & 0x7fff7fffu;
+        const uint32_t E = avg + 0x16001600u - q1 - dc;                    // (avg - q1 - delta) + 0x1000
+        uint32_t e2 = (E >> 1) & 0x7fff7fffu;
+        e2 = __vminu2(__vmaxu2(e2, 0x08000800u - th), 0x08000800u + th);
+        l[5] = sel2(mq, __viaddmin_s16x2_relu(q1 + e2, n800, maxv2), q1);
+    }
+}
+
+// 8.7.2.5.8 chroma filter on a line pair (taps p1 p0 q0 q1 = l[2..5])
+__device__ __forceinline__ void chroma_pair(uint32_t (&l)[8], int tc, bool no_p, bool no_q, uint32_t maxv2) {
+    const uint32_t p1 = l[2], p0 = l[3], q0 = l[4], q1 = l[5];
+    // D = 4*(q0 - p0) + p1 - q1 + 4 + 0x6000  (|.| <= 5 * 4095 < 0x6000)
+    const uint32_t D = (q0 << 2) + p1 + 0x60046004u - ((p0 << 2) + q1);
+    const uint32_t db = (D >> 3) & 0x1fff1fffu;                            // delta + 0xc00
+    const uint32_t dc = __vminu2(__vmaxu2(db, 0x0c000c00u - rep2(tc)), 0x0c000c00u + rep2(tc));
+    const uint32_t nc00 = rep2(-0xc00);
+    if (!no_p) l[3] = __viaddmin_s16x2_relu(p0 + dc, nc00, maxv2);
+    if (!no_q) l[4] = __viaddmin_s16x2_relu(q0 + 0x18001800u - dc, nc00, maxv2);
+}
+
+// one luma segment = two line pairs; `a` / `b` = the segment's first / last line, unpacked
+__device__ __forceinline__ void luma_segment_packed(uint32_t (&u)[8], uint32_t (&w)[8], const int (&a)[8],
+                                                    const int (&b)[8], const Seg &s, uint32_t maxv2) {
+    const Dec d = decide(a, b, s);
+    if (!d.on) return;
+    if (d.strong) {
+        strong_pair(u, s.tc, s.no_p, s.no_q);
+        strong_pair(w, s.tc, s.no_p, s.no_q);
+    } else {
+        weak_pair(u, s.tc, d.dep, d.deq, s.no_p, s.no_q, maxv2);
+        weak_pair(w, s.tc, d.dep, d.deq, s.no_p, s.no_q, maxv2);
+    }
+}
+
+// half-row (4 samples) <-> two packed words
+template <typename T>
+__device__ __forceinline__ void loadw(const T *p, uint32_t &w0, uint32_t &w1);
+template <>
+__device__ __forceinline__ void loadw<uint16_t>(const uint16_t *p, uint32_t &w0, uint32_t &w1) {
+    const uint2 v = *reinterpret_cast<const uint2 *>(p);
+    w0 = v.x; w1 = v.y;
+}
+template <>
+__device__ __forceinline__ void loadw<uint8_t>(const uint8_t *p, uint32_t &w0, uint32_t &w1) {
+    const uint32_t v = *reinterpret_cast<const uint32_t *>(p);
+    w0 = prmt(v, 0, 0x4140); w1 = prmt(v, 0, 0x4342);
+}
+template <typename T>
+__device__ __forceinline__ void storew(T *p, uint32_t w0, uint32_t w1);
+template <>
+__device__ __forceinline__ void storew<uint16_t>(uint16_t *p, uint32_t w0, uint32_t w1) {
+    *reinterpret_cast<uint2 *>(p) = make_uint2(w0, w1);
+}
+template <>
+__device__ __forceinline__ void storew<uint8_t>(uint8_t *p, uint32_t w0, uint32_t w1) {
+    *reinterpret_cast<uint32_t *>(p) = prmt(w0, w1, 0x6420);
+}
+
 // grid = (ceil(items / warps per CTA), 3 components, pictures); chroma planes use the first
 // part of the luma-sized item range.
-template <typename T>
+template <typename T, bool PACKED>
 __global__ void __launch_bounds__(kDbkThreads) deblock_kernel(const __grid_constant__ DbkArgs a) {
     __shared__ uint8_t s_beta[52], s_tc[54];
     if (threadIdx.x < 52) s_beta[threadIdx.x] = c_beta[threadIdx.x];
@@ -209,18 +327,6 @@ __global__ void __launch_bounds__(kDbkThreads) deblock_kernel(const __grid_const
     const int x0 = 8 * i - 4, y0 = 8 * j - 4;
     const bool has_l = i > 0, has_r = 8 * i < w;
 
-    // ---- load the shifted block --------------------------------------------------------
-    int v[8][8];
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const int y = y0 + r;
-        const bool row_ok = y >= 0 && y < h;
-#pragma unroll
-        for (int k = 0; k < 8; k++) v[r][k] = 0;
-        if (row_ok && has_l) load4<T>(base + (size_t)y * stride + x0, v[r], 0);
-        if (row_ok && has_r) load4<T>(base + (size_t)y * stride + x0 + 4, v[r], 4);
-    }
-
     // ---- per-segment parameters ----------------------------------------------------------
     const p265_dbk_ctb *cp = a.ctb + (size_t)pic * a.ctbs_w * a.ctbs_h;
     auto ctb_of = [&](int bi, int bj) {
@@ -238,6 +344,116 @@ __global__ void __launch_bounds__(kDbkThreads) deblock_kernel(const __grid_const
         sv[1] = make_seg<false>(bs_vl, e11, e01, ctb_of(I, J), c, bd, s_beta, s_tc);
         sh[0] = make_seg<false>(bs_hl, e01, e00, ctb_of(I - 1, J), c, bd, s_beta, s_tc);
         sh[1] = make_seg<false>(bs_hr, e11, e10, ctb_of(I, J), c, bd, s_beta, s_tc);
+    }
+
+    if constexpr (PACKED) {
+        const uint32_t maxv2 = rep2(maxv);
+        // W[r][k]: row r, samples (2k, 2k+1) of the shifted block
+        uint32_t W[8][4];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int y = y0 + r;
+            const bool row_ok = y >= 0 && y < h;
+            W[r][0] = W[r][1] = W[r][2] = W[r][3] = 0u;
+            if (row_ok && has_l) loadw<T>(base + (size_t)y * stride + x0, W[r][0], W[r][1]);
+            if (row_ok && has_r) loadw<T>(base + (size_t)y * stride + x0 + 4, W[r][2], W[r][3]);
+        }
+        // ---- vertical edge: pair rows (2rp, 2rp+1) -> X[col][rp], filter, transpose back -------
+        if (sv[0].bs | sv[1].bs) {
+            uint32_t X[8][4];
+#pragma unroll
+            for (int rp = 0; rp < 4; rp++) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    X[2 * k][rp] = prmt(W[2 * rp][k], W[2 * rp + 1][k], 0x5410);
+                    X[2 * k + 1][rp] = prmt(W[2 * rp][k], W[2 * rp + 1][k], 0x7632);
+                }
+            }
+#pragma unroll
+            for (int sgm = 0; sgm < 2; sgm++) {
+                const Seg s = sv[sgm];
+                if (s.bs == 0) continue;
+                uint32_t u[8], w2[8];
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    u[t] = X[t][2 * sgm];
+                    w2[t] = X[t][2 * sgm + 1];
+                }
+                if (cs) {
+                    chroma_pair(u, s.tc, s.no_p, s.no_q, maxv2);
+                    chroma_pair(w2, s.tc, s.no_p, s.no_q, maxv2);
+                } else {
+                    int la[8], lb[8];
+#pragma unroll
+                    for (int t = 0; t < 8; t++) {
+                        la[t] = (int)(u[t] & 0xffffu);      // row 4 sgm
+                        lb[t] = (int)(w2[t] >> 16);         // row 4 sgm + 3
+                    }
+                    luma_segment_packed(u, w2, la, lb, s, maxv2);
+                }
+#pragma unroll
+                for (int t = 1; t < 7; t++) {
+                    X[t][2 * sgm] = u[t];
+                    X[t][2 * sgm + 1] = w2[t];
+                }
+            }
+#pragma unroll
+            for (int rp = 0; rp < 4; rp++) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    W[2 * rp][k] = prmt(X[2 * k][rp], X[2 * k + 1][rp], 0x5410);
+                    W[2 * rp + 1][k] = prmt(X[2 * k][rp], X[2 * k + 1][rp], 0x7632);
+                }
+            }
+        }
+        // ---- horizontal edge: the words already pair columns (2k, 2k+1) ----------------------
+#pragma unroll
+        for (int sgm = 0; sgm < 2; sgm++) {
+            const Seg s = sh[sgm];
+            if (s.bs == 0) continue;
+            uint32_t u[8], w2[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                u[r] = W[r][2 * sgm];
+                w2[r] = W[r][2 * sgm + 1];
+            }
+            if (cs) {
+                chroma_pair(u, s.tc, s.no_p, s.no_q, maxv2);
+                chroma_pair(w2, s.tc, s.no_p, s.no_q, maxv2);
+            } else {
+                int la[8], lb[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    la[r] = (int)(u[r] & 0xffffu);          // column 4 sgm
+                    lb[r] = (int)(w2[r] >> 16);             // column 4 sgm + 3
+                }
+                luma_segment_packed(u, w2, la, lb, s, maxv2);
+            }
+#pragma unroll
+            for (int r = 1; r < 7; r++) {
+                W[r][2 * sgm] = u[r];
+                W[r][2 * sgm + 1] = w2[r];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int y = y0 + r;
+            const bool row_ok = y >= 0 && y < h;
+            if (row_ok && has_l) storew<T>(base + (size_t)y * stride + x0, W[r][0], W[r][1]);
+            if (row_ok && has_r) storew<T>(base + (size_t)y * stride + x0 + 4, W[r][2], W[r][3]);
+        }
+        return;
+    }
+    // ---- load the shifted block --------------------------------------------------------
+    int v[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int y = y0 + r;
+        const bool row_ok = y >= 0 && y < h;
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[r][k] = 0;
+        if (row_ok && has_l) load4<T>(base + (size_t)y * stride + x0, v[r], 0);
+        if (row_ok && has_r) load4<T>(base + (size_t)y * stride + x0 + 4, v[r], 4);
     }
 
     // ---- vertical edge x = 8i: rows 0-3 and 4-7, across = columns -----------------------
@@ -331,8 +547,11 @@ int launch_deblock(p265_ctx *ctx, void *d_pix, const p265_pic_geom *g, int ctb_l
     const int items = a.chunks_y * a.rows_y;
     const int warps = kDbkThreads / 32;
     const dim3 grid((unsigned)((items + warps - 1) / warps), 3, g->n_pics);
-    if (g->bit_depth_y > 8 || g->bit_depth_c > 8) deblock_kernel<uint16_t><<<grid, kDbkThreads, 0, ctx->stream>>>(a);
-    else deblock_kernel<uint8_t><<<grid, kDbkThreads, 0, ctx->stream>>>(a);
+    // packed 2 x 16-bit arithmetic needs 12 * maxVal < 0x6000: bit depths up to 11
+    const int bd_max = g->bit_depth_y > g->bit_depth_c ? g->bit_depth_y : g->bit_depth_c;
+    if (bd_max > 11) deblock_kernel<uint16_t, false><<<grid, kDbkThreads, 0, ctx->stream>>>(a);
+    else if (bd_max > 8) deblock_kernel<uint16_t, true><<<grid, kDbkThreads, 0, ctx->stream>>>(a);
+    else deblock_kernel<uint8_t, true><<<grid, kDbkThreads, 0, ctx->stream>>>(a);
     P265_CUDA(cudaGetLastError());
     ctx->launches++;
     return P265_OK;

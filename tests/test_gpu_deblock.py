@@ -12,6 +12,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("width,height,bit_depth,ctb_log2,dense", [
     (64, 64, 8, 6, True), (128, 72, 8, 5, False), (352, 288, 8, 6, False), (200, 120, 10, 4, True),
     (1920, 1088, 8, 6, False), (264, 136, 10, 6, False), (8, 8, 8, 4, True), (16, 8, 10, 4, True),
+    (128, 64, 12, 6, True), (128, 64, 11, 6, True), (136, 72, 9, 5, False),
 ])
 def test_deblock_matches_oracle(engine, c_oracle, width, height, bit_depth, ctb_log2, dense):
     geom, buf, blk, ctb = synth.deblock_batch(width, height, bit_depth, 2, ctb_log2, seed=width + height,
@@ -53,6 +54,18 @@ def test_noise_picture_hits_every_decision(engine, c_oracle):
     buf[::2] = smooth[::2]
     got = engine.deblock(buf, geom, 6, blk, ctb)
     assert np.array_equal(got, c_oracle.deblock_batch(buf, geom, 6, blk, ctb))
+
+
+def test_full_range_noise_at_every_bit_depth(engine, c_oracle):
+    """Worst-case magnitudes for the packed arithmetic (bit depths <= 11) and the 32-bit path (12)."""
+    for bd in (8, 9, 10, 11, 12):
+        geom, buf, blk, ctb = synth.deblock_batch(256, 128, bd, 1, 6, seed=40 + bd, dense=True)
+        rng = np.random.default_rng(bd)
+        noise = rng.integers(0, 1 << bd, buf.size).astype(buf.dtype)
+        flat = np.where(rng.random(buf.size) < 0.5, 0, (1 << bd) - 1).astype(buf.dtype)
+        for data in (noise, flat, np.where(np.arange(buf.size) % 16 < 8, noise, buf)):
+            got = engine.deblock(data, geom, 6, blk, ctb)
+            assert np.array_equal(got, c_oracle.deblock_batch(data, geom, 6, blk, ctb)), bd
 
 
 def test_bad_arguments(engine):
