@@ -17,14 +17,18 @@
 // own 8-sample grid (Bs = 2 only, one sample per side).
 //
 // Per segment the lane derives beta / tC from the edge map (QpY of the two CUs, Bs) and the
-// CTB's slice offsets through two small tables staged in shared memory.
+// CTB's slice offsets (beta' in closed form, tC' through a 54-byte read-only table).
 #include <cuda_runtime.h>
 
 #include "internal.h"
 
 namespace p265 {
 
+static_assert(sizeof(p265_dbk_ctb) == 4, "p265_dbk_ctb is read as one 32-bit word");
 constexpr int kDbkThreads = 128;
+#ifndef P265_DBK_CTAS
+#define P265_DBK_CTAS 6  // 80 registers; measured best of 4..8 on the 4K 10-bit workload
+#endif
 
 struct DbkArgs {
     void *pix;
@@ -37,13 +41,10 @@ struct DbkArgs {
     int32_t w8, h8;              // luma 8x8 blocks per row / column
     int32_t ctb_shift;           // ctb_log2 - 3
     int32_t ctbs_w, ctbs_h;
-    int32_t chunks_y, rows_y;    // luma: 32-block chunks per block row, block rows
+    int32_t items_y, items_c;    // warp items (32 shifted blocks of one block row) per luma / chroma plane
 };
 
-__constant__ uint8_t c_beta[52] = {0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  6,  7,
-                                   8,  9,  10, 11, 12, 13, 14, 15, 16, 17, 18, 20, 22, 24, 26, 28, 30, 32,
-                                   34, 36, 38, 40, 42, 44, 46, 48, 50, 52, 54, 56, 58, 60, 62, 64};
-__constant__ uint8_t c_tc[54] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1,  1,  1,  1,  1,  1,  1,  1,
+__device__ const uint8_t g_tc[54] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1,  1,  1,  1,  1,  1,  1,  1,
                                  2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 5, 5, 6, 6, 7, 8, 9, 10, 11, 13, 14, 16, 18, 20, 22, 24};
 
 __device__ __forceinline__ int clip3i(int lo, int hi, int v) { return min(max(v, lo), hi); }
@@ -63,22 +64,28 @@ struct Seg {
     bool no_p, no_q;
 };
 
+// beta' of Table 8-11 in closed form: 0 below 16, Q - 10 up to 28, 2Q - 38 from 29 on
+__device__ __forceinline__ int beta_prime(int q) { return q < 16 ? 0 : (q < 29 ? q - 10 : 2 * q - 38); }
+
+// p265_dbk_ctb read as one 32-bit word: beta_offset_div2 | tc_offset_div2 << 8 | cb << 16 | cr << 24
+__device__ __forceinline__ int ctb_field(uint32_t par, int byte) { return ((int)(par << (24 - 8 * byte))) >> 24; }
+
 // 8.7.2.5.3 (beta, tC) for one segment; eq / ep = edge-map entries of the blocks holding q0 / p0
 template <bool CHROMA>
-__device__ __forceinline__ Seg make_seg(int bs, uint32_t eq, uint32_t ep, const p265_dbk_ctb par, int c, int bd,
-                                        const uint8_t *s_beta, const uint8_t *s_tc) {
+__device__ __forceinline__ Seg make_seg(int bs, uint32_t eq, uint32_t ep, uint32_t par, int c, int bd) {
     Seg s;
     s.bs = CHROMA ? (bs == 2 ? 2 : 0) : bs;
     s.no_p = (ep & P265_DBK_NO_FILTER) != 0;
     s.no_q = (eq & P265_DBK_NO_FILTER) != 0;
     const int qpl = (blk_qp(eq) + blk_qp(ep) + 1) >> 1;
+    const int tc_off = 2 * ctb_field(par, 1);
     if (CHROMA) {
-        const int qpc = chroma_qp(qpl + (c == 1 ? par.cb_qp_offset : par.cr_qp_offset));
-        s.tc = (int)s_tc[clip3i(0, 53, qpc + 2 + 2 * par.tc_offset_div2)] << (bd - 8);
+        const int qpc = chroma_qp(qpl + ctb_field(par, c == 1 ? 2 : 3));
+        s.tc = (int)__ldg(&g_tc[clip3i(0, 53, qpc + 2 + tc_off)]) << (bd - 8);
         s.beta = 0;
     } else {
-        s.beta = (int)s_beta[clip3i(0, 51, qpl + 2 * par.beta_offset_div2)] << (bd - 8);
-        s.tc = (int)s_tc[clip3i(0, 53, qpl + 2 * (s.bs - 1) + 2 * par.tc_offset_div2)] << (bd - 8);
+        s.beta = beta_prime(clip3i(0, 51, qpl + 2 * ctb_field(par, 0))) << (bd - 8);
+        s.tc = (int)__ldg(&g_tc[clip3i(0, 53, qpl + 2 * (s.bs - 1) + tc_off)]) << (bd - 8);
     }
     return s;
 }
@@ -286,19 +293,24 @@ __device__ __forceinline__ void storew<uint8_t>(uint8_t *p, uint32_t w0, uint32_
 // grid = (ceil(items / warps per CTA), 3 components, pictures); chroma planes use the first
 // part of the luma-sized item range.
 template <typename T, bool PACKED>
-__global__ void __launch_bounds__(kDbkThreads) deblock_kernel(const __grid_constant__ DbkArgs a) {
-    __shared__ uint8_t s_beta[52], s_tc[54];
-    if (threadIdx.x < 52) s_beta[threadIdx.x] = c_beta[threadIdx.x];
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + 54) s_tc[threadIdx.x - 64] = c_tc[threadIdx.x - 64];
-    __syncthreads();
-
-    const int c = blockIdx.y, pic = blockIdx.z;
+__global__ void __launch_bounds__(kDbkThreads, PACKED ? P265_DBK_CTAS : 1) deblock_kernel(const __grid_constant__ DbkArgs a) {
+    // grid = (luma items + 2 x chroma items, 1, pictures); an item = 32 consecutive shifted blocks
+    const int pic = blockIdx.z;
+    int item = blockIdx.x * (kDbkThreads / 32) + (threadIdx.x >> 5);
+    int c = 0;
+    if (item >= a.items_y) {
+        item -= a.items_y;
+        c = 1;
+        if (item >= a.items_c) {
+            item -= a.items_c;
+            c = 2;
+            if (item >= a.items_c) return;
+        }
+    }
     const int cs = c ? 1 : 0;
     const int w = a.width >> cs, h = a.height >> cs;
-    const int nbx = ((w + 3) >> 3) + 1, nby = ((h + 3) >> 3) + 1;
+    const int nbx = ((w + 3) >> 3) + 1;
     const int chunks = (nbx + 31) >> 5;
-    const int item = blockIdx.x * (kDbkThreads / 32) + (threadIdx.x >> 5);
-    if (item >= chunks * nby) return;
     const int j = item / chunks;
     const int i = (item - j * chunks) * 32 + (threadIdx.x & 31);
     if (i >= nbx) return;
@@ -328,22 +340,23 @@ __global__ void __launch_bounds__(kDbkThreads) deblock_kernel(const __grid_const
     const bool has_l = i > 0, has_r = 8 * i < w;
 
     // ---- per-segment parameters ----------------------------------------------------------
-    const p265_dbk_ctb *cp = a.ctb + (size_t)pic * a.ctbs_w * a.ctbs_h;
+    const uint32_t *cp = reinterpret_cast<const uint32_t *>(a.ctb) + (size_t)pic * a.ctbs_w * a.ctbs_h;
     auto ctb_of = [&](int bi, int bj) {
         const int ci = min(max(bi, 0) >> a.ctb_shift, a.ctbs_w - 1), cj = min(max(bj, 0) >> a.ctb_shift, a.ctbs_h - 1);
-        return cp[cj * a.ctbs_w + ci];
+        return __ldg(cp + cj * a.ctbs_w + ci);
     };
+    const uint32_t par11 = ctb_of(I, J), par10 = ctb_of(I, J - 1), par01 = ctb_of(I - 1, J);
     Seg sv[2], sh[2];
     if (cs) {
-        sv[0] = make_seg<true>(bs_vu, e10, e00, ctb_of(I, J - 1), c, bd, s_beta, s_tc);
-        sv[1] = make_seg<true>(bs_vl, e11, e01, ctb_of(I, J), c, bd, s_beta, s_tc);
-        sh[0] = make_seg<true>(bs_hl, e01, e00, ctb_of(I - 1, J), c, bd, s_beta, s_tc);
-        sh[1] = make_seg<true>(bs_hr, e11, e10, ctb_of(I, J), c, bd, s_beta, s_tc);
+        sv[0] = make_seg<true>(bs_vu, e10, e00, par10, c, bd);
+        sv[1] = make_seg<true>(bs_vl, e11, e01, par11, c, bd);
+        sh[0] = make_seg<true>(bs_hl, e01, e00, par01, c, bd);
+        sh[1] = make_seg<true>(bs_hr, e11, e10, par11, c, bd);
     } else {
-        sv[0] = make_seg<false>(bs_vu, e10, e00, ctb_of(I, J - 1), c, bd, s_beta, s_tc);
-        sv[1] = make_seg<false>(bs_vl, e11, e01, ctb_of(I, J), c, bd, s_beta, s_tc);
-        sh[0] = make_seg<false>(bs_hl, e01, e00, ctb_of(I - 1, J), c, bd, s_beta, s_tc);
-        sh[1] = make_seg<false>(bs_hr, e11, e10, ctb_of(I, J), c, bd, s_beta, s_tc);
+        sv[0] = make_seg<false>(bs_vu, e10, e00, par10, c, bd);
+        sv[1] = make_seg<false>(bs_vl, e11, e01, par11, c, bd);
+        sh[0] = make_seg<false>(bs_hl, e01, e00, par01, c, bd);
+        sh[1] = make_seg<false>(bs_hr, e11, e10, par11, c, bd);
     }
 
     if constexpr (PACKED) {
@@ -541,12 +554,13 @@ int launch_deblock(p265_ctx *ctx, void *d_pix, const p265_pic_geom *g, int ctb_l
     const int ctb = 1 << ctb_log2;
     a.ctbs_w = (g->width + ctb - 1) / ctb;
     a.ctbs_h = (g->height + ctb - 1) / ctb;
-    a.chunks_y = ((a.w8 + 1) + 31) / 32;
-    a.rows_y = a.h8 + 1;
+    auto items_of = [](int w, int h) { return ((((w + 3) >> 3) + 1 + 31) >> 5) * (((h + 3) >> 3) + 1); };
+    a.items_y = items_of(g->width, g->height);
+    a.items_c = items_of(g->width / 2, g->height / 2);
     if (g->n_pics > 65535) return set_error(P265_EINVAL, "too many pictures in one deblocking batch");
-    const int items = a.chunks_y * a.rows_y;
+    const int items = a.items_y + 2 * a.items_c;
     const int warps = kDbkThreads / 32;
-    const dim3 grid((unsigned)((items + warps - 1) / warps), 3, g->n_pics);
+    const dim3 grid((unsigned)((items + warps - 1) / warps), 1, g->n_pics);
     // packed 2 x 16-bit arithmetic needs 12 * maxVal < 0x6000: bit depths up to 11
     const int bd_max = g->bit_depth_y > g->bit_depth_c ? g->bit_depth_y : g->bit_depth_c;
     if (bd_max > 11) deblock_kernel<uint16_t, false><<<grid, kDbkThreads, 0, ctx->stream>>>(a);
