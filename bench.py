@@ -142,6 +142,9 @@ def alg_int_ops(res):
 
 # ------------------------------------------------------------------ GPU arm
 def run_gpu(args):
+    # NCCL_DEBUG=VERSION / INFO make NCCL print to stdout; rank 0's stdout must hold the JSON line only
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
     from p265_b200.engine import Engine
