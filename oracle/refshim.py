@@ -142,3 +142,59 @@ def load(workdir: str | None = None):
 
 if __name__ == "__main__":
     print(build(force=True))
+
+
+def enable_multi_slice(ns) -> None:
+    """Test-harness patch: the reference creates a CTU object only for the first slice
+    segment of a picture (slice.py:237-238), so a second slice re-parses the previous CTU and
+    trips `assert self.ctu.addr_rs not in self.ctus` (image.py:15).  Wrap SliceSegmentData.parse
+    so that a non-first, independent slice segment starts at its slice_segment_address --
+    needed only for the multi-slice fuzz streams (tests/golden/make_fuzz_streams.py)."""
+    cls = ns.dec.nalu.slice.SliceSegmentData if hasattr(ns.dec, "nalu") else sys.modules["slice"].SliceSegmentData
+    if getattr(cls, "_p265_multi_slice", False):
+        return
+    ctu_mod = sys.modules["ctu"]
+    orig = cls.parse
+
+    def parse(self):
+        hdr = self.ctx.img.slice_hdrs[-1]
+        if not hdr.first_slice_segment_in_pic_flag and not hdr.dependent_slice_segment_flag:
+            self.ctx.img.ctu = ctu_mod.Ctu(self.ctx, addr_rs=int(hdr.slice_segment_address))
+        return orig(self)
+
+    cls.parse = parse
+    cls._p265_multi_slice = True
+    # ... and gives `slice_addr` only to the first CTU of a slice segment (slice.py:252; every
+    # other Ctu keeps the constructor's 0, ctu.py:13): propagate it when the next CTU is created
+    img_cls = sys.modules["image"].Image
+    orig_next = img_cls.next_ctu
+
+    def next_ctu(self, end_of_slice_segment_flag):
+        orig_next(self, end_of_slice_segment_flag)
+        if not end_of_slice_segment_flag:
+            self.ctu.slice_addr = self.slice_hdr.slice_segment_address
+
+    img_cls.next_ctu = next_ctu
+    # the reference's Sao.parse leaves sao_merge_left_flag / sao_merge_up_flag unassigned when
+    # the neighbouring CTB belongs to another slice (sao.py:26-41 -> AttributeError at :50);
+    # the product's drop-in `sao` module (golden-log identical, tests/test_dropin_golden.py)
+    # takes its place, exactly as INTEGRATION.md describes
+    from p265_b200 import sao_api
+    sys.modules["ctu"].sao = sao_api
+
+
+def enable_transquant_bypass(ns) -> None:
+    """Test-harness patch: cu.py:102-103 calls `self.parse__cu_transquant_bypass_flag()`, which
+    the reference never defines.  The syntax element is one context-coded bin, ctxInc 0
+    (9.3.4.2, Table 9-8; the reference's own init table has the entry, cabac.py:16)."""
+    cls = sys.modules["cu"].Cu
+    if hasattr(cls, "parse__cu_transquant_bypass_flag"):
+        return
+
+    def parse__cu_transquant_bypass_flag(self):
+        init_type = int(getattr(self.ctx.img.slice_hdr, "init_type", 0) or 0)
+        bit = self.ctx.cabac.decode_decision("cu_transquant_bypass_flag", init_type)
+        sys.modules["log"].syntax.info("cu_transquant_bypass_flag = %d" % bit)
+        return bit
+
+    cls.parse__cu_transquant_bypass_flag = parse__cu_transquant_bypass_flag

@@ -1,0 +1,173 @@
+"""Shared driver of the fuzz-stream tests (CPU oracle backend and GPU backend).
+
+The streams under tests/golden/fuzz/ were written by tests/golden/make_fuzz_streams.py (random
+bins through the reference's own parser, CABAC-encoded) and decoded by libavcodec; the answers are
+in tests/golden/fuzz_ffmpeg.npz.  A test parses a stream with the reference parser (py3 shim),
+packs it with the product's packer and runs
+
+    residual (backend) -> host intra prediction + reconstruction  == libavcodec, loop filters skipped
+    -> deblocking (backend) -> SAO (backend)                       == libavcodec's output pictures
+
+Two places where libavcodec 62.11 deviates from the standard are reproduced here, so that the
+comparison stays bit-exact everywhere and the deviations are characterised exactly:
+
+  * slice_loop_filter_across_slices_enabled_flag in SAO: 8.7.3 uses the flag of the LATER of the
+    two slices (current sample's slice for left / upper neighbours, the neighbour's slice for
+    right / lower ones); libavcodec uses the current CTB's flag for all eight directions.
+  * cu_transquant_bypass + SAO on chroma: libavcodec restores the unfiltered samples of bypass
+    CUs only in the top-left (CtbSize/2)^2 luma area of a CTB for the chroma planes (the
+    restore loop takes the chroma width / height as luma extents).
+
+`out_spec` (the standard's rules, what the product implements) is returned next to `out_lav`
+(libavcodec's rules) so the tests can also state where the two differ.
+"""
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+from conftest import GOLDEN
+
+sys.path.insert(0, GOLDEN)
+FUZZ_DIR = os.path.join(GOLDEN, "fuzz")
+COMPS = ("y", "cb", "cr")
+
+
+def manifest():
+    with open(os.path.join(FUZZ_DIR, "manifest.json")) as fh:
+        return json.load(fh)
+
+
+def answers():
+    return np.load(os.path.join(GOLDEN, "fuzz_ffmpeg.npz"))
+
+
+_ns = None
+
+
+def parse(name, cfg):
+    """(images, sps, pps) of a fuzz stream through the reference's parser."""
+    global _ns
+    import make_fuzz_streams as gen
+    from oracle import refshim
+    if not refshim.shim_available():
+        if not refshim.reference_available():
+            import pytest
+            pytest.skip("baseline/_ref shim not present")
+        refshim.build()
+    if _ns is None:
+        _ns = refshim.load(tempfile.mkdtemp(prefix="p265ref_"))
+    gen.prepare(_ns, cfg)
+    return gen.run_parser(_ns, os.path.join(FUZZ_DIR, name + ".bin"))
+
+
+def lav_sao_avail(img, sps):
+    """Per-CTB neighbour masks under libavcodec's rule (current CTB's flag for every direction)."""
+    wc, hc = int(sps.pic_width_in_ctbs_y), int(sps.pic_height_in_ctbs_y)
+    sl = np.zeros((hc, wc), np.int64)
+    for a, ctu in img.ctus.items():
+        sl[a // wc, a % wc] = int(ctu.slice_addr)
+    flag = {int(h.slice_segment_address): int(getattr(h, "slice_loop_filter_across_slices_enabled_flag", 1))
+            for h in img.slice_hdrs}
+    out = np.zeros((hc, wc), np.uint16)
+    for ry in range(hc):
+        for rx in range(wc):
+            m = 0
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    ny, nx = ry + dy, rx + dx
+                    if 0 <= ny < hc and 0 <= nx < wc and (sl[ny, nx] == sl[ry, rx] or flag[int(sl[ry, rx])]):
+                        m |= 1 << ((dy + 1) * 3 + (dx + 1))
+            out[ry, rx] = m
+    return out
+
+
+def lav_chroma_restored(nf, width, height, ctb_log2):
+    """Chroma-plane mask of bypass samples libavcodec restores after SAO (see module docstring)."""
+    hc, wc = height // 2, width // 2
+    yc, xc = np.mgrid[0:hc, 0:wc]
+    yl, xl = 2 * yc, 2 * xc
+    ctb = 1 << ctb_log2
+    x0, y0 = (xl >> ctb_log2) << ctb_log2, (yl >> ctb_log2) << ctb_log2
+    lim_x = np.minimum(ctb // 2, (width - x0) // 2)
+    lim_y = np.minimum(ctb // 2, (height - y0) // 2)
+    bypass = nf[yl >> 3, xl >> 3].astype(bool)
+    return bypass, bypass & (xl - x0 < lim_x) & (yl - y0 < lim_y)
+
+
+def decode_picture(img, sps, pps, backend):
+    """Returns (rec, out_spec, out_lav): three (Y, Cb, Cr) tuples."""
+    from p265_b200 import deblock_api, intra_host, packer, sao_api, scaling_list
+    from p265_b200.picture import PicGeom
+    w, h = int(sps.pic_width_in_luma_samples), int(sps.pic_height_in_luma_samples)
+    bd = int(sps.bit_depth_y)
+    ctb_log2 = int(sps.ctb_log2_size_y)
+    batch = packer.pack_pictures([img], sps, scaling_list.active_table(sps, pps))
+    res = backend.residual(batch)
+    rec = intra_host.reconstruct_intra_picture(img, sps, pps, [batch.geom.plane_view(res, 0, c) for c in range(3)])
+    geom = PicGeom(w, h, 1, bd, int(sps.bit_depth_c))
+    buf = np.zeros(geom.total_elems(), np.uint8 if bd <= 8 else np.uint16)
+    for c in range(3):
+        geom.plane_view(buf, 0, c)[:] = rec[c]
+    blk, ctb = deblock_api.edge_map_from_picture(img, sps, pps)
+    dbk = backend.deblock(buf, geom, ctb_log2, blk, ctb)
+    nf = sao_api.no_filter_from_picture(img, sps)
+
+    def sao(avail, no_filter):
+        params = packer.sao_params_from_picture(img, sps, avail)
+        o = backend.sao(dbk, geom, ctb_log2, params, no_filter)
+        return [geom.plane_view(o, 0, c).copy() for c in range(3)]
+
+    out_spec = sao(sao_api.availability_from_picture(img, sps, pps), nf)
+    out_lav = sao(lav_sao_avail(img, sps), nf)
+    if nf is not None:
+        unfiltered = sao(lav_sao_avail(img, sps), None)
+        bypass, restored = lav_chroma_restored(nf, w, h, ctb_log2)
+        for c in (1, 2):
+            out_lav[c] = np.where(bypass & ~restored, unfiltered[c], out_lav[c])
+    return rec, out_spec, out_lav
+
+
+def check_stream(name, cfg, backend, want):
+    """Runs every picture of a stream; returns per-picture counts of samples where the standard's
+    rules and libavcodec's differ (for the assertions the tests make about them)."""
+    imgs, sps, pps = parse(name, cfg)
+    assert len(imgs) == cfg["pictures"]
+    diffs = []
+    for p, img in enumerate(imgs):
+        rec, out_spec, out_lav = decode_picture(img, sps, pps, backend)
+        for c, n in enumerate(COMPS):
+            assert np.array_equal(rec[c], want["%s/rec%d_%s" % (name, p, n)]), (name, "rec", p, n)
+            assert np.array_equal(out_lav[c], want["%s/out%d_%s" % (name, p, n)]), (name, "out", p, n)
+        diffs.append([int((out_spec[c] != out_lav[c]).sum()) for c in range(3)])
+    return diffs
+
+
+class OracleBackend:
+    def __init__(self, c_oracle):
+        self.co = c_oracle
+
+    def residual(self, batch):
+        return self.co.residual_batch(batch)
+
+    def deblock(self, buf, geom, ctb_log2, blk, ctb):
+        return self.co.deblock_batch(buf, geom, ctb_log2, blk, ctb)
+
+    def sao(self, buf, geom, ctb_log2, params, nf):
+        return self.co.sao_batch(buf, geom, ctb_log2, params, nf)
+
+
+class GpuBackend:
+    def __init__(self, engine):
+        self.eng = engine
+
+    def residual(self, batch):
+        return self.eng.residual(batch)
+
+    def deblock(self, buf, geom, ctb_log2, blk, ctb):
+        return self.eng.deblock(buf, geom, ctb_log2, blk, ctb)
+
+    def sao(self, buf, geom, ctb_log2, params, nf):
+        return self.eng.sao(buf, geom, ctb_log2, params, no_filter=nf)

@@ -48,19 +48,24 @@ def _libs():
 
 
 def access_units(data: bytes):
-    """Annex-B byte stream -> one packet per picture (non-VCL NAL units ride with the next
-    VCL NAL unit; every picture of sanity.bin is a single slice)."""
+    """Annex-B byte stream -> one packet per picture: a new packet starts at the first non-VCL
+    NAL unit after a VCL one, or at a VCL NAL unit with first_slice_segment_in_pic_flag = 1."""
     pos = [m.start() for m in re.finditer(b"\x00\x00\x01", data)]
-    cur = b""
+    cur, have_vcl = b"", False
     for i, p in enumerate(pos):
         e = pos[i + 1] if i + 1 < len(pos) else len(data)
         if i + 1 < len(pos) and data[e - 1] == 0:
             e -= 1
         nal = data[p:e]
-        cur += b"\x00" + nal
-        if ((nal[3] >> 1) & 0x3F) < 32:
+        vcl = ((nal[3] >> 1) & 0x3F) < 32
+        first = vcl and len(nal) > 5 and (nal[5] & 0x80) != 0
+        if have_vcl and (not vcl or first):
             yield cur
-            cur = b""
+            cur, have_vcl = b"", False
+        cur += b"\x00" + nal
+        have_vcl = have_vcl or vcl
+    if have_vcl:
+        yield cur
 
 
 def decode(data: bytes, skip_loop_filter: bool):
@@ -77,6 +82,8 @@ def decode(data: bytes, skip_loop_filter: bool):
     avcodec.avcodec_receive_frame.argtypes = [C.c_void_p, C.c_void_p]
     avcodec.av_packet_unref.argtypes = [C.c_void_p]
     avutil.av_opt_set.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
+    avutil.av_get_pix_fmt_name.restype = C.c_char_p
+    avutil.av_get_pix_fmt_name.argtypes = [C.c_int]
     dec = avcodec.avcodec_find_decoder(AV_CODEC_ID_HEVC)
     ctx = avcodec.avcodec_alloc_context3(dec)
     if skip_loop_filter and avutil.av_opt_set(ctx, b"skip_loop_filter", b"all", 0) != 0:
@@ -89,13 +96,16 @@ def decode(data: bytes, skip_loop_filter: bool):
     def drain():
         while avcodec.avcodec_receive_frame(ctx, frm) >= 0:
             h = _FrameHead.from_address(frm)
-            if h.format != 0:
-                raise RuntimeError("expected yuv420p")
+            name = avutil.av_get_pix_fmt_name(h.format).decode()
+            if name not in ("yuv420p", "yuv420p10le", "yuv420p12le"):
+                raise RuntimeError("unexpected pixel format %s" % name)
+            dt = np.uint8 if name == "yuv420p" else np.dtype("<u2")
             planes = []
             for c in range(3):
                 hh, ww = (h.height, h.width) if c == 0 else (h.height // 2, h.width // 2)
                 buf = (C.c_uint8 * (h.linesize[c] * hh)).from_address(h.data[c])
-                planes.append(np.frombuffer(buf, np.uint8).reshape(hh, h.linesize[c])[:, :ww].copy())
+                rows = np.frombuffer(buf, np.uint8).reshape(hh, h.linesize[c])
+                planes.append(rows[:, :ww * dt.itemsize].copy().view(dt) if dt != np.uint8 else rows[:, :ww].copy())
             frames.append(planes)
 
     for au in access_units(data):

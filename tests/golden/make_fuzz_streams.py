@@ -1,0 +1,523 @@
+#!/usr/bin/env python
+"""Generate small all-intra HEVC test streams that exercise what sanity.bin does not, and
+their known answers from libavcodec (run in the dev container; needs /root/reference).
+
+    python tests/golden/make_fuzz_streams.py        # -> tests/golden/fuzz/*.bin + fuzz_ffmpeg.npz
+
+How a stream is made ("bin-level fuzzing through the reference's own parser"):
+
+  1. VPS / SPS / PPS / slice-segment headers are written by the little bit writer below
+     (H.265 7.3.1.1 - 7.3.6.1) for the feature set of the stream: bit depth 8 or 10, CTB size,
+     scaling_list_enabled_flag (default lists, or explicit lists in the PPS), cu_transquant_bypass,
+     transform_skip, sign data hiding, chroma QP offsets, deblocking offsets / disable, several
+     slices per picture with slice_loop_filter_across_slices_enabled_flag = 0, ...
+  2. The reference's parser (through the py3 shim) is run over the headers with its CABAC
+     *decoder hooked*: every decode_decision / decode_bypass / decode_terminate call returns a
+     bin drawn from a seeded policy and, at the same time, that bin is ENCODED by the CABAC
+     encoder below (9.3.4.x mirrored) with the context state the parser itself selected.  The
+     parser's control flow therefore writes a random but syntactically valid slice_segment_data().
+  3. Headers + encoded payloads are assembled into an Annex-B stream (emulation prevention
+     included).  The unhooked reference parser must read back exactly what the hooked run
+     produced (this checks the encoder), and libavcodec decodes the stream twice (loop filters
+     skipped / normal) -> the known answers.
+
+The streams are this repository's own data (nothing of the reference is stored in them).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+sys.path.insert(0, HERE)
+
+from make_ffmpeg_fixture import decode as ffmpeg_decode  # noqa: E402
+from oracle import refshim  # noqa: E402
+
+OUT_DIR = os.path.join(HERE, "fuzz")
+
+
+# ------------------------------------------------------------------------ bit writing
+class BitWriter:
+    def __init__(self):
+        self.bits = []
+
+    def u(self, n, v):
+        assert 0 <= v < (1 << n), (n, v)
+        self.bits += [(v >> (n - 1 - i)) & 1 for i in range(n)]
+
+    def ue(self, v):
+        v += 1
+        n = v.bit_length()
+        self.bits += [0] * (n - 1)
+        self.u(n, v)
+
+    def se(self, v):
+        self.ue(2 * v - 1 if v > 0 else -2 * v)
+
+    def align_one(self):                       # rbsp_trailing_bits() / byte_alignment()
+        self.bits.append(1)
+        while len(self.bits) % 8:
+            self.bits.append(0)
+
+    def to_bytes(self) -> bytes:
+        assert len(self.bits) % 8 == 0
+        return bytes(int("".join(map(str, self.bits[i:i + 8])), 2) for i in range(0, len(self.bits), 8))
+
+
+def escape(rbsp: bytes) -> bytes:
+    """emulation_prevention_three_byte insertion (7.4.2)."""
+    out, zeros = bytearray(), 0
+    for b in rbsp:
+        if zeros >= 2 and b <= 3:
+            out.append(3)
+            zeros = 0
+        out.append(b)
+        zeros = zeros + 1 if b == 0 else 0
+    if out and out[-1] == 0:                   # cabac_zero_words are not used; keep a NAL from ending in 0x00
+        out.append(3)
+    return bytes(out)
+
+
+def nal_unit(nal_type: int, rbsp: bytes) -> bytes:
+    hdr = BitWriter()
+    hdr.u(1, 0); hdr.u(6, nal_type); hdr.u(6, 0); hdr.u(3, 1)
+    return b"\x00\x00\x00\x01" + hdr.to_bytes() + escape(rbsp)
+
+
+def profile_tier_level(w: BitWriter, profile_idc: int):
+    w.u(2, 0); w.u(1, 0); w.u(5, profile_idc)
+    for i in range(32):
+        w.u(1, 1 if i == profile_idc or (profile_idc == 1 and i == 2) else 0)
+    w.u(1, 1); w.u(1, 0); w.u(1, 0); w.u(1, 1)                 # progressive, frame only
+    w.u(32, 0); w.u(12, 0)                                     # general_reserved_zero_44bits
+    w.u(8, 93)                                                 # level 3.1
+
+
+def vps_rbsp(cfg) -> bytes:
+    w = BitWriter()
+    w.u(4, 0); w.u(2, 3); w.u(6, 0); w.u(3, 0); w.u(1, 1); w.u(16, 0xFFFF)
+    profile_tier_level(w, cfg["profile"])
+    w.u(1, 1); w.ue(1); w.ue(0); w.ue(0)                       # ordering info: dpb 2, no reorder
+    w.u(6, 0); w.ue(0)                                         # vps_max_layer_id, num_layer_sets_minus1
+    w.u(1, 0); w.u(1, 0)                                       # timing info, extension
+    w.align_one()
+    return w.to_bytes()
+
+
+def sps_rbsp(cfg) -> bytes:
+    w = BitWriter()
+    w.u(4, 0); w.u(3, 0); w.u(1, 1)
+    profile_tier_level(w, cfg["profile"])
+    w.ue(0); w.ue(1)                                           # sps id, chroma_format_idc 4:2:0
+    w.ue(cfg["width"]); w.ue(cfg["height"])
+    w.u(1, 0)                                                  # conformance_window_flag
+    w.ue(cfg["bit_depth"] - 8); w.ue(cfg["bit_depth"] - 8)
+    w.ue(4)                                                    # log2_max_pic_order_cnt_lsb_minus4
+    w.u(1, 1); w.ue(1); w.ue(0); w.ue(0)
+    w.ue(0); w.ue(cfg["ctb_log2"] - 3)                         # min CB 8
+    w.ue(0); w.ue(min(cfg["ctb_log2"], 5) - 2)                 # TB 4 .. min(CTB, 32)
+    w.ue(cfg["tu_depth"]); w.ue(cfg["tu_depth"])
+    w.u(1, cfg["scaling_lists"] != "off")
+    if cfg["scaling_lists"] != "off":
+        w.u(1, 0)                                              # sps_scaling_list_data_present_flag
+    w.u(1, 0)                                                  # amp
+    w.u(1, 1)                                                  # sample_adaptive_offset_enabled_flag
+    w.u(1, 0)                                                  # pcm
+    w.ue(0)                                                    # num_short_term_ref_pic_sets
+    w.u(1, 0); w.u(1, 0)                                       # long-term refs, temporal mvp
+    w.u(1, cfg["strong_smoothing"])
+    w.u(1, 0); w.u(1, 0)                                       # vui, extension
+    w.align_one()
+    return w.to_bytes()
+
+
+def write_scaling_list_data(w: BitWriter, lists, dc, modes):
+    """scaling_list_data() (7.3.4); modes[(s, m)] = 'explicit' | 'default' | ('ref', delta)."""
+    for s in range(4):
+        for m in range(2 if s == 3 else 6):
+            how = modes[(s, m)]
+            if how == "explicit":
+                w.u(1, 1)
+                nxt = 8
+                if s >= 2:
+                    w.se(dc[(s, m)] - 8)
+                    nxt = dc[(s, m)]
+                for v in lists[(s, m)]:
+                    w.se((v - nxt + 128) % 256 - 128)
+                    nxt = v
+            else:
+                w.u(1, 0)
+                w.ue(0 if how == "default" else how[1])
+
+
+def pps_rbsp(cfg, sl=None) -> bytes:
+    w = BitWriter()
+    w.ue(0); w.ue(0)
+    w.u(1, 0); w.u(1, 0); w.u(3, 0)                            # dependent slices, output flag, extra bits
+    w.u(1, cfg["sdh"]); w.u(1, 0)                              # sign data hiding, cabac_init_present
+    w.ue(0); w.ue(0)
+    w.se(0)                                                    # init_qp_minus26
+    w.u(1, 0)                                                  # constrained_intra_pred_flag
+    w.u(1, cfg["transform_skip"])
+    w.u(1, 0)                                                  # cu_qp_delta_enabled_flag
+    w.se(cfg["cb_qp_offset"]); w.se(cfg["cr_qp_offset"])
+    w.u(1, 0)                                                  # slice chroma qp offsets present
+    w.u(1, 0); w.u(1, 0)                                       # weighted pred / bipred
+    w.u(1, cfg["bypass"])                                      # transquant_bypass_enabled_flag
+    w.u(1, 0); w.u(1, 0)                                       # tiles, wavefront
+    w.u(1, 1)                                                  # pps_loop_filter_across_slices_enabled_flag
+    ctl = cfg["dbk_disable"] or cfg["beta_offset_div2"] or cfg["tc_offset_div2"]
+    w.u(1, 1 if ctl else 0)                                    # deblocking_filter_control_present_flag
+    if ctl:
+        w.u(1, 0)                                              # override enabled
+        w.u(1, cfg["dbk_disable"])
+        if not cfg["dbk_disable"]:
+            w.se(cfg["beta_offset_div2"]); w.se(cfg["tc_offset_div2"])
+    w.u(1, 1 if sl else 0)                                     # pps_scaling_list_data_present_flag
+    if sl:
+        write_scaling_list_data(w, *sl)
+    w.u(1, 0)                                                  # lists_modification_present_flag
+    w.ue(0)                                                    # log2_parallel_merge_level_minus2
+    w.u(1, 0); w.u(1, 0)                                       # slice header extension, pps extension
+    w.align_one()
+    return w.to_bytes()
+
+
+def slice_header_bits(cfg, first: bool, address: int, qp: int, across: int) -> BitWriter:
+    w = BitWriter()
+    w.u(1, 1 if first else 0)
+    w.u(1, 0)                                                  # no_output_of_prior_pics_flag (IDR)
+    w.ue(0)                                                    # slice_pic_parameter_set_id
+    if not first:
+        n_ctb = cfg["ctbs_w"] * cfg["ctbs_h"]
+        w.u(max(1, (n_ctb - 1).bit_length()), address)
+    w.ue(2)                                                    # slice_type I
+    w.u(1, 1); w.u(1, cfg["sao_chroma"])                       # slice_sao_luma_flag, slice_sao_chroma_flag
+    w.se(qp - 26)                                              # slice_qp_delta (init_qp_minus26 = 0)
+    w.u(1, across)                                             # slice_loop_filter_across_slices_enabled_flag
+    w.align_one()                                              # byte_alignment()
+    return w
+
+
+# ------------------------------------------------------------------------ CABAC encoder
+class CabacEncoder:
+    """9.3.4.x arithmetic *encoding* (the mirror of cabac.py:214-294), context state supplied
+    by the caller for every decision."""
+
+    def __init__(self, lps_range_table):
+        self.lps = lps_range_table
+        self.reset()
+
+    def reset(self):
+        self.low, self.range, self.first, self.outstanding, self.bits = 0, 510, True, 0, []
+
+    def _put(self, b):
+        if self.first:
+            self.first = False
+        else:
+            self.bits.append(b)
+        while self.outstanding:
+            self.bits.append(1 - b)
+            self.outstanding -= 1
+
+    def _renorm(self):
+        while self.range < 256:
+            if self.low < 256:
+                self._put(0)
+            elif self.low >= 512:
+                self.low -= 512
+                self._put(1)
+            else:
+                self.low -= 256
+                self.outstanding += 1
+            self.range <<= 1
+            self.low <<= 1
+
+    def decision(self, p_state_idx, val_mps, b):
+        r_lps = self.lps[p_state_idx][(self.range >> 6) & 3]
+        self.range -= r_lps
+        if b != val_mps:
+            self.low += self.range
+            self.range = r_lps
+        self._renorm()
+
+    def bypass(self, b):
+        self.low <<= 1
+        if b:
+            self.low += self.range
+        if self.low >= 1024:
+            self._put(1)
+            self.low -= 1024
+        elif self.low < 512:
+            self._put(0)
+        else:
+            self.low -= 512
+            self.outstanding += 1
+
+    def terminate(self, b):
+        self.range -= 2
+        if b:
+            self.low += self.range
+            self.range = 2                       # EncodeFlush
+            self._renorm()
+            self._put((self.low >> 9) & 1)
+            self.bits += [(self.low >> 8) & 1, 1]   # WriteBits(((low >> 7) & 3) | 1, 2): last bit = rbsp_stop_one_bit
+        else:
+            self._renorm()
+
+    def payload(self) -> bytes:
+        bits = list(self.bits)
+        while len(bits) % 8:
+            bits.append(0)
+        return bytes(int("".join(map(str, bits[i:i + 8])), 2) for i in range(0, len(bits), 8))
+
+
+# ------------------------------------------------------------------------ bin policy
+class Policy:
+    def __init__(self, seed, dense, big=False):
+        self.rng = np.random.default_rng(seed)
+        self.max_ones = 13 if big else 9
+        d = dense
+        self.p = {"split_cu_flag": 0.7, "part_mode": 0.5, "prev_intra_luma_pred_flag": 0.5,
+                  "intra_chroma_pred_mode": 0.5, "split_transform_flag": 0.5,
+                  "cbf_luma": 0.75 if d else 0.35, "cbf_chroma": 0.5 if d else 0.2,
+                  "transform_skip_flag": 0.3, "cu_transquant_bypass_flag": 0.15,
+                  "last_sig_coeff_x_prefix": 0.55 if d else 0.3, "last_sig_coeff_y_prefix": 0.55 if d else 0.3,
+                  "coded_sub_block_flag": 0.5 if d else 0.3, "sig_coeff_flag": 0.45 if d else 0.25,
+                  "coeff_abs_level_greater1_flag": 0.4 if d else 0.15,
+                  "coeff_abs_level_greater2_flag": 0.4 if d else 0.15,
+                  "sao_merge_leftup_flag": 0.3, "sao_type_idx_lumachroma_flag": 0.75}
+        self.p_bypass = 0.62 if big else (0.4 if d else 0.3)    # big: long remaining-level prefixes
+        self.ones = 0
+
+    def decision(self, name):
+        return int(self.rng.random() < self.p.get(name, 0.5))
+
+    def bypass(self):
+        b = int(self.rng.random() < self.p_bypass)
+        if self.ones >= self.max_ones:                     # bounds coeff_abs_level_remaining prefixes (|level| stays in int16)
+            b = 0
+        self.ones = self.ones + 1 if b else 0
+        return b
+
+
+# ------------------------------------------------------------------------ generation
+def run_parser(ns, path, hook=None):
+    """Run the reference's Decoder over `path`; returns (images, sps, pps)."""
+    import logging
+    wd = tempfile.mkdtemp(prefix="p265_fuzz_")
+    os.makedirs(os.path.join(wd, "logs"), exist_ok=True)
+    args = types.SimpleNamespace(bitstream=path, skip_syntax_dump=1000000, output=None, plot=None)
+    cwd = os.getcwd()
+    os.chdir(wd)
+    prev, logging.raiseExceptions = logging.raiseExceptions, False
+    try:
+        d = ns.dec.Decoder(args)
+        if hook:
+            hook(d)
+        try:
+            d.decode()
+        except SystemExit:
+            pass
+    finally:
+        logging.raiseExceptions = prev
+        os.chdir(cwd)
+    return d.ctx.dpb.images, d.ctx.sps, d.ctx.pps
+
+
+def make_stream(ns, cfg):
+    ctb = 1 << cfg["ctb_log2"]
+    cfg["ctbs_w"], cfg["ctbs_h"] = -(-cfg["width"] // ctb), -(-cfg["height"] // ctb)
+    n_ctb = cfg["ctbs_w"] * cfg["ctbs_h"]
+    sl = None
+    if cfg["scaling_lists"] == "pps":
+        sl = random_scaling_lists(cfg["seed"])
+    head = nal_unit(32, vps_rbsp(cfg)) + nal_unit(33, sps_rbsp(cfg)) + nal_unit(34, pps_rbsp(cfg, sl))
+    # slices of every picture: list of (first CTB address, qp, across flag)
+    rng = np.random.default_rng(cfg["seed"] + 1)
+    pictures = []
+    for _ in range(cfg["pictures"]):
+        starts = [0] + sorted(rng.choice(np.arange(1, n_ctb), size=min(cfg["slices"] - 1, n_ctb - 1),
+                                         replace=False).tolist()) if cfg["slices"] > 1 else [0]
+        # slice_loop_filter_across_slices_enabled_flag: 1, 0, 1, ... (the first slice has no left / upper slice)
+        pictures.append([(a, int(rng.choice(cfg["qps"])), 1 - (i & 1)) for i, a in enumerate(starts)])
+    headers = [[slice_header_bits(cfg, a == 0, a, qp, across).to_bytes() for a, qp, across in pic] for pic in pictures]
+    # pass 1: headers only; the hooked parser writes the slice data
+    skeleton = head + b"".join(nal_unit(19, h) for pic in headers for h in pic) + b"\x00" * 16
+    tmp = tempfile.NamedTemporaryFile(suffix=".bin", delete=False)
+    tmp.write(skeleton)
+    tmp.close()
+    policy = Policy(cfg["seed"], cfg["dense"], cfg["big"])
+    payloads = []
+    ends = [[(pic[i + 1][0] if i + 1 < len(pic) else n_ctb) - 1 for i in range(len(pic))] for pic in pictures]
+    state = {"pic": 0, "slice": 0}
+
+    def hook(d):
+        cab = d.ctx.cabac
+        enc = CabacEncoder(cab.tables.lps_range_table)
+        cab.initialization_process_arithmetic_decoding_engine = enc.reset
+
+        def decision(ctx_table, ctx_idx):
+            m = cab.context_models[ctx_table][ctx_idx]
+            b = policy.decision(ctx_table)
+            enc.decision(m.p_state_idx, m.val_mps, b)
+            cab.state_transition_process(ctx_table, ctx_idx, b)
+            return b
+
+        def bypass():
+            b = policy.bypass()
+            enc.bypass(b)
+            return b
+
+        def terminate():
+            last = ends[state["pic"]][state["slice"]]
+            b = int(d.ctx.img.ctu.addr_rs == last)
+            enc.terminate(b)
+            if b:
+                payloads.append(enc.payload())
+                state["slice"] += 1
+                if state["slice"] == len(ends[state["pic"]]):
+                    state["pic"], state["slice"] = state["pic"] + 1, 0
+            return b
+        cab.decode_decision, cab.decode_bypass, cab.decode_terminate = decision, bypass, terminate
+
+    prepare(ns, cfg)
+    imgs, sps, pps = run_parser(ns, tmp.name, hook)
+    os.unlink(tmp.name)
+    assert len(imgs) == cfg["pictures"] and len(payloads) == sum(len(p) for p in pictures)
+    k, body = 0, b""
+    for pic in headers:
+        for h in pic:
+            body += nal_unit(19, h + payloads[k])
+            k += 1
+    return head + body + b"\x00" * 8, (imgs, sps, pps)
+
+
+def random_scaling_lists(seed):
+    rng = np.random.default_rng(seed + 7)
+    lists, dc, modes = {}, {}, {}
+    for s in range(4):
+        for m in range(2 if s == 3 else 6):
+            r = rng.random()
+            if m > 0 and r < 0.2:
+                delta = int(rng.integers(1, m + 1))
+                modes[(s, m)] = ("ref", delta)
+                lists[(s, m)] = list(lists[(s, m - delta)])
+                if s >= 2:
+                    dc[(s, m)] = dc[(s, m - delta)]
+            elif r < 0.35:
+                from p265_b200 import scaling_list
+                modes[(s, m)] = "default"
+                lists[(s, m)] = scaling_list.default_list(s, m)
+                if s >= 2:
+                    dc[(s, m)] = 16
+            else:
+                modes[(s, m)] = "explicit"
+                base = rng.integers(8, 40)
+                lists[(s, m)] = [int(np.clip(base + i // 3 + rng.integers(-4, 5), 1, 255))
+                                 for i in range(16 if s == 0 else 64)]
+                if s >= 2:
+                    dc[(s, m)] = int(rng.integers(4, 64))
+    return lists, dc, modes
+
+
+def use_sld_dropin(ns):
+    """PPS-level scaling_list_data(): the reference's own sld.ScalingListData.decode cannot run
+    (SURVEY.md G4); swap in p265_b200's drop-in class for pps.py:11."""
+    from p265_b200.scaling_list import ScalingListData
+    sys.modules["sld"].ScalingListData = ScalingListData
+    sys.modules["pps"].sld.ScalingListData = ScalingListData
+
+
+def summarize(imgs, sps):
+    """Everything the hot path consumes, for the hooked-vs-clean comparison."""
+    from p265_b200 import packer
+    out = []
+    for img in imgs:
+        b = packer.pack_pictures([img], sps)
+        modes = []
+        for a in sorted(img.ctus):
+            for cu in packer._leaf_cus(img.ctus[a]):
+                modes.append((cu.x, cu.y, cu.log2size, cu.part_mode, cu.intra_pred_mode_c,
+                              tuple(sorted((x, y, int(v)) for x, col in cu.intra_pred_mode_y.items()
+                                           for y, v in col.items())), int(cu.cu_transquant_bypass_flag)))
+        out.append((b.tus.tobytes(), b.coeffs.tobytes(), packer.sao_params_from_picture(img, sps).tobytes(), modes))
+    return out
+
+
+STREAMS = [
+    # name, overrides of BASE
+    ("main8_dense", dict()),
+    ("main8_smooth_slices", dict(dense=False, slices=3, qps=(27, 34, 40), ctb_log2=5, seed=11,
+                                 beta_offset_div2=2, tc_offset_div2=-3)),
+    ("main10_lists_bypass", dict(bit_depth=10, profile=2, scaling_lists="default", bypass=1, dense=False, seed=12,
+                                 qps=(22, 30, 37), cb_qp_offset=3, cr_qp_offset=-4, width=136, height=72)),
+    # libavcodec's SAO lags deblocking by one CTB, which is not enough for chroma with 16x16 CTBs
+    # (observed: a chroma edge-offset neighbour read before its horizontal-edge deblocking): luma SAO only
+    ("main10_pps_lists_ctb16", dict(bit_depth=10, profile=2, scaling_lists="pps", ctb_log2=4, dense=True, seed=13,
+                                    qps=(17, 26, 45), width=64, height=48, tu_depth=1, sdh=0, sao_chroma=0)),
+    ("main8_dbk_off_bypass", dict(dbk_disable=1, bypass=1, dense=False, seed=14, qps=(30, 51), sao_chroma=0,
+                                  width=72, height=40, ctb_log2=5)),
+    ("main10_big_levels_ctb32", dict(bit_depth=10, profile=2, ctb_log2=5, dense=True, big=True, seed=15,
+                                     qps=(40, 46, 51), width=96, height=64, strong_smoothing=0)),
+    ("main8_big_levels_slices", dict(dense=True, big=True, slices=2, seed=16, qps=(8, 51), width=192, height=128,
+                                     tu_depth=3, cb_qp_offset=-5, cr_qp_offset=6, tc_offset_div2=4)),
+]
+BASE = dict(width=128, height=96, bit_depth=8, profile=1, ctb_log2=6, tu_depth=2, scaling_lists="off",
+            strong_smoothing=1, sdh=1, transform_skip=1, bypass=0, cb_qp_offset=0, cr_qp_offset=0,
+            dbk_disable=0, beta_offset_div2=0, tc_offset_div2=0, sao_chroma=1, pictures=2, slices=1,
+            qps=(24, 32), dense=True, big=False, seed=10)
+
+
+def prepare(ns, cfg):
+    """Harness patches a stream needs before the reference's parser can read it (also used by
+    the tests): see oracle/refshim.py for what each one works around."""
+    if cfg["scaling_lists"] == "pps":
+        use_sld_dropin(ns)
+    if cfg["slices"] > 1:
+        refshim.enable_multi_slice(ns)
+    if cfg["bypass"]:
+        refshim.enable_transquant_bypass(ns)
+
+
+def main():
+    import json
+    ns = refshim.load(tempfile.mkdtemp(prefix="p265ref_"))
+    os.makedirs(OUT_DIR, exist_ok=True)
+    answers, manifest = {}, {}
+    for name, over in STREAMS:
+        cfg = dict(BASE, **over)
+        stream, (imgs, sps, pps) = make_stream(ns, cfg)
+        path = os.path.join(OUT_DIR, name + ".bin")
+        with open(path, "wb") as fh:
+            fh.write(stream)
+        want = summarize(imgs, sps)
+        imgs2, sps2, _ = run_parser(ns, path)                  # the unhooked parser reads back the same syntax
+        got = summarize(imgs2, sps2)
+        assert got == want, "%s: clean parse differs from the generating run" % name
+        n_tb = sum(len(np.frombuffer(w[0], dtype=np.uint8)) // 16 for w in want)
+        for key, skip in (("rec", True), ("out", False)):
+            frames = ffmpeg_decode(stream, skip)
+            assert len(frames) == cfg["pictures"], (name, len(frames))
+            for p, planes in enumerate(frames):
+                for c, n in enumerate(("y", "cb", "cr")):
+                    answers["%s/%s%d_%s" % (name, key, p, n)] = planes[c]
+        manifest[name] = {k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()}
+        manifest[name]["tbs"] = n_tb
+        print("%-28s %6d bytes  %5d TBs  %dx%d %d-bit" % (name, len(stream), n_tb, cfg["width"], cfg["height"],
+                                                         cfg["bit_depth"]))
+    np.savez_compressed(os.path.join(HERE, "fuzz_ffmpeg.npz"), **answers)
+    with open(os.path.join(OUT_DIR, "manifest.json"), "w") as fh:
+        json.dump(manifest, fh, indent=1, sort_keys=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
