@@ -205,7 +205,7 @@ struct Geo {
 
 template <typename T, int CLS, bool NOFILT>
 __device__ __forceinline__ void edge_strip(const T *in, T *out, const Geo &g, const Strip &s, const MaskCtx &m,
-                                           const ItemConst &k, const uint8_t *nf_row, int nf_stride, int nf_shift) {
+                                           const ItemConst &k, const uint8_t *nf_row, int nf_stride, int nf_shift, bool nf_second) {
     // `in` / `out` point at (row y0, lane's first column)
     constexpr bool HALO = CLS != 1;
     auto rowptr = [&](int ly) {
@@ -240,7 +240,7 @@ __device__ __forceinline__ void edge_strip(const T *in, T *out, const Geo &g, co
                 if (f[0]) keep[0] = keep[1] = keep[2] = keep[3] = 0xffffffffu;
             } else {
                 if (f[0]) keep[0] = keep[1] = 0xffffffffu;
-                if (f[1]) keep[2] = keep[3] = 0xffffffffu;
+                if (nf_second && f[1]) keep[2] = keep[3] = 0xffffffffu;
             }
         }
         edge_row<CLS>(rw[j], rw[j + 1], rw[j + 2], k, keep, o);
@@ -300,6 +300,7 @@ __device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int r
 
     const uint8_t *nf_row = nullptr;
     int nf_stride = 0, nf_shift = 3;
+    bool nf_second = true;
     if (NOFILT) {
         nf_stride = (a.width + 7) >> 3;
         const int h8 = (a.height + 7) >> 3;
@@ -307,7 +308,10 @@ __device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int r
         // luma: lane strip = one 8x8 block column; chroma: two 4x4 block columns
         const int bx = c ? ((x0 + s.lx * 8) >> 2) : ((x0 + s.lx * 8) >> 3);
         const int by0 = g.y0 >> nf_shift;
-        nf_row = a.no_filter + ((int64_t)pic * h8 + by0) * nf_stride + min(bx, nf_stride - (c ? 2 : 1));
+        // a chroma strip at the right picture edge may own a single 8x8 luma block column (odd
+        // number of columns): its second flag does not exist
+        nf_row = a.no_filter + ((int64_t)pic * h8 + by0) * nf_stride + min(bx, nf_stride - 1);
+        if (c && bx + 1 >= nf_stride) nf_second = false;
     }
 
     ItemConst k;
@@ -336,7 +340,7 @@ __device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int r
             if (NOFILT) {
                 const uint8_t *f = nf_row + (int64_t)(lyr >> nf_shift) * nf_stride;
                 skip[0] = f[0] != 0;
-                skip[1] = nf_shift == 3 ? skip[0] : (f[1] != 0);
+                skip[1] = nf_shift == 3 ? skip[0] : (nf_second && f[1] != 0);
             }
 #pragma unroll
             for (int i = 0; i < 4; i++) o[i] = (type == 1 && !skip[i >> 1]) ? band_word(wv[j][i], k) : wv[j][i];
@@ -371,10 +375,10 @@ __device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int r
         }
     }
     switch (q.eo_class) {
-        case 0: edge_strip<T, 0, NOFILT>(in, out, g, s, m, k, nf_row, nf_stride, nf_shift); break;
-        case 1: edge_strip<T, 1, NOFILT>(in, out, g, s, m, k, nf_row, nf_stride, nf_shift); break;
-        case 2: edge_strip<T, 2, NOFILT>(in, out, g, s, m, k, nf_row, nf_stride, nf_shift); break;
-        default: edge_strip<T, 3, NOFILT>(in, out, g, s, m, k, nf_row, nf_stride, nf_shift); break;
+        case 0: edge_strip<T, 0, NOFILT>(in, out, g, s, m, k, nf_row, nf_stride, nf_shift, nf_second); break;
+        case 1: edge_strip<T, 1, NOFILT>(in, out, g, s, m, k, nf_row, nf_stride, nf_shift, nf_second); break;
+        case 2: edge_strip<T, 2, NOFILT>(in, out, g, s, m, k, nf_row, nf_stride, nf_shift, nf_second); break;
+        default: edge_strip<T, 3, NOFILT>(in, out, g, s, m, k, nf_row, nf_stride, nf_shift, nf_second); break;
     }
 }
 

@@ -58,13 +58,16 @@ def test_random_availability_masks(engine, c_oracle, bit_depth):
 
 
 @pytest.mark.parametrize("bit_depth", [8, 10])
-def test_no_filter_blocks(engine, c_oracle, bit_depth):
-    """pcm + pcm_loop_filter_disabled / cu_transquant_bypass blocks keep their samples."""
-    geom, rec, params = synth.sao_batch(256, 192, bit_depth, n_pics=2, ctb_log2=6, seed=5)
+@pytest.mark.parametrize("width,height,ctb_log2", [(256, 192, 6), (136, 72, 6), (72, 40, 5), (24, 24, 4)])
+def test_no_filter_blocks(engine, c_oracle, bit_depth, width, height, ctb_log2):
+    """pcm + pcm_loop_filter_disabled / cu_transquant_bypass blocks keep their samples.  Odd
+    numbers of 8x8 block columns matter: a chroma strip at the right edge then owns a single
+    flag (found by the libavcodec fuzz stream main10_lists_bypass)."""
+    geom, rec, params = synth.sao_batch(width, height, bit_depth, n_pics=2, ctb_log2=ctb_log2, seed=5)
     rng = np.random.default_rng(6)
-    nf = (rng.random((2, 192 // 8, 256 // 8)) < 0.3).astype(np.uint8)
-    got = engine.sao(rec, geom, 6, params, no_filter=nf)
-    assert_planes_equal(geom, got, c_oracle.sao_batch(rec, geom, 6, params, nf))
+    nf = (rng.random((2, height // 8, width // 8)) < 0.4).astype(np.uint8)
+    got = engine.sao(rec, geom, ctb_log2, params, no_filter=nf)
+    assert_planes_equal(geom, got, c_oracle.sao_batch(rec, geom, ctb_log2, params, nf))
 
 
 def test_extreme_offsets_clip(engine, c_oracle):
