@@ -222,6 +222,31 @@ def run_gpu(args):
     ms_res = timed(residual, args.steps) / args.steps
     ms_sao = timed(sao, args.steps) / args.steps
     clocks = sampler.stop()
+    # the neighbouring kernels of the path (reconstruction, deblocking), rank 0 only,
+    # outside the metric: same pictures, device resident, in place / out of place as they run
+    other = {}
+    if rank == 0 and not args.no_other:
+        from p265_b200 import synth
+        n_o = min(args.pics, 8)
+        dg, drec, dblk, dctb = synth.deblock_batch(PIC_W, PIC_H, 10, n_pics=n_o, n_unique=min(2, n_o))
+        t_pix, t_blk, t_ctb = to_dev(drec), to_dev(dblk), to_dev(dctb)
+        t_work = torch.empty_like(t_pix)
+        ts = []
+        for _ in range(max(5, args.steps // 2) + 2):
+            t_work.copy_(t_pix)                       # deblocking is in place: fresh input every time
+            torch.cuda.synchronize()
+            ts.append(timed(lambda: eng.deblock_dev(t_work.data_ptr(), dg, 6, t_blk.data_ptr(), t_ctb.data_ptr()), 1))
+        ms = float(np.median(ts[2:]))
+        b = 4 * n_o * (PIC_W * PIC_H * 3 // 2)
+        other["deblock_kernel"] = {"ms": round(ms, 4), "pics": n_o, "alg_bytes": b,
+                                   "frac_hbm": round(b / (ms * 1e-3) / 1e9 / measured_peaks()[0]["hbm_gbs"], 4)}
+        t_res = torch.zeros(dg.total_elems() * 2, dtype=torch.uint8, device=dev)
+        ms = timed(lambda: eng.reconstruct_dev(t_pix.data_ptr(), t_res.data_ptr(), t_work.data_ptr(), dg),
+                   args.steps) / args.steps
+        b = 6 * n_o * (PIC_W * PIC_H * 3 // 2)
+        other["recon_kernel"] = {"ms": round(ms, 4), "pics": n_o, "alg_bytes": b,
+                                 "frac_hbm": round(b / (ms * 1e-3) / 1e9 / measured_peaks()[0]["hbm_gbs"], 4)}
+        del t_pix, t_work, t_res
 
     ms_total_max = partition.max_over_ranks(ms_total, dev)
     pixels_step = PIC_W * PIC_H * args.pics * world
@@ -347,6 +372,7 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "gpu_launches_per_step": {"residual_kernel<bin 32/16/8/4>": 4, "sao_kernel": 1},
         "clocks": clocks,
+        "other_kernels": other,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1),
                      "peak": peaks["hbm_gbs"], "peak_source": peak_kind, "unit": "GB/s",
                      "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": traffic,
@@ -514,6 +540,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-other", action="store_true", help="skip the deblocking / reconstruction kernel timings")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

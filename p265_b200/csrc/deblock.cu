@@ -455,8 +455,7 @@ __global__ void __launch_bounds__(kDbkThreads, PACKED ? P265_DBK_CTAS : 1) deblo
             if (row_ok && has_l) storew<T>(base + (size_t)y * stride + x0, W[r][0], W[r][1]);
             if (row_ok && has_r) storew<T>(base + (size_t)y * stride + x0 + 4, W[r][2], W[r][3]);
         }
-        return;
-    }
+    } else {
     // ---- load the shifted block --------------------------------------------------------
     int v[8][8];
 #pragma unroll
@@ -531,6 +530,7 @@ __global__ void __launch_bounds__(kDbkThreads, PACKED ? P265_DBK_CTAS : 1) deblo
         const bool row_ok = y >= 0 && y < h;
         if (row_ok && has_l) store4<T>(base + (size_t)y * stride + x0, v[r], 0);
         if (row_ok && has_r) store4<T>(base + (size_t)y * stride + x0 + 4, v[r], 4);
+    }
     }
 }
 

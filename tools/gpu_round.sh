@@ -13,7 +13,7 @@ timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT
 BENCH_RC=$?
 echo "bench exit $BENCH_RC"; cat $OUT/bench_$TAG.json; tail -3 $OUT/bench_$TAG.err
 if [ "$BENCH_RC" = "0" ] && [ "$2" != "noncu" ]; then
-  NCU_CMD="python bench.py --steps 3 --warmup 3 --no-cpu --e2e-steps 3 --e2e-pics 1"
+  NCU_CMD="python bench.py --steps 3 --warmup 3 --no-cpu --no-other --e2e-steps 3 --e2e-pics 1"
   $NCU_CMD > $OUT/ncu_plain_$TAG.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches_$TAG.csv $NCU_CMD > $OUT/ncu_launches_$TAG.log 2>&1
   echo "ncu launches exit $?"
