@@ -22,6 +22,9 @@ namespace p265 {
 #ifndef P265_CTAS_PER_SM
 #define P265_CTAS_PER_SM 11
 #endif
+#ifndef P265_CTAS_BIN0
+#define P265_CTAS_BIN0 12  // 8.3 KB of shared memory per warp after the per-TB descriptor ring
+#endif
 constexpr int kWarpsPerCta = P265_WARPS_PER_CTA;
 constexpr int kCtasPerSm = P265_CTAS_PER_SM;
 constexpr int kDescRingBytes = 2 * 32 * 16;                          // 2 slots x 32 lanes x 16 B
@@ -63,8 +66,10 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
     const int n_items = a.first_item[bin + 1] - a.first_item[bin];
     if (gw >= n_items) return;
     unsigned char *in_base = wbase, *g_base = wbase + L::WARP_BYTES;
-    uint4 *ring = reinterpret_cast<uint4 *>(wbase + 2 * L::WARP_BYTES) + lane;  // slot s at ring[32 * s]
     const int tb_l = lane / L::TPB, tl = lane % L::TPB;
+    // descriptor ring: one entry per TB of the item (all lanes of a TB read the same one), 2 slots
+    constexpr int RS = L::TBS;  // slot s at ring[RS * s]
+    uint4 *ring = reinterpret_cast<uint4 *>(wbase + 2 * L::WARP_BYTES) + tb_l;
     const unsigned char *in = in_base + tb_l * L::TB_BYTES;
     unsigned char *g = g_base + tb_l * L::TB_BYTES;
     const int x0 = slot_index_rt(N, tl, 0), x1 = slot_index_rt(N, tl, 1);
@@ -77,7 +82,7 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
         if (gw + stride < n_items) {
             bool v1;
             const int tb1 = lane_tb<LOG2N>(a, gw + stride, lane, v1);
-            if (v1) copy16_async(&ring[32], &a.tus[tb1]);
+            if (v1 && tl == 0) copy16_async(&ring[RS], &a.tus[tb1]);
         }
         cp_async_commit();
     }
@@ -86,7 +91,7 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
         cp_async_wait<0>();  // tile k and descriptor k+1 have landed
         __syncwarp();        // ... for every lane; also: all lanes are done with g of item k-1
         lane_tb<LOG2N>(a, it, lane, valid);
-        const TbParams t = make_params(a, ring[32 * k], valid);
+        const TbParams t = make_params(a, ring[RS * k], valid);
         const bool is_special = (t.flags & (P265_TU_SKIP | P265_TU_BYPASS)) != 0;
         const bool slow = __any_sync(0xffffffffu, t.lsh != 0);
         if (__any_sync(0xffffffffu, t.valid && is_special)) phase_special<LOG2N>(lane, t, in_base);
@@ -94,7 +99,7 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
         // SF_REPLICATED: stage 1 reads the CTA's compact copy of this TB's matrix
         const uint8_t *sf1 = t.sf;
         if (SF == SF_REPLICATED && t.sf)
-            sf1 = sfc + sf_matrix_id(LOG2N, (int)((ring[32 * k].y >> 8) & 0xff), t.flags) * kSfcStride;
+            sf1 = sfc + sf_matrix_id(LOG2N, (int)((ring[RS * k].y >> 8) & 0xff), t.flags) * kSfcStride;
         if (!slow) {
             stage1_call<LOG2N, SF, false>(in, g, x0, tl, 0, sf1, t.w, t.rnd, t.sh, 0, dstf);
             stage1_call<LOG2N, SF, false>(in, g, x1, tl, 1, sf1, t.w, t.rnd, t.sh, 0, dstf);
@@ -106,12 +111,12 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
         if (it + stride < n_items) {
             bool v1;
             lane_tb<LOG2N>(a, it + stride, lane, v1);
-            const uint4 dn = ring[32 * (k ^ 1)];
+            const uint4 dn = ring[RS * (k ^ 1)];
             tile_issue<LOG2N>(lane, a.coeffs + (size_t)dn.z * 16, v1, in_base);
             if (it + 2 * stride < n_items) {  // slot k is free: its descriptor sits in `t`
                 bool v2;
                 const int tb2 = lane_tb<LOG2N>(a, it + 2 * stride, lane, v2);
-                if (v2) copy16_async(&ring[32 * k], &a.tus[tb2]);
+                if (v2 && tl == 0) copy16_async(&ring[RS * k], &a.tus[tb2]);
             }
         }
         cp_async_commit();
@@ -262,10 +267,13 @@ __device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride
 constexpr int kSfcBytes = 512;  // compact ScalingFactor copy at the start of a CTA's shared memory (6 x 80 B)
 template <int BIN>
 struct BinCfg {
-    static constexpr int ctas = BIN == 1 ? P265_CTAS_BIN1 : (BIN == 3 ? P265_CTAS_BIN3 : kCtasPerSm);
+    static constexpr int ctas = BIN == 0 ? P265_CTAS_BIN0 : (BIN == 1 ? P265_CTAS_BIN1 : (BIN == 3 ? P265_CTAS_BIN3 : kCtasPerSm));
+    // per warp: tile + g buffers + descriptor ring (2 slots x TBs per item x 16 B for the big sizes)
     static constexpr int smem =
         BIN == 3 ? kSfcBytes + kWarpsPerCta * kBin4WarpBytes
-                 : kSfcBytes + (BIN == 1 ? kWarpsPerCta * (2 * Layout<4>::WARP_BYTES + kDescRingBytes) : kCtaSmemBytes);
+        : BIN == 0 ? kSfcBytes + kWarpsPerCta * (2 * Layout<5>::WARP_BYTES + 2 * Layout<5>::TBS * 16)
+        : BIN == 1 ? kSfcBytes + kWarpsPerCta * (2 * Layout<4>::WARP_BYTES + 2 * Layout<4>::TBS * 16)
+                   : kSfcBytes + kCtaSmemBytes;
 };
 
 template <int BIN, int SF>

@@ -203,3 +203,15 @@ def test_many_items_per_warp(engine, c_oracle):
     (exercises the double-buffered tile prefetch)."""
     batch = synth.residual_batch("1080p8", n_pics=6, n_unique=2)
     assert_planes_equal(batch.geom, engine.residual(batch), c_oracle.residual_batch(batch, zero_fill=False))
+
+
+@pytest.mark.parametrize("log2n", [5, 4, 3, 2])
+def test_each_size_bin_alone_at_scale(engine, c_oracle, log2n):
+    """Four 4K pictures' worth of one TB size: every persistent warp loops over many items, every
+    CTA slot of the SM is occupied (catches shared-memory layout overruns that small grids hide)."""
+    from p265_b200.picture import ResidualBatch
+    full = synth.residual_batch("4k10", n_pics=4, n_unique=2, seed=77)
+    sel = np.ascontiguousarray(full.tus[full.tus["log2n"] == log2n])
+    assert len(sel) > 15000
+    b = ResidualBatch(full.geom, sel, full.coeffs, full.scaling_factor, covers_all=False)
+    assert np.array_equal(engine.residual(b), c_oracle.residual_batch(b))
