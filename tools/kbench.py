@@ -128,6 +128,8 @@ def bench_sao_recon(args, eng, dev, stream, to_dev, want):
     d_rec, d_par = to_dev(rec), to_dev(params)
     d_o = torch.empty_like(d_rec)
     for label, mod in (("SAO config 4 mix", None), ("SAO all off (copy)", 0), ("SAO all band", 1), ("SAO all edge", 2)):
+        if not want("sao"):
+            break
         p = params.copy()
         if mod is not None:
             p["type"][:] = mod
