@@ -255,12 +255,17 @@ def ref_literal_transform_xy(d_xy, log2size, c_idx):
 
 
 # ---------------------------------------------------------------------------- SAO
-def sao_offset_val(type_idx, offset_abs, offset_sign, bit_depth):
+def sao_offset_val(type_idx, offset_abs, offset_sign, bit_depth, log2_offset_scale=0):
     """7.4.9.3.2 SaoOffsetVal[1..4] for one CTB component (sao.py:43-77 fields).
 
     Edge offset: signs are fixed (+,+,-,-) whatever `offset_sign` holds (the reference
-    leaves it 0 for non-merged edge CTBs, sao.py:111-116)."""
-    shift = bit_depth - min(bit_depth, 10)
+    leaves it 0 for non-merged edge CTBs, sao.py:111-116).  Scale: the 04/2013 edition
+    shifts by bitDepth - Min(bitDepth, 10), which is 0 for every bit depth its profiles
+    allow; from the 10/2014 edition on (the one that defines profiles above 10 bits) the
+    shift is log2_sao_offset_scale_{luma,chroma} of the PPS range extension, 0 when absent.
+    This follows the later text -- identical up to 10 bits, and what libavcodec decodes at
+    12 bits (tests/golden/fuzz/rext12_lists_ctb32.bin)."""
+    shift = int(log2_offset_scale)
     vals = []
     for i in range(4):
         if type_idx == 2:

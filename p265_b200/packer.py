@@ -94,11 +94,13 @@ def pack_pictures(imgs, sps, scaling_factor=None) -> ResidualBatch:
 
 
 # ------------------------------------------------------------------------- SAO
-def sao_offset_val(type_idx: int, offset_abs, offset_sign, bit_depth: int):
+def sao_offset_val(type_idx: int, offset_abs, offset_sign, bit_depth: int, log2_offset_scale: int = 0):
     """SaoOffsetVal[1..4] (7.4.9.3.2) from the fields `sao.Sao.parse` fills
     (sao.py:43-77).  Edge offsets have fixed signs (+,+,-,-); the reference only writes
-    them into `sao_offset_sign` on the merge path (sao.py:111-116)."""
-    shift = bit_depth - min(bit_depth, 10)
+    them into `sao_offset_sign` on the merge path (sao.py:111-116).  The scale is
+    log2_sao_offset_scale_{luma,chroma} (PPS range extension, 0 when absent): for bit depths up
+    to 10 that equals the 04/2013 edition's bitDepth - Min(bitDepth, 10)."""
+    shift = int(log2_offset_scale)
     out = []
     for i in range(4):
         if type_idx == 2:
@@ -110,9 +112,11 @@ def sao_offset_val(type_idx: int, offset_abs, offset_sign, bit_depth: int):
     return out
 
 
-def sao_params_from_picture(img, sps, avail=None) -> np.ndarray:
+def sao_params_from_picture(img, sps, avail=None, pps=None) -> np.ndarray:
     """(ctbs_h, ctbs_w) SAO_CTB table from `img.ctus[addr].sao` (ctu.py:22)."""
     wc, hc = int(sps.pic_width_in_ctbs_y), int(sps.pic_height_in_ctbs_y)
+    scale = (int(getattr(pps, "log2_sao_offset_scale_luma", 0)),) + \
+        (int(getattr(pps, "log2_sao_offset_scale_chroma", 0)),) * 2
     tab = np.zeros((hc, wc), dtype=SAO_CTB)
     tab["avail"] = AVAIL_ALL
     for addr, ctu in img.ctus.items():
@@ -126,8 +130,8 @@ def sao_params_from_picture(img, sps, avail=None) -> np.ndarray:
             e["band_pos"][c] = int(s.sao_band_position[c])
             e["eo_class"][c] = int(s.sao_eo_class[c])
             bd = int(sps.bit_depth_y if c == 0 else sps.bit_depth_c)
-            e["offset_val"][c] = sao_offset_val(t, s.sao_offset_abs[c],
-                                                s.sao_offset_sign[c], bd) if t else 0
+            e["offset_val"][c] = sao_offset_val(t, s.sao_offset_abs[c], s.sao_offset_sign[c], bd,
+                                                scale[c]) if t else 0
     if avail is not None:
         tab["avail"] = avail
     return tab

@@ -197,7 +197,7 @@ def filter_picture(planes, img, sps, pps=None, device: int = 0):
     buf = np.zeros(geom.total_elems(), dtype=dtype)
     for c, p in enumerate((y, cb, cr)):
         geom.plane_view(buf, 0, c)[:] = p
-    params = packer.sao_params_from_picture(img, sps, availability_from_picture(img, sps, pps))
+    params = packer.sao_params_from_picture(img, sps, availability_from_picture(img, sps, pps), pps)
     out = get_engine(device).sao(buf, geom, int(sps.ctb_log2_size_y), params,
                                  no_filter=no_filter_from_picture(img, sps))
     return tuple(geom.plane_view(out, 0, c).copy() for c in range(3))

@@ -116,7 +116,7 @@ def decode_picture(img, sps, pps, backend):
     nf = sao_api.no_filter_from_picture(img, sps)
 
     def sao(avail, no_filter):
-        params = packer.sao_params_from_picture(img, sps, avail)
+        params = packer.sao_params_from_picture(img, sps, avail, pps)
         o = backend.sao(dbk, geom, ctb_log2, params, no_filter)
         return [geom.plane_view(o, 0, c).copy() for c in range(3)]
 

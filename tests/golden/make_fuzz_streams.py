@@ -467,6 +467,11 @@ STREAMS = [
                                   width=72, height=40, ctb_log2=5)),
     ("main10_big_levels_ctb32", dict(bit_depth=10, profile=2, ctb_log2=5, dense=True, big=True, seed=15,
                                      qps=(40, 46, 51), width=96, height=64, strong_smoothing=0)),
+    # 12 bit: libavcodec's qP % 6 / qP / 6 tables stop at qP 73, so QpY 50 / 51 (qP 74 / 75) dequantise as
+    # qP 0 / 1 there (observed); the stream stays at QpY <= 49
+    ("rext12_lists_ctb32", dict(bit_depth=12, profile=4, scaling_lists="default", ctb_log2=5, dense=True, seed=17,
+                                qps=(20, 33, 49), width=96, height=64, cb_qp_offset=2, cr_qp_offset=-2,
+                                beta_offset_div2=-2, tc_offset_div2=3)),
     ("main8_big_levels_slices", dict(dense=True, big=True, slices=2, seed=16, qps=(8, 51), width=192, height=128,
                                      tu_depth=3, cb_qp_offset=-5, cr_qp_offset=6, tc_offset_div2=4)),
 ]

@@ -272,7 +272,8 @@ def test_sao_known_answers():
 def test_sao_offset_val_derivation():
     assert so.sao_offset_val(2, [1, 2, 3, 4], [0, 0, 0, 0], 8) == [1, 2, -3, -4]
     assert so.sao_offset_val(1, [1, 2, 3, 4], [1, 0, 1, 0], 10) == [-1, 2, -3, 4]
-    assert so.sao_offset_val(1, [1, 2, 3, 4], [0, 0, 0, 0], 12) == [4, 8, 12, 16]
+    assert so.sao_offset_val(1, [1, 2, 3, 4], [0, 0, 0, 0], 12) == [1, 2, 3, 4]          # 10/2014 edition on
+    assert so.sao_offset_val(1, [1, 2, 3, 4], [0, 0, 0, 0], 12, 2) == [4, 8, 12, 16]   # log2_sao_offset_scale
     from p265_b200 import packer
     for args in ((2, [1, 2, 3, 4], [1, 1, 0, 0], 8), (1, [7, 0, 3, 4], [1, 0, 1, 0], 10),
                  (1, [31, 2, 3, 4], [0, 1, 0, 0], 12)):
