@@ -370,7 +370,7 @@ def run_gpu(args):
                        "(p265_ctx_set_async), pinned host buffers, every H2D / D2H copy inside the timed "
                        "region, all contexts synchronised before the step ends"},
         "gpu_launches": int(launches),
-        "gpu_launches_per_step": {"residual_kernel<bin 32/16/8/4>": 4, "sao_kernel": 1},
+        "gpu_launches_per_step": {"expand_kernel": 1, "residual_kernel<bin 32/16/8/4>": 4, "sao_kernel": 1},
         "clocks": clocks,
         "other_kernels": other,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1),

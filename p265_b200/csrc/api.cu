@@ -154,6 +154,7 @@ int p265_ctx_destroy(p265_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 8; i++)
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    if (ctx->xtus) cudaFree(ctx->xtus);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return P265_OK;

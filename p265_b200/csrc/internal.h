@@ -18,6 +18,8 @@ struct p265_ctx {
     // grow-only device scratch for the host-buffer entry points
     void *scratch[8] = {nullptr};
     size_t scratch_bytes[8] = {0};
+    void *xtus = nullptr;  // expanded TU descriptors of the current residual launch (grow-only)
+    size_t xtus_bytes = 0;
 };
 
 namespace p265 {

@@ -76,13 +76,13 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
     bool valid;
     {   // prologue: first descriptor by plain load, its tile and the second descriptor async
         const int tb = lane_tb<LOG2N>(a, gw, lane, valid);
-        const uint4 d0 = load_desc(a, tb, valid);
+        const uint4 d0 = load_xdesc(a, tb, valid);
         ring[0] = d0;
         tile_issue<LOG2N>(lane, a.coeffs + (size_t)d0.z * 16, valid, in_base);
         if (gw + stride < n_items) {
             bool v1;
             const int tb1 = lane_tb<LOG2N>(a, gw + stride, lane, v1);
-            if (v1 && tl == 0) copy16_async(&ring[RS], &a.tus[tb1]);
+            if (v1 && tl == 0) copy16_async(&ring[RS], &a.xtus[tb1]);
         }
         cp_async_commit();
     }
@@ -91,7 +91,7 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
         cp_async_wait<0>();  // tile k and descriptor k+1 have landed
         __syncwarp();        // ... for every lane; also: all lanes are done with g of item k-1
         lane_tb<LOG2N>(a, it, lane, valid);
-        const TbParams t = make_params(a, ring[RS * k], valid);
+        const TbParams t = params_from_x(a, ring[RS * k], valid);
         const bool is_special = (t.flags & (P265_TU_SKIP | P265_TU_BYPASS)) != 0;
         const bool slow = __any_sync(0xffffffffu, t.lsh != 0);
         if (__any_sync(0xffffffffu, t.valid && is_special)) phase_special<LOG2N>(lane, t, in_base);
@@ -99,7 +99,7 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
         // SF_REPLICATED: stage 1 reads the CTA's compact copy of this TB's matrix
         const uint8_t *sf1 = t.sf;
         if (SF == SF_REPLICATED && t.sf)
-            sf1 = sfc + sf_matrix_id(LOG2N, (int)((ring[RS * k].y >> 8) & 0xff), t.flags) * kSfcStride;
+            sf1 = sfc + (int)((ring[RS * k].y >> 16) & 0xff) * kSfcStride;  // matrixId from the expanded record
         if (!slow) {
             stage1_call<LOG2N, SF, false>(in, g, x0, tl, 0, sf1, t.w, t.rnd, t.sh, 0, dstf);
             stage1_call<LOG2N, SF, false>(in, g, x1, tl, 1, sf1, t.w, t.rnd, t.sh, 0, dstf);
@@ -116,7 +116,7 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
             if (it + 2 * stride < n_items) {  // slot k is free: its descriptor sits in `t`
                 bool v2;
                 const int tb2 = lane_tb<LOG2N>(a, it + 2 * stride, lane, v2);
-                if (v2 && tl == 0) copy16_async(&ring[RS * k], &a.tus[tb2]);
+                if (v2 && tl == 0) copy16_async(&ring[RS * k], &a.xtus[tb2]);
             }
         }
         cp_async_commit();
@@ -130,10 +130,27 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
 }
 
 // ---- small TBs: one lane = one TB (residual_core.cuh: tb8_lane / tb4_lane) -----------
+// Whether the 8x8 / 4x4 bins read expanded descriptors too.  No instruction is saved there (one
+// lane per TB), but with a ScalingFactor table the per-TB table pointer is cheaper from the
+// expanded record and expand_kernel's pass leaves the descriptors in L2: measured on the 4K
+// 10-bit mix, +3 % with a table, -3 % without -> chosen by the SF mode.
+template <int SF>
+struct SmallDesc {
+    static constexpr bool X = SF != SF_NONE;
+    static __device__ __forceinline__ uint4 load(const KernelArgs &a, int i, bool v) {
+        return X ? load_xdesc(a, i, v) : load_desc(a, i, v);
+    }
+    static __device__ __forceinline__ const uint4 *ptr(const KernelArgs &a, int i) {
+        return X ? &a.xtus[i] : reinterpret_cast<const uint4 *>(&a.tus[i]);
+    }
+    static __device__ __forceinline__ TbParams params(const KernelArgs &a, const uint4 d, bool v) {
+        return X ? params_from_x(a, d, v) : make_params(a, d, v);
+    }
+};
 template <int SF, bool SLOW>
 __device__ __noinline__ void tb8_call(const KernelArgs &a, const uint4 d, bool valid, const unsigned char *tile,
                                       int lane) {
-    const TbParams t = make_params(a, d, valid);
+    const TbParams t = SmallDesc<SF>::params(a, d, valid);
     tb8_lane<SF, SLOW>(t, tile, lane);
 }
 
@@ -154,11 +171,11 @@ __device__ __forceinline__ void run_bin8(const KernelArgs &a, int gw, int stride
     };
     bool valid = gw * 32 + lane < n_tb;
     {
-        const uint4 d0 = load_desc(a, first + gw * 32 + lane, valid);
+        const uint4 d0 = SmallDesc<SF>::load(a, first + gw * 32 + lane, valid);
         ring[0] = d0;
         issue(d0, valid, wbase);
         const int i1 = (gw + stride) * 32 + lane;
-        if (gw + stride < n_items && i1 < n_tb) copy16_async(&ring[32], &a.tus[first + i1]);
+        if (gw + stride < n_items && i1 < n_tb) copy16_async(&ring[32], SmallDesc<SF>::ptr(a, first + i1));
         cp_async_commit();
     }
     int k = 0;
@@ -170,14 +187,19 @@ __device__ __forceinline__ void run_bin8(const KernelArgs &a, int gw, int stride
             const int i1 = (it + stride) * 32 + lane;
             issue(ring[32 * (k ^ 1)], i1 < n_tb, wbase + (k ^ 1) * kWarpSmemBytes);
             const int i2 = (it + 2 * stride) * 32 + lane;
-            if (it + 2 * stride < n_items && i2 < n_tb) copy16_async(&ring[32 * k], &a.tus[first + i2]);
+            if (it + 2 * stride < n_items && i2 < n_tb) copy16_async(&ring[32 * k], SmallDesc<SF>::ptr(a, first + i2));
         }
         cp_async_commit();
         // per >= bdShift needs qP >= 6 * (bitDepth - 2): impossible for 8x8 below 14 bits,
         // but the descriptor is caller data: decide warp-uniformly like the other sizes
-        const int qp = (int)((d_cur.y >> 16) & 0xff), c_idx = (int)((d_cur.y >> 8) & 0xff);
-        const int bd = c_idx ? a.bit_depth_c : a.bit_depth_y;
-        const bool slow = __any_sync(0xffffffffu, valid && ((qp * 43) >> 8) >= bd - 2);
+        bool slow_lane;
+        if (SmallDesc<SF>::X) {
+            slow_lane = (d_cur.w >> 24) != 0;
+        } else {
+            const int qp = (int)((d_cur.y >> 16) & 0xff), c_idx = (int)((d_cur.y >> 8) & 0xff);
+            slow_lane = ((qp * 43) >> 8) >= (c_idx ? a.bit_depth_c : a.bit_depth_y) - 2;
+        }
+        const bool slow = __any_sync(0xffffffffu, valid && slow_lane);
         if (slow) tb8_call<SF, true>(a, d_cur, valid, wbase + k * kWarpSmemBytes, lane);
         else tb8_call<SF, false>(a, d_cur, valid, wbase + k * kWarpSmemBytes, lane);
     }
@@ -206,7 +228,7 @@ __device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride
     uint4 *ring = reinterpret_cast<uint4 *>(wbase + kBin4Stages * 1024) + lane;      // slot s at ring[32 * s]
     auto desc_async = [&](int item, int slot) {
         const int i = item * 32 + lane;
-        if (item < n_items && i < n_tb) copy16_async(&ring[32 * slot], &a.tus[first + i]);
+        if (item < n_items && i < n_tb) copy16_async(&ring[32 * slot], SmallDesc<SF>::ptr(a, first + i));
     };
     auto tile_async = [&](int item, const uint4 d, int stage) {
         const int i = item * 32 + lane;
@@ -222,7 +244,7 @@ __device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride
     {   // prologue: descriptors 0..2 by plain loads (paid once per warp and bin)
         for (int j = 0; j < 3; j++) {
             const int i = (gw + j * stride) * 32 + lane;
-            ring[32 * j] = load_desc(a, first + i, gw + j * stride < n_items && i < n_tb);
+            ring[32 * j] = SmallDesc<SF>::load(a, first + i, gw + j * stride < n_items && i < n_tb);
         }
         tile_async(gw, ring[0], 0);
         cp_async_commit();
@@ -240,7 +262,7 @@ __device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride
         tile_async(it + 2 * stride, ring[32 * ((k + 2) & 3)], (k + 2) % kBin4Stages);
         desc_async(it + 4 * stride, k & 3);
         cp_async_commit();
-        const TbParams t = make_params(a, d_cur, valid);
+        const TbParams t = SmallDesc<SF>::params(a, d_cur, valid);
         uint32_t w[8];
         {
             const uint4 v0 = *reinterpret_cast<const uint4 *>(tiles + st * 1024 + tb4_slot_off(lane, 0));
@@ -282,6 +304,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, BinCfg<BIN>::ctas) residual
     // The four bin kernels are independent (disjoint TBs): let the next one be scheduled
     // as soon as CTAs of this one retire (programmatic dependent launch) so the tail of a
     // bin overlaps the head of the next instead of idling SMs.
+    // The first bin kernel of a batch is launched on top of expand_kernel and must see its
+    // output: it waits for that grid before letting its own successor in, so every later bin
+    // is ordered behind expand_kernel as well.
+    if (a.wait_prev) asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stride = gridDim.x * kWarpsPerCta;
@@ -297,6 +323,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, BinCfg<BIN>::ctas) residual
     else if (BIN == 1) run_bin<4, SF>(a, gw, stride, lane, wbase, smem);
     else if (BIN == 2) run_bin8<SF>(a, gw, stride, lane, wbase);
     else run_bin4<SF>(a, gw, stride, lane, wbase);
+}
+
+// One thread per TB: public descriptor -> expanded record (residual_core.cuh: expand_desc).
+__global__ void __launch_bounds__(256) expand_kernel(const __grid_constant__ KernelArgs a, int n_tus, uint4 *out) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the first bin kernel may be scheduled early
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_tus) out[i] = expand_desc(a, load_desc(a, i, true));
 }
 
 // ---- auxiliary, non-hot kernels ------------------------------------------------------
@@ -380,6 +413,8 @@ int launch_idct1d(p265_ctx *ctx, const int32_t *d_x, int log2size, int tr_type, 
 static int fill_args(KernelArgs &a, const p265_tu_desc *d_tus, const int32_t bin_counts[4], const int16_t *d_coeffs,
                      const uint8_t *d_sf, const p265_pic_geom *g, int16_t *d_out) {
     a.tus = d_tus;
+    a.xtus = nullptr;
+    a.wait_prev = 0;
     a.coeffs = d_coeffs;
     a.sf = d_sf;
     a.sf_replicated = 0;
@@ -405,7 +440,11 @@ static int fill_args(KernelArgs &a, const p265_tu_desc *d_tus, const int32_t bin
 }
 
 template <int BIN, int SF>
-static int launch_bin(p265_ctx *ctx, const KernelArgs &a, bool overlap_previous) {
+static int launch_bin(p265_ctx *ctx, KernelArgs a, bool first) {
+    // behind expand_kernel (first big-size bin: wait for it) or overlapping the previous bin
+    const bool expanded = a.n_tb[0] + a.n_tb[1] + (a.sf ? a.n_tb[2] + a.n_tb[3] : 0) > 0;
+    const bool overlap_previous = !first || expanded;
+    a.wait_prev = (first && expanded) ? 1 : 0;
     const int items = a.first_item[BIN + 1] - a.first_item[BIN];
     if (items == 0) return P265_OK;
     constexpr int smem = BinCfg<BIN>::smem;
@@ -447,10 +486,10 @@ static int launch_residual_sf(p265_ctx *ctx, const KernelArgs &a) {
     // stream (zero fill, copies); the following bins may overlap their predecessor
     int rc;
     bool first = true;
-    if (a.n_tb[0]) { if ((rc = launch_bin<0, SF>(ctx, a, !first))) return rc; first = false; }
-    if (a.n_tb[1]) { if ((rc = launch_bin<1, SF>(ctx, a, !first))) return rc; first = false; }
-    if (a.n_tb[2]) { if ((rc = launch_bin<2, SF>(ctx, a, !first))) return rc; first = false; }
-    if (a.n_tb[3]) { if ((rc = launch_bin<3, SF>(ctx, a, !first))) return rc; first = false; }
+    if (a.n_tb[0]) { if ((rc = launch_bin<0, SF>(ctx, a, first))) return rc; first = false; }
+    if (a.n_tb[1]) { if ((rc = launch_bin<1, SF>(ctx, a, first))) return rc; first = false; }
+    if (a.n_tb[2]) { if ((rc = launch_bin<2, SF>(ctx, a, first))) return rc; first = false; }
+    if (a.n_tb[3]) { if ((rc = launch_bin<3, SF>(ctx, a, first))) return rc; first = false; }
     return P265_OK;
 }
 
@@ -465,6 +504,24 @@ int launch_residual(p265_ctx *ctx, const p265_tu_desc *d_tus, const int32_t bin_
     if (flags & P265_RES_ZERO_FILL)
         P265_CUDA(cudaMemsetAsync(d_out, 0, sizeof(int16_t) * (size_t)g->pic_stride * g->n_pics, ctx->stream));
     if (a.first_item[4] == 0) return P265_OK;
+    // Expanded descriptors for the 32x32 / 16x16 bins (16 or 8 lanes share a TB there and would
+    // all re-derive its parameters) and, with a ScalingFactor table, for the small bins as well
+    // (SmallDesc), in a grow-only device buffer of the context.  The list is sorted by size.
+    const int n_tus = a.n_tb[0] + a.n_tb[1] + (a.sf ? a.n_tb[2] + a.n_tb[3] : 0);
+    const size_t need = sizeof(uint4) * (size_t)n_tus;
+    if (ctx->xtus_bytes < need) {
+        if (ctx->xtus) P265_CUDA(cudaFree(ctx->xtus));
+        ctx->xtus = nullptr;
+        ctx->xtus_bytes = 0;
+        P265_CUDA(cudaMalloc(&ctx->xtus, need + need / 4));
+        ctx->xtus_bytes = need + need / 4;
+    }
+    a.xtus = static_cast<const uint4 *>(ctx->xtus);
+    if (n_tus) {
+        expand_kernel<<<(n_tus + 255) / 256, 256, 0, ctx->stream>>>(a, n_tus, static_cast<uint4 *>(ctx->xtus));
+        P265_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
     if (!a.sf) return launch_residual_sf<SF_NONE>(ctx, a);
     if (a.sf_replicated) return launch_residual_sf<SF_REPLICATED>(ctx, a);
     return launch_residual_sf<SF_GENERAL>(ctx, a);

@@ -294,6 +294,7 @@ struct TbParams {
 
 struct KernelArgs {
     const p265_tu_desc *tus;
+    const uint4 *xtus;  // expanded descriptors (expand_desc), one per TB, same order as `tus`
     const int16_t *coeffs;
     const uint8_t *sf;  // P265_SF_BYTES or nullptr
     int32_t sf_replicated;  // 16x16 / 32x32 matrices obey the 7.4.5 up-sampling (+ DC at [0][0])
@@ -305,6 +306,7 @@ struct KernelArgs {
     int32_t first_tb[4];  // index of the first descriptor of each size bin (32,16,8,4)
     int32_t n_tb[4];
     int32_t first_item[5];  // warp-item prefix sums per bin
+    int32_t wait_prev;      // this launch directly follows expand_kernel: wait for it (griddepcontrol.wait)
 };
 
 P265_HD int sf_matrix_offset(int log2n, int c_idx, int intra) {
@@ -383,6 +385,62 @@ P265_HD TbParams make_params(const KernelArgs &a, const uint4 d, bool valid) {
     t.sh2 = 20 - bit_depth;
     t.rnd2 = 1 << (t.sh2 - 1);
     return t;
+}
+
+P265_HD int sf_matrix_id(int log2n, int c_idx, int flags) {
+    const int not_intra = (flags & P265_TU_INTRA) ? 0 : 1;
+    return log2n == 5 ? not_intra : c_idx + 3 * not_intra;
+}
+
+// ------------------------------------------------------------------ expanded descriptors
+// Everything make_params derives from a public 16-byte descriptor is TB-uniform, but inside
+// the bin kernels every lane of every item would recompute it (~100 instructions per item).
+// expand_kernel does it once per TB, into a 16-byte record with the same positions for the
+// fields the pipeline code reads directly:
+//   .x  element offset of the TB's top-left in the residual buffer
+//   .y  log2n | c_idx << 8 | matrixId << 16 | flags << 24       (qP byte -> matrixId)
+//   .z  coefficient arena offset, units of 16 coefficients       (unchanged)
+//   .w  w (16 bits: 16 * levelScale, levelScale with a table, 1 when prescaled) | sh << 16 | lsh << 24
+P265_HD uint4 expand_desc(const KernelArgs &a, const uint4 d) {
+    const TbParams t = make_params(a, d, true);
+    const int log2n = (int)(d.y & 0xff), c_idx = (int)((d.y >> 8) & 0xff);
+    const uint32_t dst_off = (uint32_t)(t.dst - a.out);
+    // PRESCALED (identity dequantisation) is folded into w = 1, sh = lsh = 0 and "no table"
+    const int mid = sf_matrix_id(log2n, c_idx, t.flags);
+    const uint32_t flags = (uint32_t)t.flags;
+    return make_uint4(dst_off, (uint32_t)log2n | ((uint32_t)c_idx << 8) | ((uint32_t)mid << 16) | (flags << 24), d.z,
+                      (uint32_t)t.w | ((uint32_t)t.sh << 16) | ((uint32_t)t.lsh << 24));
+}
+
+P265_HD TbParams params_from_x(const KernelArgs &a, const uint4 x, bool valid) {
+    TbParams t;
+    t.valid = valid;
+    if (!valid) {
+        t.src = nullptr; t.dst = nullptr; t.sf = nullptr; t.stride = 0; t.w = 0; t.rnd = 0; t.sh = 0;
+        t.lsh = 0; t.rnd2 = 0; t.sh2 = 0; t.flags = 0;
+        return t;
+    }
+    const int log2n = (int)(x.y & 0xff), c_idx = (int)((x.y >> 8) & 0xff), mid = (int)((x.y >> 16) & 0xff);
+    t.flags = (int)(x.y >> 24);
+    t.src = a.coeffs + (size_t)x.z * 16;
+    t.dst = a.out + x.x;
+    t.stride = c_idx ? a.stride_c : a.stride_y;
+    t.w = (int)(x.w & 0xffff);
+    t.sh = (int)((x.w >> 16) & 0xff);
+    t.lsh = (int)(x.w >> 24);
+    t.rnd = (1 << t.sh) >> 1;
+    t.sh2 = 20 - (c_idx ? a.bit_depth_c : a.bit_depth_y);
+    t.rnd2 = 1 << (t.sh2 - 1);
+    t.sf = nullptr;
+    if (a.sf && !(t.flags & P265_TU_PRESCALED)) {
+        const int base = (int)((0x07e001e000600000ull >> (16 * (log2n - 2))) & 0xffff);
+        t.sf = a.sf + base + (mid << (2 * log2n));
+    }
+    return t;
+}
+
+P265_HD uint4 load_xdesc(const KernelArgs &a, int tb_index, bool valid) {
+    return valid ? a.xtus[tb_index] : make_uint4(0, 0, 0, 0);
 }
 
 // d = Clip3(-32768, 32767, (lv * m * levelScale << per + round) >> bdShift) without the
@@ -530,10 +588,6 @@ P265_HD void build_sf_compact(const uint8_t *table, uint8_t *out, int tid, int n
             out[m * kSfcStride + e] = mat[(y8 * REP + (REP > 1 ? 1 : 0)) * N + x8 * REP + (REP - 1)];
         }
     }
-}
-P265_HD int sf_matrix_id(int log2n, int c_idx, int flags) {
-    const int not_intra = (flags & P265_TU_INTRA) ? 0 : 1;
-    return log2n == 5 ? not_intra : c_idx + 3 * not_intra;
 }
 
 // ------------------------------------------------- stage 1: ONE column of one TB

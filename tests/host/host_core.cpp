@@ -24,7 +24,7 @@ static void run_item_sf(const KernelArgs &a, int item) {
         bool valid;
         int tb = lane_tb<LOG2N>(a, item, lane, valid);
         lane_tb_index[lane] = valid ? tb : 0;
-        t[lane] = make_params(a, tb, valid);
+        t[lane] = params_from_x(a, valid ? expand_desc(a, load_desc(a, tb, true)) : make_uint4(0, 0, 0, 0), valid);
         slow |= t[lane].lsh != 0;
         tile_issue<LOG2N>(lane, t[lane].src, valid, in_buf);
     }
@@ -71,7 +71,7 @@ static void run_small_item(const KernelArgs &a, int bin, int item) {
     for (int lane = 0; lane < 32; lane++) {
         const int local = item * 32 + lane;
         const bool valid = local < a.n_tb[bin];
-        t[lane] = make_params(a, a.first_tb[bin] + local, valid);
+        t[lane] = params_from_x(a, valid ? expand_desc(a, load_desc(a, a.first_tb[bin] + local, true)) : make_uint4(0, 0, 0, 0), valid);
         slow |= valid && t[lane].lsh != 0;
     }
     for (int lane = 0; lane < 32; lane++) {
@@ -106,7 +106,7 @@ static void run_item(const KernelArgs &a, int item) {
 extern "C" int host_residual_batch(const p265_tu_desc *tus, const int32_t bin_counts[4], const int16_t *coeffs,
                                    const uint8_t *sf, int sf_replicated, const p265_pic_geom *g, int16_t *out) {
     KernelArgs a;
-    a.tus = tus; a.coeffs = coeffs; a.sf = sf; a.out = out; a.sf_replicated = sf_replicated;
+    a.tus = tus; a.xtus = nullptr; a.wait_prev = 0; a.coeffs = coeffs; a.sf = sf; a.out = out; a.sf_replicated = sf_replicated;
     for (int c = 0; c < 3; c++) a.plane_off[c] = g->plane_off[c];
     a.pic_stride = g->pic_stride;
     a.stride_y = g->stride_y; a.stride_c = g->stride_c;

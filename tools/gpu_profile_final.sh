@@ -9,7 +9,7 @@ $CMD > $OUT/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launches_$TAG.log 2>&1
 echo "launch list exit $?"
 $CMD > $OUT/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'residual_kernel|sao_kernel' -s 15 -c 5 -f -o $OUT/prof_$TAG $CMD > $OUT/ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'expand_kernel|residual_kernel|sao_kernel' -s 18 -c 6 -f -o $OUT/prof_$TAG $CMD > $OUT/ncu_full_$TAG.log 2>&1
 echo "full capture exit $?"
 KB="python tools/kbench.py --only deblock,recon --pics 8 --reps 3"
 $KB > $OUT/kb_plain_$TAG.log 2>&1 &&

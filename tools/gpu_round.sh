@@ -18,7 +18,7 @@ if [ "$BENCH_RC" = "0" ] && [ "$2" != "noncu" ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches_$TAG.csv $NCU_CMD > $OUT/ncu_launches_$TAG.log 2>&1
   echo "ncu launches exit $?"
   $NCU_CMD > $OUT/ncu_plain2_$TAG.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:'residual_kernel|sao_kernel' -s 8 -c 4 -f -o $OUT/prof_$TAG $NCU_CMD > $OUT/ncu_full_$TAG.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:'expand_kernel|residual_kernel|sao_kernel' -s 18 -c 6 -f -o $OUT/prof_$TAG $NCU_CMD > $OUT/ncu_full_$TAG.log 2>&1
   echo "ncu full exit $?"
 fi
 ls -la $OUT
