@@ -8,6 +8,7 @@
 // -> stage 2 transpose) is warp-private shared memory fenced by __syncwarp(), so there
 // is no __syncthreads() in the kernel and CTAs are only a scheduling container.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "internal.h"
 #include "residual_core.cuh"
@@ -461,7 +462,15 @@ static int launch_bin(p265_ctx *ctx, KernelArgs a, bool first) {
         occ = o < 1 ? 1 : o;
     }
     // persistent grid, trimmed so that every warp gets the same number of items
-    const int max_warps = ctx->sm_count * occ * kWarpsPerCta;
+    static int pct = -1;  // tuning knob: P265_GRID_PCT limits the resident CTAs (kernels sharing the SMs)
+    if (pct < 0) {
+        const char *e = getenv("P265_GRID_PCT");
+        pct = e ? atoi(e) : 100;
+        if (pct < 1 || pct > 100) pct = 100;
+    }
+    int occ_use = (occ * pct + 99) / 100;
+    if (occ_use < 1) occ_use = 1;
+    const int max_warps = ctx->sm_count * occ_use * kWarpsPerCta;
     const int rounds = (items + max_warps - 1) / max_warps;
     const int warps = (items + rounds - 1) / rounds;
     const int grid = (warps + kWarpsPerCta - 1) / kWarpsPerCta;

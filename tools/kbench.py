@@ -68,6 +68,46 @@ def main():
         bench_deblock(args, eng, dev, stream, to_dev)
     if want("overlap"):
         bench_overlap(args, eng, dev, stream, to_dev)
+    if want("split"):
+        bench_split(args, eng, dev, stream, to_dev)
+
+
+def bench_split(args, eng, dev, stream, to_dev):
+    """Big bins (32x32 + 16x16) on one stream, small bins (8x8 + 4x4) on another, concurrently
+    (run with P265_GRID_PCT=50 so that both kernels' CTAs fit an SM together)."""
+    full = synth.residual_batch("4k10", n_pics=args.pics, n_unique=min(2, args.pics))
+    d_co, d_sf = to_dev(full.coeffs), to_dev(full.scaling_factor)
+    d_out = torch.empty(full.geom.total_elems() * 2, dtype=torch.uint8, device=dev)
+    stream2 = torch.cuda.Stream(device=dev)
+    eng2 = Engine(0, stream2.cuda_stream)
+    l2 = full.tus["log2n"]
+    for label, sel_a, sel_b in (("{32,16} || {8,4}", l2 >= 4, l2 < 4), ("{32,4} || {16,8}", (l2 == 5) | (l2 == 2), (l2 == 4) | (l2 == 3))):
+        ba = ResidualBatch(full.geom, np.ascontiguousarray(full.tus[sel_a]), full.coeffs, full.scaling_factor, covers_all=True)
+        bb = ResidualBatch(full.geom, np.ascontiguousarray(full.tus[sel_b]), full.coeffs, full.scaling_factor, covers_all=True)
+        ta, tb = to_dev(ba.tus), to_dev(bb.tus)
+        bins_a, bins_b = ba.bin_counts(), bb.bin_counts()
+
+        def run_a():
+            eng.residual_dev(ta.data_ptr(), bins_a, d_co.data_ptr(), d_sf.data_ptr(), full.geom, d_out.data_ptr(),
+                             zero_fill=False, sf_replicated=True)
+
+        def run_b():
+            eng2.residual_dev(tb.data_ptr(), bins_b, d_co.data_ptr(), d_sf.data_ptr(), full.geom, d_out.data_ptr(),
+                              zero_fill=False, sf_replicated=True)
+        for _ in range(3):
+            run_a(); run_b()
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(stream)
+        stream2.wait_event(e0)
+        for _ in range(args.reps):
+            run_a(); run_b()
+        e2.record(stream2)
+        stream.wait_event(e2)
+        e1.record(stream)
+        e1.synchronize()
+        print("split residual %-20s %8.4f ms per batch (P265_GRID_PCT=%s)" % (label, e0.elapsed_time(e1) / args.reps,
+                                                                              os.environ.get("P265_GRID_PCT", "100")), flush=True)
 
 
 def bench_overlap(args, eng, dev, stream, to_dev):
