@@ -24,7 +24,7 @@ namespace p265 {
 #define P265_CTAS_PER_SM 11
 #endif
 #ifndef P265_CTAS_BIN0
-#define P265_CTAS_BIN0 12  // 8.3 KB of shared memory per warp after the per-TB descriptor ring
+#define P265_CTAS_BIN0 8   // 128 registers for the lock-step two-column / two-row passes (8.3 KB smem per warp)
 #endif
 constexpr int kWarpsPerCta = P265_WARPS_PER_CTA;
 constexpr int kCtasPerSm = P265_CTAS_PER_SM;
@@ -47,6 +47,18 @@ __device__ __noinline__ void stage1_call(const unsigned char *in, unsigned char 
                                          const uint8_t *sf, int w, int rnd, int sh, int lsh, int dst_flag) {
     stage1_column<LOG2N, SF, SLOW>(in, g, x, tl, half, sf, w, rnd, sh, lsh, dst_flag);
 }
+template <int LOG2N, int SF, bool SLOW>
+__device__ __noinline__ void stage1_pair_call(const unsigned char *in, unsigned char *g, int x0, int x1, int tl,
+                                              const uint8_t *sf, int w, int rnd, int sh, int lsh) {
+    stage1_pair<LOG2N, SF, SLOW>(in, g, x0, x1, tl, sf, w, rnd, sh, lsh);
+}
+#ifndef P265_PAIR16
+#define P265_PAIR16 1  // 16x16: both columns of a lane in lock step (stage1_pair): -6 % on that bin
+#endif
+#ifndef P265_PAIR32
+#define P265_PAIR32 1  // 32x32: lock-step form at 128 registers / 8 CTAs per SM: -10 % on that bin (12..16
+#endif                 // warps perform alike: the bin is bound by per-warp ILP, not by occupancy)
+// (the same lock-step form for the two rows of stage 2 was measured too: no gain on 32x32, -3 % on 16x16)
 template <int LOG2N>
 __device__ __noinline__ void stage2_call(const unsigned char *g, int row, int16_t *dst, int rnd2, int sh2,
                                          int dst_flag) {
@@ -101,7 +113,10 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
         const uint8_t *sf1 = t.sf;
         if (SF == SF_REPLICATED && t.sf)
             sf1 = sfc + (int)((ring[RS * k].y >> 16) & 0xff) * kSfcStride;  // matrixId from the expanded record
-        if (!slow) {
+        if ((P265_PAIR16 && LOG2N == 4) || (P265_PAIR32 && LOG2N == 5)) {
+            if (!slow) stage1_pair_call<LOG2N, SF, false>(in, g, x0, x1, tl, sf1, t.w, t.rnd, t.sh, 0);
+            else stage1_pair_call<LOG2N, SF, true>(in, g, x0, x1, tl, sf1, t.w, t.rnd, t.sh, t.lsh);
+        } else if (!slow) {
             stage1_call<LOG2N, SF, false>(in, g, x0, tl, 0, sf1, t.w, t.rnd, t.sh, 0, dstf);
             stage1_call<LOG2N, SF, false>(in, g, x1, tl, 1, sf1, t.w, t.rnd, t.sh, 0, dstf);
         } else {  // rare

@@ -653,6 +653,62 @@ P265_HD void stage1_column(const unsigned char *in, unsigned char *g, int x, int
         *reinterpret_cast<uint16_t *>(base[L::swz(y)] + y * L::ROW_BYTES) = sat_s16(e[0][y] >> 7);
 }
 
+// ------------------------------------------------- stage 1: BOTH columns of a lane in lock step
+// Same arithmetic as two stage1_column calls (columns x0 = slot tl half 0, x1 = half 1), but
+// the two columns share every basis constant and their results leave as one packed 32-bit
+// store per row (half the I2IP / STS of the one-column form).  Needs twice the registers of
+// the transform state, so it is used where that fits the occupancy target (16x16).
+template <int LOG2N, int SF, bool SLOW>
+P265_HD void stage1_pair(const unsigned char *in, unsigned char *g, int x0, int x1, int tl, const uint8_t *sf, int w,
+                         int rnd, int sh, int lsh) {
+    using L = Layout<LOG2N>;
+    constexpr int N = L::N;
+    constexpr int K = N < 8 ? N : 8;
+    constexpr int REP = N / K;
+    static_assert(N >= 8, "pair form is for the shared-memory sizes");
+    if (SF != SF_NONE && sf == nullptr) return;
+    TbParams t;
+    t.rnd = rnd; t.sh = sh; t.lsh = lsh;
+    int p[2][N / 2];
+    P265_UNROLL
+    for (int c = 0; c < 2; c++) {
+        const int x = c ? x1 : x0;
+        int mw[K];
+        int dc = 0;
+        if (SF == SF_REPLICATED) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(sf + (x / REP) * 8);
+            P265_UNROLL
+            for (int k = 0; k < K; k++) mw[k] = (int)(((k < 4 ? v.x : v.y) >> (8 * (k & 3))) & 0xff) * w;
+            dc = (x == 0) ? (int)sf[64] * w : mw[0];
+        }
+        P265_UNROLL
+        for (int s = 0; s < N / 2; s++) {
+            const int y0 = slot_index(N, s, 0), y1 = slot_index(N, s, 1);
+            const int e0 = y0 * N + x, e1 = y1 * N + x;
+            const int l0 = lds_s16(in, e0 * 2), l1 = lds_s16(in, e1 * 2);
+            int m0 = w, m1 = w;
+            if (SF == SF_GENERAL) {
+                m0 *= (int)sf[e0];
+                m1 *= (int)sf[e1];
+            } else if (SF == SF_REPLICATED) {
+                m0 = y0 == 0 ? dc : mw[y0 / REP];
+                m1 = mw[y1 / REP];
+            }
+            if (!SLOW) p[c][s] = pack_sat(dequant_fast(l0, m0, t), dequant_fast(l1, m1, t));
+            else p[c][s] = pack_sat(dequant(l0, m0, t), dequant(l1, m1, t));
+        }
+    }
+    int e[2][N];
+    Idct<N, 2>::run(p, 64, e);
+    // g[y][slot tl] = (clip16((e0[y] + 64) >> 7), clip16((e1[y] + 64) >> 7)); chunk index XOR-swizzled per row
+    unsigned char *base[4];
+    P265_UNROLL
+    for (int q = 0; q < 4; q++) base[q] = g + ((((tl >> 2) ^ q) << 4) | ((tl & 3) << 2));
+    P265_UNROLL
+    for (int y = 0; y < N; y++)
+        *reinterpret_cast<uint32_t *>(base[L::swz(y)] + y * L::ROW_BYTES) = (uint32_t)pack_sat(e[0][y] >> 7, e[1][y] >> 7);
+}
+
 // ------------------------------------------------- stage 2: ONE row of one TB
 // Horizontal pass (8.6.4.2) over row `row` of g, final bdShift rounding (8.6.2), int16
 // saturation and the 2N-byte row store into the residual plane.

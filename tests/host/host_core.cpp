@@ -42,6 +42,12 @@ static void run_item_sf(const KernelArgs &a, int item) {
             const p265_tu_desc &d = a.tus[lane_tb_index[lane]];
             sf1 = sfc + sf_matrix_id(LOG2N, d.c_idx, q.flags) * kSfcStride;
         }
+        if constexpr (LOG2N >= 4) {  // the kernel runs both columns of a lane in lock step
+            const int xa = slot_index_rt(N, tl, 0), xb = slot_index_rt(N, tl, 1);
+            if (slow) stage1_pair<LOG2N, SF, true>(in, g, xa, xb, tl, sf1, q.w, q.rnd, q.sh, q.lsh);
+            else stage1_pair<LOG2N, SF, false>(in, g, xa, xb, tl, sf1, q.w, q.rnd, q.sh, 0);
+            continue;
+        }
         for (int half = 0; half < 2; half++) {
             const int x = slot_index_rt(N, tl, half);
             const int dstf = q.flags & P265_TU_DST;
