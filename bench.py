@@ -30,7 +30,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -148,7 +147,6 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from p265_b200.engine import Engine
-    from p265_b200.picture import SAO_CTB, TU_DESC
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

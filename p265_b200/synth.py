@@ -19,7 +19,7 @@ from __future__ import annotations
 import numpy as np
 
 from .picture import (AVAIL_ALL, SAO_CTB, TU_BYPASS, TU_DESC, TU_DST, TU_INTRA, TU_SKIP,
-                      PicGeom, ResidualBatch, pack_scaling_factor, sort_by_size)
+                      PicGeom, ResidualBatch, pack_scaling_factor)
 from .scaling_list import default_scaling_factor
 
 CONFIGS = {

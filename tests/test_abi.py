@@ -4,7 +4,6 @@ import ctypes as C
 import os
 import re
 
-import numpy as np
 
 from conftest import REPO
 from p265_b200 import _lib, build, picture

@@ -4,14 +4,12 @@ and against the spec oracle."""
 import importlib
 import os
 import sys
-import tempfile
 import types
 
 import numpy as np
 import pytest
 
 from conftest import GOLDEN, REPO
-from oracle import refshim
 from oracle import spec_oracle as so
 
 sys.path.insert(0, os.path.join(REPO, "tests", "golden"))

@@ -10,7 +10,6 @@ import pytest
 
 from conftest import REPO, small_cfg
 from p265_b200 import synth
-from p265_b200.picture import PicGeom, ResidualBatch
 
 
 @pytest.fixture(scope="module")

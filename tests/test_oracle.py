@@ -11,7 +11,7 @@ from conftest import GOLDEN
 from oracle import refshim
 from oracle import spec_oracle as so
 from p265_b200 import scaling_list, synth
-from p265_b200.picture import PicGeom, ResidualBatch, pack_scaling_factor
+from p265_b200.picture import pack_scaling_factor
 
 # sha256 of the 32x32 int8 basis as bytes (row-major) -- pins the table on boxes without
 # the reference; test_tables_equal_reference checks it against transform.py:7-72 here.

@@ -4,7 +4,7 @@ Quick A/B tool for tuning runs (not the contract benchmark -- that is bench.py).
 
     python tools/kbench.py [--pics 8] [--reps 20]
 """
-import argparse, os, sys, json
+import argparse, os, sys
 import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)

@@ -1,7 +1,6 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (run here, no GPU needed):  python tools/ncu_summary.py rep [kernel-regex]"""
 import csv, io, subprocess, sys
-from collections import Counter
 
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
