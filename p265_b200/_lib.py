@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libp265b200.so")
+# P265_LIB: another build of the same library (A/B tuning runs, tools/kbench.py); never a fallback
+LIB_PATH = os.environ.get("P265_LIB") or os.path.join(HERE, "libp265b200.so")
 
 P265_OK, P265_EINVAL, P265_ECUDA, P265_ENOMEM = 0, -1, -2, -3
 RES_ZERO_FILL = 1

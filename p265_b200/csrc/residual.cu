@@ -59,87 +59,119 @@ __device__ __noinline__ void stage1_pair_call(const unsigned char *in, unsigned 
 #define P265_PAIR32 1  // 32x32: lock-step form at 128 registers / 8 CTAs per SM: -10 % on that bin (12..16
 #endif                 // warps perform alike: the bin is bound by per-warp ILP, not by occupancy)
 // (the same lock-step form for the two rows of stage 2 was measured too: no gain on 32x32, -3 % on 16x16)
+// Both rows of a lane in one call, one after the other (not unrolled: one copy of the pass).  The
+// result rows go back into g (stage2_row_g) and leave through the coalesced copy-out of run_bin.
 template <int LOG2N>
-__device__ __noinline__ void stage2_call(const unsigned char *g, int row, int16_t *dst, int rnd2, int sh2,
-                                         int dst_flag) {
-    stage2_row<LOG2N>(g, row, dst, rnd2, sh2, dst_flag);
+__device__ __noinline__ void stage2_call(unsigned char *g, int row, int rnd2, int sh2) {
+#pragma unroll 1
+    for (int r = 0; r < 2; r++) {
+        stage2_row_g<LOG2N>(g, row, rnd2, sh2);
+        row += Layout<LOG2N>::TPB;
+    }
 }
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // One size bin, one warp: items w, w + W, w + 2W, ... of the bin.  Software pipeline,
 // everything asynchronous (cp.async / LDGSTS, no register staging):
-//     descriptor of item k+2  ->  lane-private slot of a 2-entry ring in shared memory
-//     tile of item k+1        ->  `in`, issued as soon as stage 1 of item k has consumed it
-//     stage 2 of item k       ->  overlaps the tile copy
-// so both dependent global-memory latencies of an item hide behind arithmetic.
+//     descriptor of item k+2  ->  slot (k+2) % 3 of a ring in shared memory (one entry per TB)
+//     tile of item k+1        ->  prefetched into L2 at the top of item k (one line per lane), copied into
+//                                 `in` as soon as stage 1 of item k has consumed it (an L2 hit by then)
+//     stage 2 of item k       ->  overlaps the tile copy; its result rows go back into g
+//     copy-out of item k      ->  whole rows per store instruction (OutMap)
+// so both dependent global-memory latencies of an item hide behind arithmetic.  The per-item
+// set-up reads the expanded record's fields as they are (no parameter derivation in the loop).
 template <int LOG2N, int SF>
 __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride, int lane, unsigned char *wbase,
                                         const uint8_t *sfc) {
     using L = Layout<LOG2N>;
+    using M = OutMap<LOG2N>;
     constexpr int N = L::N, bin = 5 - LOG2N;
     const int n_items = a.first_item[bin + 1] - a.first_item[bin];
     if (gw >= n_items) return;
+    const int n_tb = a.n_tb[bin];
+    const uint4 *xt = a.xtus + a.first_tb[bin];
     unsigned char *in_base = wbase, *g_base = wbase + L::WARP_BYTES;
     const int tb_l = lane / L::TPB, tl = lane % L::TPB;
-    // descriptor ring: one entry per TB of the item (all lanes of a TB read the same one), 2 slots
-    constexpr int RS = L::TBS;  // slot s at ring[RS * s]
-    uint4 *ring = reinterpret_cast<uint4 *>(wbase + 2 * L::WARP_BYTES) + tb_l;
+    constexpr int RS = L::TBS;  // ring slot s = ring0[RS * s .. RS * s + RS)
+    uint4 *ring0 = reinterpret_cast<uint4 *>(wbase + 2 * L::WARP_BYTES);
+    uint4 *ring = ring0 + tb_l;  // the lane's own TB
     const unsigned char *in = in_base + tb_l * L::TB_BYTES;
     unsigned char *g = g_base + tb_l * L::TB_BYTES;
     const int x0 = slot_index_rt(N, tl, 0), x1 = slot_index_rt(N, tl, 1);
-    bool valid;
+    constexpr int kLines = N * N * 2 / 128;  // 128-byte lines per TB (<= lanes per TB)
     {   // prologue: first descriptor by plain load, its tile and the second descriptor async
-        const int tb = lane_tb<LOG2N>(a, gw, lane, valid);
-        const uint4 d0 = load_xdesc(a, tb, valid);
+        const int tb = gw * L::TBS + tb_l;
+        const bool valid = tb < n_tb;
+        const uint4 d0 = valid ? xt[tb] : make_uint4(0, 0, 0, 0);
         ring[0] = d0;
         tile_issue<LOG2N>(lane, a.coeffs + (size_t)d0.z * 16, valid, in_base);
-        if (gw + stride < n_items) {
-            bool v1;
-            const int tb1 = lane_tb<LOG2N>(a, gw + stride, lane, v1);
-            if (v1 && tl == 0) copy16_async(&ring[RS], &a.xtus[tb1]);
-        }
+        const int tb1 = (gw + stride) * L::TBS + tb_l;
+        if (gw + stride < n_items && tb1 < n_tb && tl == 0) copy16_async(&ring[RS], &xt[tb1]);
         cp_async_commit();
     }
-    int k = 0;
-    for (int it = gw; it < n_items; it += stride, k ^= 1) {
+    int k = 0, k1 = 1, k2 = 2;  // ring slots of items it, it + stride, it + 2 * stride
+    for (int it = gw; it < n_items; it += stride) {
         cp_async_wait<0>();  // tile k and descriptor k+1 have landed
         __syncwarp();        // ... for every lane; also: all lanes are done with g of item k-1
-        lane_tb<LOG2N>(a, it, lane, valid);
-        const TbParams t = params_from_x(a, ring[RS * k], valid);
-        const bool is_special = (t.flags & (P265_TU_SKIP | P265_TU_BYPASS)) != 0;
-        const bool slow = __any_sync(0xffffffffu, t.lsh != 0);
-        if (__any_sync(0xffffffffu, t.valid && is_special)) phase_special<LOG2N>(lane, t, in_base);
-        const int dstf = t.flags & P265_TU_DST;
-        // SF_REPLICATED: stage 1 reads the CTA's compact copy of this TB's matrix
-        const uint8_t *sf1 = t.sf;
-        if (SF == SF_REPLICATED && t.sf)
-            sf1 = sfc + (int)((ring[RS * k].y >> 16) & 0xff) * kSfcStride;  // matrixId from the expanded record
+        const bool valid = it * L::TBS + tb_l < n_tb;
+        const bool more = it + stride < n_items;
+        const bool v1 = more && (it + stride) * L::TBS + tb_l < n_tb;
+        const uint4 d = ring[RS * k];
+        if (v1 && tl < kLines)  // next tile -> L2 while this item is transformed
+            prefetch_l2(a.coeffs + (size_t)ring[RS * k1].z * 16 + tl * 64);
+        const int flags = valid ? (int)xd_flags(d) : 0;
+        const int w = valid ? xd_w(d) : 0, sh = xd_sh(d), lsh = valid ? xd_lsh(d) : 0;
+        const int rnd = (1 << sh) >> 1;
+        // SF_REPLICATED: stage 1 reads the CTA's compact copy of this TB's matrix (matrixId from the record)
+        const uint8_t *sf1 = nullptr;
+        if (SF != SF_NONE && valid && !(flags & P265_TU_PRESCALED))
+            sf1 = SF == SF_REPLICATED ? sfc + xd_mid(d) * kSfcStride
+                                      : a.sf + sf_matrix_offset(LOG2N, 0, 1) + (xd_mid(d) << (2 * LOG2N));
+        // rare, warp-uniform: transform-skip / bypass TBs, left-shift dequantisation
+        const bool is_special = (flags & (P265_TU_SKIP | P265_TU_BYPASS)) != 0;
+        bool slow = false;
+        if (__any_sync(0xffffffffu, is_special || lsh != 0)) {
+            slow = __any_sync(0xffffffffu, lsh != 0);
+            if (__any_sync(0xffffffffu, is_special)) phase_special<LOG2N>(lane, params_from_x(a, d, valid, LOG2N), in_base);
+        }
         if ((P265_PAIR16 && LOG2N == 4) || (P265_PAIR32 && LOG2N == 5)) {
-            if (!slow) stage1_pair_call<LOG2N, SF, false>(in, g, x0, x1, tl, sf1, t.w, t.rnd, t.sh, 0);
-            else stage1_pair_call<LOG2N, SF, true>(in, g, x0, x1, tl, sf1, t.w, t.rnd, t.sh, t.lsh);
+            if (!slow) stage1_pair_call<LOG2N, SF, false>(in, g, x0, x1, tl, sf1, w, rnd, sh, 0);
+            else stage1_pair_call<LOG2N, SF, true>(in, g, x0, x1, tl, sf1, w, rnd, sh, lsh);
         } else if (!slow) {
-            stage1_call<LOG2N, SF, false>(in, g, x0, tl, 0, sf1, t.w, t.rnd, t.sh, 0, dstf);
-            stage1_call<LOG2N, SF, false>(in, g, x1, tl, 1, sf1, t.w, t.rnd, t.sh, 0, dstf);
+            stage1_call<LOG2N, SF, false>(in, g, x0, tl, 0, sf1, w, rnd, sh, 0, 0);
+            stage1_call<LOG2N, SF, false>(in, g, x1, tl, 1, sf1, w, rnd, sh, 0, 0);
         } else {  // rare
-            stage1_call<LOG2N, SF, true>(in, g, x0, tl, 0, sf1, t.w, t.rnd, t.sh, t.lsh, dstf);
-            stage1_call<LOG2N, SF, true>(in, g, x1, tl, 1, sf1, t.w, t.rnd, t.sh, t.lsh, dstf);
+            stage1_call<LOG2N, SF, true>(in, g, x0, tl, 0, sf1, w, rnd, sh, lsh, 0);
+            stage1_call<LOG2N, SF, true>(in, g, x1, tl, 1, sf1, w, rnd, sh, lsh, 0);
         }
         __syncwarp();  // `in` is consumed, g is complete
-        if (it + stride < n_items) {
-            bool v1;
-            lane_tb<LOG2N>(a, it + stride, lane, v1);
-            const uint4 dn = ring[RS * (k ^ 1)];
-            tile_issue<LOG2N>(lane, a.coeffs + (size_t)dn.z * 16, v1, in_base);
-            if (it + 2 * stride < n_items) {  // slot k is free: its descriptor sits in `t`
-                bool v2;
-                const int tb2 = lane_tb<LOG2N>(a, it + 2 * stride, lane, v2);
-                if (v2 && tl == 0) copy16_async(&ring[RS * k], &a.xtus[tb2]);
-            }
+        if (more) {
+            tile_issue<LOG2N>(lane, a.coeffs + (size_t)ring[RS * k1].z * 16, v1, in_base);
+            const int tb2 = (it + 2 * stride) * L::TBS + tb_l;
+            if (it + 2 * stride < n_items && tb2 < n_tb && tl == 0) copy16_async(&ring[RS * k2], &xt[tb2]);
         }
         cp_async_commit();
-        if (t.valid && !is_special) {
-            stage2_call<LOG2N>(g, tl, t.dst + (size_t)tl * t.stride, t.rnd2, t.sh2, dstf);
-            stage2_call<LOG2N>(g, tl + L::TPB, t.dst + (size_t)(tl + L::TPB) * t.stride, t.rnd2, t.sh2, dstf);
+        if (valid && !is_special) {
+            const int sh2 = xd_sh2(d);
+            stage2_call<LOG2N>(g, tl, 1 << (sh2 - 1), sh2);
         }
+        __syncwarp();  // every result row of the item sits in g
+        // copy-out: store instruction i = 32 / (N/8) whole rows of TB i / IPT
+        const int n_here = n_tb - it * L::TBS;  // TBs of this item that exist (>= 1)
+#pragma unroll
+        for (int t = 0; t < L::TBS; t++) {
+            const uint4 dt = ring0[RS * k + t];  // same record for every lane
+            const bool skip = t >= n_here || (xd_flags(dt) & (P265_TU_SKIP | P265_TU_BYPASS));
+            const size_t row_step = (size_t)xd_stride(dt);
+            int16_t *dst = a.out + dt.x + (size_t)M::row(t * M::IPT, lane) * row_step + M::part(lane) * 8;
+#pragma unroll
+            for (int j = 0; j < M::IPT; j++) {
+                const uint4 v = out_chunk_load<LOG2N>(g_base, t * M::IPT + j, lane);
+                if (!skip) *reinterpret_cast<uint4 *>(dst + (size_t)(j * M::RPI) * row_step) = v;
+            }
+        }
+        const int kk = k; k = k1; k1 = k2; k2 = kk;
     }
     cp_async_wait<0>();
     __syncwarp();
@@ -150,7 +182,7 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
 // lane per TB), but with a ScalingFactor table the per-TB table pointer is cheaper from the
 // expanded record and expand_kernel's pass leaves the descriptors in L2: measured on the 4K
 // 10-bit mix, +3 % with a table, -3 % without -> chosen by the SF mode.
-template <int SF>
+template <int SF, int LOG2N>
 struct SmallDesc {
     static constexpr bool X = SF != SF_NONE;
     static __device__ __forceinline__ uint4 load(const KernelArgs &a, int i, bool v) {
@@ -160,21 +192,37 @@ struct SmallDesc {
         return X ? &a.xtus[i] : reinterpret_cast<const uint4 *>(&a.tus[i]);
     }
     static __device__ __forceinline__ TbParams params(const KernelArgs &a, const uint4 d, bool v) {
-        return X ? params_from_x(a, d, v) : make_params(a, d, v);
+        return X ? params_from_x(a, d, v, LOG2N) : make_params(a, d, v);
     }
 };
+// Small bins with a ScalingFactor table: the CTA keeps the 6 matrices of its size ([y][x] bytes,
+// as in the table) plus an all-ones matrix (matrixId 6 of the expanded record = prescaled TB,
+// m = 1) at the start of its shared memory, so a TB's factors come from an LDS issued next to
+// its tile reads instead of a dependent global load at the head of every item.
+template <int LOG2N>
+__device__ __forceinline__ void build_sf_small(const uint8_t *table, uint8_t *out, int tid, int nthreads) {
+    constexpr int NN = 1 << (2 * LOG2N);
+    const uint8_t *base = table + sf_matrix_offset(LOG2N, 0, 1);
+    for (int i = tid; i < 7 * NN; i += nthreads) out[i] = i < 6 * NN ? base[i] : (uint8_t)1;
+}
+template <int SF, int LOG2N>
+__device__ __forceinline__ const uint8_t *small_sf_ptr(const uint8_t *sfs, const uint4 d) {
+    return SF != SF_NONE ? sfs + (xd_mid(d) << (2 * LOG2N)) : nullptr;
+}
+
 template <int SF, bool SLOW>
 __device__ __noinline__ void tb8_call(const KernelArgs &a, const uint4 d, bool valid, const unsigned char *tile,
-                                      int lane) {
-    const TbParams t = SmallDesc<SF>::params(a, d, valid);
-    tb8_lane<SF, SLOW>(t, tile, lane);
+                                      int lane, const uint8_t *sfs) {
+    const TbParams t = SmallDesc<SF, 3>::params(a, d, valid);
+    tb8_lane<SF, SLOW>(t, tile, lane, small_sf_ptr<SF, 3>(sfs, d));
 }
 
 // 8x8 bin: 32 TBs per item; the lane's 128-byte TB is copied asynchronously into a
 // lane-private, chunk-swizzled slot of one of the warp's two tile buffers while the
 // previous item is being transformed; descriptors run two items ahead in the ring.
 template <int SF>
-__device__ __forceinline__ void run_bin8(const KernelArgs &a, int gw, int stride, int lane, unsigned char *wbase) {
+__device__ __forceinline__ void run_bin8(const KernelArgs &a, int gw, int stride, int lane, unsigned char *wbase,
+                                         const uint8_t *sfs) {
     const int n_tb = a.n_tb[2], first = a.first_tb[2];
     const int n_items = (n_tb + 31) >> 5;
     if (gw >= n_items) return;
@@ -187,11 +235,11 @@ __device__ __forceinline__ void run_bin8(const KernelArgs &a, int gw, int stride
     };
     bool valid = gw * 32 + lane < n_tb;
     {
-        const uint4 d0 = SmallDesc<SF>::load(a, first + gw * 32 + lane, valid);
+        const uint4 d0 = SmallDesc<SF, 3>::load(a, first + gw * 32 + lane, valid);
         ring[0] = d0;
         issue(d0, valid, wbase);
         const int i1 = (gw + stride) * 32 + lane;
-        if (gw + stride < n_items && i1 < n_tb) copy16_async(&ring[32], SmallDesc<SF>::ptr(a, first + i1));
+        if (gw + stride < n_items && i1 < n_tb) copy16_async(&ring[32], SmallDesc<SF, 3>::ptr(a, first + i1));
         cp_async_commit();
     }
     int k = 0;
@@ -203,21 +251,21 @@ __device__ __forceinline__ void run_bin8(const KernelArgs &a, int gw, int stride
             const int i1 = (it + stride) * 32 + lane;
             issue(ring[32 * (k ^ 1)], i1 < n_tb, wbase + (k ^ 1) * kWarpSmemBytes);
             const int i2 = (it + 2 * stride) * 32 + lane;
-            if (it + 2 * stride < n_items && i2 < n_tb) copy16_async(&ring[32 * k], SmallDesc<SF>::ptr(a, first + i2));
+            if (it + 2 * stride < n_items && i2 < n_tb) copy16_async(&ring[32 * k], SmallDesc<SF, 3>::ptr(a, first + i2));
         }
         cp_async_commit();
         // per >= bdShift needs qP >= 6 * (bitDepth - 2): impossible for 8x8 below 14 bits,
         // but the descriptor is caller data: decide warp-uniformly like the other sizes
         bool slow_lane;
-        if (SmallDesc<SF>::X) {
+        if (SmallDesc<SF, 3>::X) {
             slow_lane = (d_cur.w >> 24) != 0;
         } else {
             const int qp = (int)((d_cur.y >> 16) & 0xff), c_idx = (int)((d_cur.y >> 8) & 0xff);
             slow_lane = ((qp * 43) >> 8) >= (c_idx ? a.bit_depth_c : a.bit_depth_y) - 2;
         }
         const bool slow = __any_sync(0xffffffffu, valid && slow_lane);
-        if (slow) tb8_call<SF, true>(a, d_cur, valid, wbase + k * kWarpSmemBytes, lane);
-        else tb8_call<SF, false>(a, d_cur, valid, wbase + k * kWarpSmemBytes, lane);
+        if (slow) tb8_call<SF, true>(a, d_cur, valid, wbase + k * kWarpSmemBytes, lane, sfs);
+        else tb8_call<SF, false>(a, d_cur, valid, wbase + k * kWarpSmemBytes, lane, sfs);
     }
     cp_async_wait<0>();
 }
@@ -236,7 +284,8 @@ __device__ __forceinline__ int tb4_slot_off(int lane, int half) {
 }
 
 template <int SF>
-__device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride, int lane, unsigned char *wbase) {
+__device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride, int lane, unsigned char *wbase,
+                                         const uint8_t *sfs) {
     const int n_tb = a.n_tb[3], first = a.first_tb[3];
     const int n_items = (n_tb + 31) >> 5;
     if (gw >= n_items) return;
@@ -244,7 +293,7 @@ __device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride
     uint4 *ring = reinterpret_cast<uint4 *>(wbase + kBin4Stages * 1024) + lane;      // slot s at ring[32 * s]
     auto desc_async = [&](int item, int slot) {
         const int i = item * 32 + lane;
-        if (item < n_items && i < n_tb) copy16_async(&ring[32 * slot], SmallDesc<SF>::ptr(a, first + i));
+        if (item < n_items && i < n_tb) copy16_async(&ring[32 * slot], SmallDesc<SF, 2>::ptr(a, first + i));
     };
     auto tile_async = [&](int item, const uint4 d, int stage) {
         const int i = item * 32 + lane;
@@ -260,7 +309,7 @@ __device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride
     {   // prologue: descriptors 0..2 by plain loads (paid once per warp and bin)
         for (int j = 0; j < 3; j++) {
             const int i = (gw + j * stride) * 32 + lane;
-            ring[32 * j] = SmallDesc<SF>::load(a, first + i, gw + j * stride < n_items && i < n_tb);
+            ring[32 * j] = SmallDesc<SF, 2>::load(a, first + i, gw + j * stride < n_items && i < n_tb);
         }
         tile_async(gw, ring[0], 0);
         cp_async_commit();
@@ -278,7 +327,7 @@ __device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride
         tile_async(it + 2 * stride, ring[32 * ((k + 2) & 3)], (k + 2) % kBin4Stages);
         desc_async(it + 4 * stride, k & 3);
         cp_async_commit();
-        const TbParams t = SmallDesc<SF>::params(a, d_cur, valid);
+        const TbParams t = SmallDesc<SF, 2>::params(a, d_cur, valid);
         uint32_t w[8];
         {
             const uint4 v0 = *reinterpret_cast<const uint4 *>(tiles + st * 1024 + tb4_slot_off(lane, 0));
@@ -287,8 +336,9 @@ __device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride
             w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
         }
         const bool slow = __any_sync(0xffffffffu, t.lsh != 0);
-        if (slow) tb4_lane<SF, true>(t, w);
-        else tb4_lane<SF, false>(t, w);
+        const uint8_t *sfm = small_sf_ptr<SF, 2>(sfs, d_cur);
+        if (slow) tb4_lane<SF, true>(t, w, sfm);
+        else tb4_lane<SF, false>(t, w, sfm);
     }
     cp_async_wait<0>();
 }
@@ -309,8 +359,8 @@ struct BinCfg {
     // per warp: tile + g buffers + descriptor ring (2 slots x TBs per item x 16 B for the big sizes)
     static constexpr int smem =
         BIN == 3 ? kSfcBytes + kWarpsPerCta * kBin4WarpBytes
-        : BIN == 0 ? kSfcBytes + kWarpsPerCta * (2 * Layout<5>::WARP_BYTES + 2 * Layout<5>::TBS * 16)
-        : BIN == 1 ? kSfcBytes + kWarpsPerCta * (2 * Layout<4>::WARP_BYTES + 2 * Layout<4>::TBS * 16)
+        : BIN == 0 ? kSfcBytes + kWarpsPerCta * (2 * Layout<5>::WARP_BYTES + 3 * Layout<5>::TBS * 16 + 32)
+        : BIN == 1 ? kSfcBytes + kWarpsPerCta * (2 * Layout<4>::WARP_BYTES + 3 * Layout<4>::TBS * 16)
                    : kSfcBytes + kCtaSmemBytes;
 };
 
@@ -335,10 +385,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, BinCfg<BIN>::ctas) residual
         else build_sf_compact<4>(a.sf, smem, threadIdx.x, blockDim.x);
         __syncthreads();  // the only block-wide barrier: once per persistent CTA
     }
+    if (SF != SF_NONE && BIN >= 2) {
+        if (BIN == 2) build_sf_small<3>(a.sf, smem, threadIdx.x, blockDim.x);
+        else build_sf_small<2>(a.sf, smem, threadIdx.x, blockDim.x);
+        __syncthreads();
+    }
     if (BIN == 0) run_bin<5, SF>(a, gw, stride, lane, wbase, smem);
     else if (BIN == 1) run_bin<4, SF>(a, gw, stride, lane, wbase, smem);
-    else if (BIN == 2) run_bin8<SF>(a, gw, stride, lane, wbase);
-    else run_bin4<SF>(a, gw, stride, lane, wbase);
+    else if (BIN == 2) run_bin8<SF>(a, gw, stride, lane, wbase, smem);
+    else run_bin4<SF>(a, gw, stride, lane, wbase, smem);
 }
 
 // One thread per TB: public descriptor -> expanded record (residual_core.cuh: expand_desc).

@@ -395,24 +395,35 @@ P265_HD int sf_matrix_id(int log2n, int c_idx, int flags) {
 // ------------------------------------------------------------------ expanded descriptors
 // Everything make_params derives from a public 16-byte descriptor is TB-uniform, but inside
 // the bin kernels every lane of every item would recompute it (~100 instructions per item).
-// expand_kernel does it once per TB, into a 16-byte record with the same positions for the
-// fields the pipeline code reads directly:
+// expand_kernel does it once per TB, into a 16-byte record whose fields the pipeline code uses
+// as they are:
 //   .x  element offset of the TB's top-left in the residual buffer
-//   .y  log2n | c_idx << 8 | matrixId << 16 | flags << 24       (qP byte -> matrixId)
+//   .y  flags | matrixId << 8 (3 bits; 6 = prescaled, no table) | (20 - BitDepth) << 11 (4 bits)
+//       | (plane stride / 8) << 15
 //   .z  coefficient arena offset, units of 16 coefficients       (unchanged)
 //   .w  w (16 bits: 16 * levelScale, levelScale with a table, 1 when prescaled) | sh << 16 | lsh << 24
+// (the TB size is the bin's; strides are multiples of 8 elements, checked by the launcher)
+P265_HD uint32_t xd_flags(const uint4 x) { return x.y & 0xff; }
+P265_HD uint32_t xd_mid(const uint4 x) { return (x.y >> 8) & 7; }
+P265_HD int xd_sh2(const uint4 x) { return (int)((x.y >> 11) & 15); }
+P265_HD int xd_stride(const uint4 x) { return (int)((x.y >> 15) << 3); }
+P265_HD int xd_w(const uint4 x) { return (int)(x.w & 0xffff); }
+P265_HD int xd_sh(const uint4 x) { return (int)((x.w >> 16) & 0xff); }
+P265_HD int xd_lsh(const uint4 x) { return (int)(x.w >> 24); }
+
 P265_HD uint4 expand_desc(const KernelArgs &a, const uint4 d) {
     const TbParams t = make_params(a, d, true);
     const int log2n = (int)(d.y & 0xff), c_idx = (int)((d.y >> 8) & 0xff);
     const uint32_t dst_off = (uint32_t)(t.dst - a.out);
-    // PRESCALED (identity dequantisation) is folded into w = 1, sh = lsh = 0 and "no table"
-    const int mid = sf_matrix_id(log2n, c_idx, t.flags);
-    const uint32_t flags = (uint32_t)t.flags;
-    return make_uint4(dst_off, (uint32_t)log2n | ((uint32_t)c_idx << 8) | ((uint32_t)mid << 16) | (flags << 24), d.z,
-                      (uint32_t)t.w | ((uint32_t)t.sh << 16) | ((uint32_t)t.lsh << 24));
+    // PRESCALED (identity dequantisation) is folded into w = 1, sh = lsh = 0 and "no table":
+    // matrixId 6, where the small-bin kernels keep an all-ones matrix
+    const int mid = (t.flags & P265_TU_PRESCALED) ? 6 : sf_matrix_id(log2n, c_idx, t.flags);
+    const uint32_t flags = (uint32_t)t.flags & 0xff;
+    return make_uint4(dst_off, flags | ((uint32_t)mid << 8) | ((uint32_t)t.sh2 << 11) | ((uint32_t)(t.stride >> 3) << 15),
+                      d.z, (uint32_t)t.w | ((uint32_t)t.sh << 16) | ((uint32_t)t.lsh << 24));
 }
 
-P265_HD TbParams params_from_x(const KernelArgs &a, const uint4 x, bool valid) {
+P265_HD TbParams params_from_x(const KernelArgs &a, const uint4 x, bool valid, int log2n) {
     TbParams t;
     t.valid = valid;
     if (!valid) {
@@ -420,21 +431,20 @@ P265_HD TbParams params_from_x(const KernelArgs &a, const uint4 x, bool valid) {
         t.lsh = 0; t.rnd2 = 0; t.sh2 = 0; t.flags = 0;
         return t;
     }
-    const int log2n = (int)(x.y & 0xff), c_idx = (int)((x.y >> 8) & 0xff), mid = (int)((x.y >> 16) & 0xff);
-    t.flags = (int)(x.y >> 24);
+    t.flags = (int)xd_flags(x);
     t.src = a.coeffs + (size_t)x.z * 16;
     t.dst = a.out + x.x;
-    t.stride = c_idx ? a.stride_c : a.stride_y;
-    t.w = (int)(x.w & 0xffff);
-    t.sh = (int)((x.w >> 16) & 0xff);
-    t.lsh = (int)(x.w >> 24);
+    t.stride = xd_stride(x);
+    t.w = xd_w(x);
+    t.sh = xd_sh(x);
+    t.lsh = xd_lsh(x);
     t.rnd = (1 << t.sh) >> 1;
-    t.sh2 = 20 - (c_idx ? a.bit_depth_c : a.bit_depth_y);
+    t.sh2 = xd_sh2(x);
     t.rnd2 = 1 << (t.sh2 - 1);
     t.sf = nullptr;
     if (a.sf && !(t.flags & P265_TU_PRESCALED)) {
         const int base = (int)((0x07e001e000600000ull >> (16 * (log2n - 2))) & 0xffff);
-        t.sf = a.sf + base + (mid << (2 * log2n));
+        t.sf = a.sf + base + ((int)xd_mid(x) << (2 * log2n));
     }
     return t;
 }
@@ -711,9 +721,10 @@ P265_HD void stage1_pair(const unsigned char *in, unsigned char *g, int x0, int 
 
 // ------------------------------------------------- stage 2: ONE row of one TB
 // Horizontal pass (8.6.4.2) over row `row` of g, final bdShift rounding (8.6.2), int16
-// saturation and the 2N-byte row store into the residual plane.
+// saturation: the row leaves as N/2 packed words.
 template <int LOG2N>
-P265_HD void stage2_row(const unsigned char *g, int row, int16_t *dst, int rnd2, int sh2, int dst_flag) {
+P265_HD void stage2_compute(const unsigned char *g, int row, int rnd2, int sh2, int dst_flag,
+                            uint32_t (&w)[(1 << LOG2N) / 2]) {
     using L = Layout<LOG2N>;
     constexpr int N = L::N;
     const unsigned char *grow = g + row * L::ROW_BYTES;
@@ -743,9 +754,17 @@ P265_HD void stage2_row(const unsigned char *g, int row, int16_t *dst, int rnd2,
     } else {
         Idct<N, 1>::run(p, rnd2, r);
     }
-    uint32_t w[N / 2];
     P265_UNROLL
     for (int i = 0; i < N / 2; i++) w[i] = (uint32_t)pack_sat(r[0][2 * i] >> sh2, r[0][2 * i + 1] >> sh2);
+}
+
+// ... and the 2N-byte row store straight into the residual plane (one lane = one row: a warp's
+// store instruction touches 32 different rows)
+template <int LOG2N>
+P265_HD void stage2_row(const unsigned char *g, int row, int16_t *dst, int rnd2, int sh2, int dst_flag) {
+    constexpr int N = 1 << LOG2N;
+    uint32_t w[N / 2];
+    stage2_compute<LOG2N>(g, row, rnd2, sh2, dst_flag, w);
     if (N >= 8) {
         P265_UNROLL
         for (int q = 0; q < N / 8; q++)
@@ -753,6 +772,46 @@ P265_HD void stage2_row(const unsigned char *g, int row, int16_t *dst, int rnd2,
     } else {
         *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
     }
+}
+
+// ... or back into the lane's own row of g (consumed by the loads above; same chunk swizzle), for
+// the coalesced copy-out below: the scattered form costs 32 LSU wavefronts per store instruction
+// (32 rows), measured as 16-20 % of the big-size bins.
+template <int LOG2N>
+P265_HD void stage2_row_g(unsigned char *g, int row, int rnd2, int sh2) {
+    using L = Layout<LOG2N>;
+    constexpr int N = L::N;
+    static_assert(N >= 16, "shared-memory sizes only");
+    uint32_t w[N / 2];
+    stage2_compute<LOG2N>(g, row, rnd2, sh2, 0, w);
+    unsigned char *grow = g + row * L::ROW_BYTES;
+    const int sw = L::swz(row);
+    P265_UNROLL
+    for (int q = 0; q < N / 8; q++)
+        *reinterpret_cast<uint4 *>(grow + ((q ^ sw) << 4)) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+}
+
+// Copy-out of a finished item: store instruction `i` of the warp moves 32 consecutive 16-byte
+// chunks of the item's result rows, i.e. 32 / (N/8) whole rows of one TB (8 rows of 64 bytes for
+// 32x32, 16 rows of 32 bytes for 16x16) instead of one chunk of 32 different rows.
+template <int LOG2N>
+struct OutMap {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int CPR = N / 8;                            // 16-byte chunks per row
+    static constexpr int RPI = 32 / CPR;                         // rows per store instruction
+    static constexpr int IPT = N / RPI;                          // store instructions per TB
+    static constexpr int ITERS = Layout<LOG2N>::TBS * IPT;       // per item
+    static P265_HD constexpr int tb(int i) { return i / IPT; }
+    static P265_HD int row(int i, int lane) { return (i % IPT) * RPI + lane / CPR; }
+    static P265_HD int part(int lane) { return lane % CPR; }
+};
+template <int LOG2N>
+P265_HD uint4 out_chunk_load(const unsigned char *g_base, int i, int lane) {
+    using L = Layout<LOG2N>;
+    using M = OutMap<LOG2N>;
+    const int row = M::row(i, lane);
+    return *reinterpret_cast<const uint4 *>(g_base + M::tb(i) * L::TB_BYTES + row * L::ROW_BYTES +
+                                            ((M::part(lane) ^ L::swz(row)) << 4));
 }
 
 // ======================================================================================
@@ -796,10 +855,12 @@ P265_HD void lane_special(const TbParams &t, const uint32_t *w, const uint8_t *s
 }
 
 // 4x4: `w` = the TB's 8 packed words (rows 0..3, two words per row)
+// `sf` = the TB's ScalingFactor matrix ([y][x] bytes) or nullptr: t.sf on the host, the CTA's
+// shared-memory copy on the device (small_sf_ptr below).
 template <int SF, bool SLOW>
-P265_HD void tb4_lane(const TbParams &t, const uint32_t (&w)[8]) {
+P265_HD void tb4_lane(const TbParams &t, const uint32_t (&w)[8], const uint8_t *sf) {
     if (!t.valid) return;
-    const uint8_t *sfm = (SF != SF_NONE) ? t.sf : nullptr;
+    const uint8_t *sfm = (SF != SF_NONE) ? sf : nullptr;
     if (t.flags & (P265_TU_SKIP | P265_TU_BYPASS)) {
         lane_special<4>(t, w, sfm);
         return;
@@ -852,9 +913,9 @@ P265_HD void tb4_lane(const TbParams &t, const uint32_t (&w)[8]) {
 P265_HD int tb8_chunk_off(int lane, int row) { return lane * 128 + ((row ^ (lane & 7)) << 4); }
 
 template <int SF, bool SLOW>
-P265_HD void tb8_lane(const TbParams &t, const unsigned char *tile, int lane) {
+P265_HD void tb8_lane(const TbParams &t, const unsigned char *tile, int lane, const uint8_t *sf) {
     if (!t.valid) return;
-    const uint8_t *sfm = (SF != SF_NONE) ? t.sf : nullptr;
+    const uint8_t *sfm = (SF != SF_NONE) ? sf : nullptr;
     if (t.flags & P265_TU_BYPASS) {
         uint32_t w[32];
         P265_UNROLL

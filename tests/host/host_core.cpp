@@ -24,7 +24,7 @@ static void run_item_sf(const KernelArgs &a, int item) {
         bool valid;
         int tb = lane_tb<LOG2N>(a, item, lane, valid);
         lane_tb_index[lane] = valid ? tb : 0;
-        t[lane] = params_from_x(a, valid ? expand_desc(a, load_desc(a, tb, true)) : make_uint4(0, 0, 0, 0), valid);
+        t[lane] = params_from_x(a, valid ? expand_desc(a, load_desc(a, tb, true)) : make_uint4(0, 0, 0, 0), valid, LOG2N);
         slow |= t[lane].lsh != 0;
         tile_issue<LOG2N>(lane, t[lane].src, valid, in_buf);
     }
@@ -57,13 +57,24 @@ static void run_item_sf(const KernelArgs &a, int item) {
     }
     for (int lane = 0; lane < 32; lane++) {
         const int tb_l = lane / L::TPB, tl = lane % L::TPB;
-        const unsigned char *g = g_buf + tb_l * L::TB_BYTES;
+        unsigned char *g = g_buf + tb_l * L::TB_BYTES;
         const TbParams &q = t[lane];
         if (!q.valid || (q.flags & (P265_TU_SKIP | P265_TU_BYPASS))) continue;
         for (int c = 0; c < 2; c++) {
             const int row = tl + c * L::TPB;
-            stage2_row<LOG2N>(g, row, q.dst + (size_t)row * q.stride, q.rnd2, q.sh2, q.flags & P265_TU_DST);
+            if constexpr (LOG2N >= 4) stage2_row_g<LOG2N>(g, row, q.rnd2, q.sh2);  // the kernel's path
+            else stage2_row<LOG2N>(g, row, q.dst + (size_t)row * q.stride, q.rnd2, q.sh2, q.flags & P265_TU_DST);
         }
+    }
+    if constexpr (LOG2N >= 4) {  // coalesced copy-out of the result rows (run_bin)
+        using M = OutMap<LOG2N>;
+        for (int i = 0; i < M::ITERS; i++)
+            for (int lane = 0; lane < 32; lane++) {
+                const TbParams &q = t[M::tb(i) * L::TPB];  // any lane of that TB
+                if (!q.valid || (q.flags & (P265_TU_SKIP | P265_TU_BYPASS))) continue;
+                const uint4 v = out_chunk_load<LOG2N>(g_buf, i, lane);
+                std::memcpy(q.dst + (size_t)M::row(i, lane) * q.stride + M::part(lane) * 8, &v, 16);
+            }
     }
 }
 
@@ -77,7 +88,7 @@ static void run_small_item(const KernelArgs &a, int bin, int item) {
     for (int lane = 0; lane < 32; lane++) {
         const int local = item * 32 + lane;
         const bool valid = local < a.n_tb[bin];
-        t[lane] = params_from_x(a, valid ? expand_desc(a, load_desc(a, a.first_tb[bin] + local, true)) : make_uint4(0, 0, 0, 0), valid);
+        t[lane] = params_from_x(a, valid ? expand_desc(a, load_desc(a, a.first_tb[bin] + local, true)) : make_uint4(0, 0, 0, 0), valid, 5 - bin);
         slow |= valid && t[lane].lsh != 0;
     }
     for (int lane = 0; lane < 32; lane++) {
@@ -85,13 +96,13 @@ static void run_small_item(const KernelArgs &a, int bin, int item) {
         if (!q.valid) continue;
         if (bin == 2) {
             for (int r = 0; r < 8; r++) copy16_async(tile + tb8_chunk_off(lane, r), q.src + r * 8);
-            if (slow) tb8_lane<SF, true>(q, tile, lane);
-            else tb8_lane<SF, false>(q, tile, lane);
+            if (slow) tb8_lane<SF, true>(q, tile, lane, q.sf);
+            else tb8_lane<SF, false>(q, tile, lane, q.sf);
         } else {
             uint32_t w[8];
             std::memcpy(w, q.src, 32);
-            if (slow) tb4_lane<SF, true>(q, w);
-            else tb4_lane<SF, false>(q, w);
+            if (slow) tb4_lane<SF, true>(q, w, q.sf);
+            else tb4_lane<SF, false>(q, w, q.sf);
         }
     }
 }

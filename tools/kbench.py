@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--tag", default="")
     ap.add_argument("--only", default="", help="comma list of sections: residual,sao,recon,deblock")
+    ap.add_argument("--quick", action="store_true", help="residual: the SF-replicated mix and the per-size runs with a table only")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     stream = torch.cuda.Stream(device=dev)
@@ -152,12 +153,15 @@ def bench_overlap(args, eng, dev, stream, to_dev):
 def bench_residual(args, time_residual):
     full = synth.residual_batch("4k10", n_pics=args.pics, n_unique=min(2, args.pics))
     time_residual(full, "4k10 mix, SF replicated")
-    time_residual(full, "4k10 mix, SF general", force_general=True)
-    flat = ResidualBatch(full.geom, full.tus, full.coeffs, None, covers_all=True)
-    time_residual(flat, "4k10 mix, flat lists")
+    if not args.quick:
+        time_residual(full, "4k10 mix, SF general", force_general=True)
+        flat = ResidualBatch(full.geom, full.tus, full.coeffs, None, covers_all=True)
+        time_residual(flat, "4k10 mix, flat lists")
     for l2 in (5, 4, 3, 2):
         sel = full.tus[full.tus["log2n"] == l2]
         for sf, name in ((full.scaling_factor, "SF repl"), (None, "flat")):
+            if args.quick and sf is None:
+                continue
             b = ResidualBatch(full.geom, np.ascontiguousarray(sel), full.coeffs, sf, covers_all=True)
             time_residual(b, "only %2dx%-2d (%7d TBs) %s" % (1 << l2, 1 << l2, len(sel), name))
 
