@@ -226,30 +226,39 @@ __device__ __forceinline__ void run_bin8(const KernelArgs &a, int gw, int stride
     const int n_tb = a.n_tb[2], first = a.first_tb[2];
     const int n_items = (n_tb + 31) >> 5;
     if (gw >= n_items) return;
-    uint4 *ring = reinterpret_cast<uint4 *>(wbase + 2 * kWarpSmemBytes) + lane;
-    auto issue = [&](const uint4 d, bool valid, unsigned char *tile) {
-        if (!valid) return;
-        const int16_t *src = a.coeffs + (size_t)d.z * 16;
+    uint4 *ring0 = reinterpret_cast<uint4 *>(wbase + 2 * kWarpSmemBytes);  // slot s, TB t at ring0[32 * s + t]
+    uint4 *ring = ring0 + lane;
+    // Cooperative tile copy: copy instruction i moves the 8 chunks (rows) of TBs 4i .. 4i+3, i.e. four
+    // whole 128-byte lines when the arena is dense, instead of one 16-byte chunk of 32 different TBs
+    // (32 LSU wavefronts per instruction).  The TB's arena offset comes from its ring entry.
+    auto issue = [&](int slot, int item, unsigned char *tile) {
+        const int n_here = n_tb - item * 32;
 #pragma unroll
-        for (int r = 0; r < 8; r++) copy16_async(tile + tb8_chunk_off(lane, r), src + r * 8);
+        for (int i = 0; i < 8; i++) {
+            const int t = (lane >> 3) + 4 * i;
+            if (t < n_here)
+                copy16_async(tile + tb8_chunk_off(t, lane & 7),
+                             a.coeffs + (size_t)ring0[32 * slot + t].z * 16 + (lane & 7) * 8);
+        }
     };
     bool valid = gw * 32 + lane < n_tb;
     {
         const uint4 d0 = SmallDesc<SF, 3>::load(a, first + gw * 32 + lane, valid);
         ring[0] = d0;
-        issue(d0, valid, wbase);
+        __syncwarp();
+        issue(0, gw, wbase);
         const int i1 = (gw + stride) * 32 + lane;
         if (gw + stride < n_items && i1 < n_tb) copy16_async(&ring[32], SmallDesc<SF, 3>::ptr(a, first + i1));
         cp_async_commit();
     }
     int k = 0;
     for (int it = gw; it < n_items; it += stride, k ^= 1) {
-        cp_async_wait<0>();  // own tile k and descriptor k+1 (lane-private: no warp sync needed)
+        cp_async_wait<0>();  // tile k and descriptor k+1 ...
+        __syncwarp();        // ... of every lane; all lanes are done with the other tile buffer
         valid = it * 32 + lane < n_tb;
         const uint4 d_cur = ring[32 * k];
         if (it + stride < n_items) {
-            const int i1 = (it + stride) * 32 + lane;
-            issue(ring[32 * (k ^ 1)], i1 < n_tb, wbase + (k ^ 1) * kWarpSmemBytes);
+            issue(k ^ 1, it + stride, wbase + (k ^ 1) * kWarpSmemBytes);
             const int i2 = (it + 2 * stride) * 32 + lane;
             if (it + 2 * stride < n_items && i2 < n_tb) copy16_async(&ring[32 * k], SmallDesc<SF, 3>::ptr(a, first + i2));
         }
