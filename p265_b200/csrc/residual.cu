@@ -110,6 +110,7 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
         if (gw + stride < n_items && tb1 < n_tb && tl == 0) copy16_async(&ring[RS], &xt[tb1]);
         cp_async_commit();
     }
+    const uint32_t out_row0 = (uint32_t)M::row(0, lane), out_part8 = (uint32_t)M::part(lane) * 8;
     int k = 0, k1 = 1, k2 = 2;  // ring slots of items it, it + stride, it + 2 * stride
     for (int it = gw; it < n_items; it += stride) {
         cp_async_wait<0>();  // tile k and descriptor k+1 have landed
@@ -124,10 +125,12 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
         const int w = valid ? xd_w(d) : 0, sh = xd_sh(d), lsh = valid ? xd_lsh(d) : 0;
         const int rnd = (1 << sh) >> 1;
         // SF_REPLICATED: stage 1 reads the CTA's compact copy of this TB's matrix (matrixId from the record)
+        // (always a valid shared-memory address -- no generic-pointer select: a lane without a TB runs
+        // with w = 0 into its own unused part of g; matrixId 6 = prescaled TB = the all-ones entry)
         const uint8_t *sf1 = nullptr;
-        if (SF != SF_NONE && valid && !(flags & P265_TU_PRESCALED))
-            sf1 = SF == SF_REPLICATED ? sfc + xd_mid(d) * kSfcStride
-                                      : a.sf + sf_matrix_offset(LOG2N, 0, 1) + (xd_mid(d) << (2 * LOG2N));
+        if (SF == SF_REPLICATED) sf1 = sfc + (valid ? xd_mid(d) : 0u) * kSfcStride;
+        else if (SF == SF_GENERAL && valid && !(flags & P265_TU_PRESCALED))
+            sf1 = a.sf + sf_matrix_offset(LOG2N, 0, 1) + (xd_mid(d) << (2 * LOG2N));
         // rare, warp-uniform: transform-skip / bypass TBs, left-shift dequantisation
         const bool is_special = (flags & (P265_TU_SKIP | P265_TU_BYPASS)) != 0;
         bool slow = false;
@@ -157,18 +160,19 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
             stage2_call<LOG2N>(g, tl, 1 << (sh2 - 1), sh2);
         }
         __syncwarp();  // every result row of the item sits in g
-        // copy-out: store instruction i = 32 / (N/8) whole rows of TB i / IPT
+        // copy-out: store instruction i = 32 / (N/8) whole rows of TB i / IPT (32-bit element offsets:
+        // the launcher keeps a batch's planes below 2^32 elements)
         const int n_here = n_tb - it * L::TBS;  // TBs of this item that exist (>= 1)
 #pragma unroll
         for (int t = 0; t < L::TBS; t++) {
-            const uint4 dt = ring0[RS * k + t];  // same record for every lane
-            const bool skip = t >= n_here || (xd_flags(dt) & (P265_TU_SKIP | P265_TU_BYPASS));
-            const size_t row_step = (size_t)xd_stride(dt);
-            int16_t *dst = a.out + dt.x + (size_t)M::row(t * M::IPT, lane) * row_step + M::part(lane) * 8;
+            const uint2 dt = *reinterpret_cast<const uint2 *>(&ring0[RS * k + t]);  // .x, .y: same for every lane
+            const bool skip = t >= n_here || (dt.y & (P265_TU_SKIP | P265_TU_BYPASS));
+            const uint32_t row_step = (dt.y >> 15) << 3;
+            const uint32_t e0 = dt.x + out_row0 * row_step + out_part8;
 #pragma unroll
             for (int j = 0; j < M::IPT; j++) {
                 const uint4 v = out_chunk_load<LOG2N>(g_base, t * M::IPT + j, lane);
-                if (!skip) *reinterpret_cast<uint4 *>(dst + (size_t)(j * M::RPI) * row_step) = v;
+                if (!skip) *reinterpret_cast<uint4 *>(a.out + (e0 + (uint32_t)(j * M::RPI) * row_step)) = v;
             }
         }
         const int kk = k; k = k1; k1 = k2; k2 = kk;
@@ -361,7 +365,7 @@ __device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride
 #ifndef P265_CTAS_BIN3
 #define P265_CTAS_BIN3 16
 #endif
-constexpr int kSfcBytes = 512;  // compact ScalingFactor copy at the start of a CTA's shared memory (6 x 80 B)
+constexpr int kSfcBytes = 640;  // compact ScalingFactor copy at the start of a CTA's shared memory (7 x 80 B)
 template <int BIN>
 struct BinCfg {
     static constexpr int ctas = BIN == 0 ? P265_CTAS_BIN0 : (BIN == 1 ? P265_CTAS_BIN1 : (BIN == 3 ? P265_CTAS_BIN3 : kCtasPerSm));
@@ -392,6 +396,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, BinCfg<BIN>::ctas) residual
     if (SF == SF_REPLICATED && BIN <= 1) {
         if (BIN == 0) build_sf_compact<5>(a.sf, smem, threadIdx.x, blockDim.x);
         else build_sf_compact<4>(a.sf, smem, threadIdx.x, blockDim.x);
+        for (int i = threadIdx.x; i < kSfcStride; i += blockDim.x) smem[6 * kSfcStride + i] = 1;  // matrixId 6: m = 1
         __syncthreads();  // the only block-wide barrier: once per persistent CTA
     }
     if (SF != SF_NONE && BIN >= 2) {
