@@ -413,8 +413,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, BinCfg<BIN>::ctas) residual
 // One thread per TB: public descriptor -> expanded record (residual_core.cuh: expand_desc).
 __global__ void __launch_bounds__(256) expand_kernel(const __grid_constant__ KernelArgs a, int n_tus, uint4 *out) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the first bin kernel may be scheduled early
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_tus) out[i] = expand_desc(a, load_desc(a, i, true));
+    // four records per thread, all four loads in flight before the first is used
+    const int i0 = blockIdx.x * (blockDim.x * 4) + threadIdx.x;
+    uint4 d[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int i = i0 + j * blockDim.x;
+        d[j] = i < n_tus ? load_desc(a, i, true) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int i = i0 + j * blockDim.x;
+        if (i < n_tus) out[i] = expand_desc(a, d[j]);
+    }
 }
 
 // ---- auxiliary, non-hot kernels ------------------------------------------------------
@@ -611,7 +622,7 @@ int launch_residual(p265_ctx *ctx, const p265_tu_desc *d_tus, const int32_t bin_
     }
     a.xtus = static_cast<const uint4 *>(ctx->xtus);
     if (n_tus) {
-        expand_kernel<<<(n_tus + 255) / 256, 256, 0, ctx->stream>>>(a, n_tus, static_cast<uint4 *>(ctx->xtus));
+        expand_kernel<<<(n_tus + 1023) / 1024, 256, 0, ctx->stream>>>(a, n_tus, static_cast<uint4 *>(ctx->xtus));
         P265_CUDA(cudaGetLastError());
         ctx->launches++;
     }
