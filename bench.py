@@ -540,7 +540,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pics", type=int, default=16, help="4K pictures per step per GPU")
     ap.add_argument("--e2e-pics", type=int, default=8)
-    ap.add_argument("--e2e-ctx", type=int, default=4)
+    ap.add_argument("--e2e-ctx", type=int, default=6)
     ap.add_argument("--e2e-steps", type=int, default=9)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

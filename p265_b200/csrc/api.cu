@@ -64,21 +64,32 @@ static int check_geom(const p265_pic_geom *g, int elem_align) {
 }
 
 // host-side validation of a descriptor list (host entry points only)
-static int check_tus(const p265_tu_desc *tus, const int32_t bin_counts[4], size_t n_coeffs, const p265_pic_geom *g) {
+static int check_tus(const p265_tu_desc *tus, const int32_t bin_counts[4], size_t n_coeffs, const p265_pic_geom *g,
+                     bool have_table) {
+    // one pass over caller data, on the latency path of every host call: plane limits and the qP
+    // bound are hoisted per component, the rare diagnostics are formatted only on failure
+    const int wmax[3] = {g->width, g->width / 2, g->width / 2}, hmax[3] = {g->height, g->height / 2, g->height / 2};
+    const int qmax[3] = {51 + 6 * (g->bit_depth_y - 8), 51 + 6 * (g->bit_depth_c - 8), 51 + 6 * (g->bit_depth_c - 8)};
     int64_t k = 0;
     for (int b = 0; b < 4; b++) {
         if (bin_counts[b] < 0) return set_error(P265_EINVAL, "negative bin count");
         const int log2n = 5 - b, n = 1 << log2n;
+        const unsigned bad_flags = (log2n != 2 ? (P265_TU_SKIP | P265_TU_DST) : 0u) | (have_table ? P265_TU_PRESCALED : 0u);
         for (int32_t i = 0; i < bin_counts[b]; i++, k++) {
             const p265_tu_desc &t = tus[k];
+            const unsigned c = t.c_idx < 3 ? t.c_idx : 0;
+            const bool ok = t.log2n == log2n && t.c_idx <= 2 && ((t.x | t.y) & (n - 1)) == 0 && t.x + n <= wmax[c] &&
+                            t.y + n <= hmax[c] && t.pic < g->n_pics &&
+                            (size_t)t.coeff_off * 16 + (size_t)n * n <= n_coeffs && !(t.flags & bad_flags) &&
+                            !((t.flags & P265_TU_DST) && t.c_idx != 0) && t.qp <= qmax[c];
+            if (ok) continue;
             if (t.log2n != log2n)
                 return set_error(P265_EINVAL, "descriptor %lld: log2n %d where bin expects %d (list must be sorted "
                                  "32,16,8,4)", (long long)k, t.log2n, log2n);
             if (t.c_idx > 2) return set_error(P265_EINVAL, "descriptor %lld: c_idx %d", (long long)k, t.c_idx);
-            const int w = t.c_idx ? g->width / 2 : g->width, h = t.c_idx ? g->height / 2 : g->height;
-            if (t.x % n || t.y % n || t.x + n > w || t.y + n > h)
+            if (t.x % n || t.y % n || t.x + n > wmax[c] || t.y + n > hmax[c])
                 return set_error(P265_EINVAL, "descriptor %lld: %dx%d block at (%d,%d) outside the %dx%d plane or "
-                                 "unaligned", (long long)k, n, n, t.x, t.y, w, h);
+                                 "unaligned", (long long)k, n, n, t.x, t.y, wmax[c], hmax[c]);
             if (t.pic >= g->n_pics) return set_error(P265_EINVAL, "descriptor %lld: picture %d", (long long)k, t.pic);
             if ((size_t)t.coeff_off * 16 + (size_t)n * n > n_coeffs)
                 return set_error(P265_EINVAL, "descriptor %lld: coefficients beyond the arena", (long long)k);
@@ -86,8 +97,9 @@ static int check_tus(const p265_tu_desc *tus, const int32_t bin_counts[4], size_
                 return set_error(P265_EINVAL, "descriptor %lld: transform_skip on a %dx%d block", (long long)k, n, n);
             if ((t.flags & P265_TU_DST) && (log2n != 2 || t.c_idx != 0))
                 return set_error(P265_EINVAL, "descriptor %lld: DST on a non-4x4-luma block", (long long)k);
-            if (t.qp > 51 + 6 * ((t.c_idx ? g->bit_depth_c : g->bit_depth_y) - 8))
-                return set_error(P265_EINVAL, "descriptor %lld: qP %d out of range", (long long)k, t.qp);
+            if (have_table && (t.flags & P265_TU_PRESCALED))
+                return set_error(P265_EINVAL, "descriptor %lld: PRESCALED needs scaling_factor == NULL", (long long)k);
+            return set_error(P265_EINVAL, "descriptor %lld: qP %d out of range", (long long)k, t.qp);
         }
     }
     return P265_OK;
@@ -208,11 +220,7 @@ int p265_residual_batch(p265_ctx *ctx, const p265_tu_desc *tus, const int32_t bi
     int64_t n = 0;
     for (int b = 0; b < 4; b++) n += bin_counts[b] > 0 ? bin_counts[b] : 0;
     if (n && (!tus || !coeffs)) return set_error(P265_EINVAL, "descriptor / coefficient pointer is NULL");
-    if ((rc = check_tus(tus, bin_counts, n_coeffs, geom))) return rc;
-    if (scaling_factor)
-        for (int64_t i = 0; i < n; i++)
-            if (tus[i].flags & P265_TU_PRESCALED)
-                return set_error(P265_EINVAL, "descriptor %lld: PRESCALED needs scaling_factor == NULL", (long long)i);
+    if ((rc = check_tus(tus, bin_counts, n_coeffs, geom, scaling_factor != nullptr))) return rc;
     P265_CUDA(cudaSetDevice(ctx->device));
     void *d_tus, *d_co, *d_sf = nullptr, *d_out;
     const size_t out_bytes = sizeof(int16_t) * (size_t)geom->pic_stride * geom->n_pics;

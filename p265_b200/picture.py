@@ -116,13 +116,20 @@ class ResidualBatch:
     covers_all: bool = False                # TBs tile every plane completely
     sf_replicated: bool | None = None       # None: detect from the table (see sf_is_replicated)
 
+    bins: tuple | None = None               # TBs per size bin (32,16,8,4); None: counted once, on first use
+
     def __post_init__(self):
         if self.scaling_factor is not None and self.sf_replicated is None:
             self.sf_replicated = sf_is_replicated(self.scaling_factor)
 
     def bin_counts(self):
-        l2 = self.tus["log2n"]
-        return tuple(int((l2 == k).sum()) for k in (5, 4, 3, 2))
+        """TBs per size bin (32, 16, 8, 4).  Part of the packed format: counted once per batch (the
+        packer knows it when it sorts) -- `tus` must not change afterwards; the C-ABI re-validates
+        the counts against the list on every call."""
+        if self.bins is None:
+            c = np.bincount(np.ascontiguousarray(self.tus["log2n"]), minlength=6)
+            self.bins = (int(c[5]), int(c[4]), int(c[3]), int(c[2]))
+        return self.bins
 
     def samples(self) -> int:
         return int((1 << (2 * self.tus["log2n"].astype(np.int64))).sum())
