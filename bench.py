@@ -141,9 +141,18 @@ def alg_int_ops(res):
 
 # ------------------------------------------------------------------ GPU arm
 def run_gpu(args):
-    # NCCL_DEBUG=VERSION / INFO make NCCL print to stdout; rank 0's stdout must hold the JSON line only
+    # NCCL prints its version banner (and NCCL_DEBUG output) to the C-level stdout; rank 0's stdout must
+    # hold the JSON line only: everything written to fd 1 before the final print goes to stderr
     if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
         os.environ["NCCL_DEBUG"] = "WARN"
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
     import torch
     import torch.distributed as dist
     from p265_b200.engine import Engine
@@ -401,7 +410,7 @@ def run_gpu(args):
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(single_core=True)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
