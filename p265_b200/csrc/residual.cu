@@ -15,16 +15,20 @@
 
 namespace p265 {
 
-// Occupancy plan (per SM): 11 CTAs x 2 warps = 22 warps, <= 93 registers/thread,
-// 11 x 18.5 KB = 204 KB of shared memory (tile + g + descriptor ring per warp).
+// Occupancy plan (per SM), 4 warps per CTA (one per scheduler; measured -1.8 % on the 32x32 bin
+// and -4 % on the 8x8 bin against 2-warp CTAs at the same warp counts):
+//   32x32  4 CTAs = 16 warps, 128 registers (lock-step two-column pass), 8.4 KB smem per warp
+//   16x16  8 CTAs = 32 warps,  64 registers
+//   8x8    6 CTAs = 24 warps,  80 registers
+//   4x4    8 CTAs = 32 warps,  64 registers
 #ifndef P265_WARPS_PER_CTA
-#define P265_WARPS_PER_CTA 2
+#define P265_WARPS_PER_CTA 4
 #endif
 #ifndef P265_CTAS_PER_SM
-#define P265_CTAS_PER_SM 11
+#define P265_CTAS_PER_SM 6
 #endif
 #ifndef P265_CTAS_BIN0
-#define P265_CTAS_BIN0 8   // 128 registers for the lock-step two-column / two-row passes (8.3 KB smem per warp)
+#define P265_CTAS_BIN0 4
 #endif
 constexpr int kWarpsPerCta = P265_WARPS_PER_CTA;
 constexpr int kCtasPerSm = P265_CTAS_PER_SM;
@@ -360,10 +364,10 @@ __device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride
 // 5.25 KB per warp and fits 64 registers; 8x8 keeps 64 packed words live per lane; 4x4 is
 // register-only.
 #ifndef P265_CTAS_BIN1
-#define P265_CTAS_BIN1 16
+#define P265_CTAS_BIN1 8
 #endif
 #ifndef P265_CTAS_BIN3
-#define P265_CTAS_BIN3 16
+#define P265_CTAS_BIN3 8
 #endif
 constexpr int kSfcBytes = 640;  // compact ScalingFactor copy at the start of a CTA's shared memory (7 x 80 B)
 template <int BIN>
