@@ -9,6 +9,7 @@
 // is no __syncthreads() in the kernel and CTAs are only a scheduling container.
 #include <cuda_runtime.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "internal.h"
 #include "residual_core.cuh"
@@ -592,12 +593,32 @@ template <int SF>
 static int launch_residual_sf(p265_ctx *ctx, const KernelArgs &a) {
     // the first kernel of the batch is ordered normally behind whatever precedes it on the
     // stream (zero fill, copies); the following bins may overlap their predecessor
-    int rc;
+    // the bins are independent, so their launch order is free (tuning knob P265_BIN_ORDER, e.g. "0312")
+    static int order[4] = {-1, 0, 0, 0};
+    if (order[0] < 0) {
+        const char *e = getenv("P265_BIN_ORDER");
+        int o[4] = {0, 1, 2, 3};
+        if (e && strlen(e) == 4) {
+            int seen = 0;
+            for (int i = 0; i < 4; i++) { o[i] = e[i] - '0'; if (o[i] >= 0 && o[i] < 4) seen |= 1 << o[i]; }
+            if (seen != 15) { o[0] = 0; o[1] = 1; o[2] = 2; o[3] = 3; }
+        }
+        order[1] = o[1]; order[2] = o[2]; order[3] = o[3]; order[0] = o[0];
+    }
+    int rc = P265_OK;
     bool first = true;
-    if (a.n_tb[0]) { if ((rc = launch_bin<0, SF>(ctx, a, first))) return rc; first = false; }
-    if (a.n_tb[1]) { if ((rc = launch_bin<1, SF>(ctx, a, first))) return rc; first = false; }
-    if (a.n_tb[2]) { if ((rc = launch_bin<2, SF>(ctx, a, first))) return rc; first = false; }
-    if (a.n_tb[3]) { if ((rc = launch_bin<3, SF>(ctx, a, first))) return rc; first = false; }
+    for (int i = 0; i < 4; i++) {
+        const int b = order[i];
+        if (!a.n_tb[b]) continue;
+        switch (b) {
+            case 0: rc = launch_bin<0, SF>(ctx, a, first); break;
+            case 1: rc = launch_bin<1, SF>(ctx, a, first); break;
+            case 2: rc = launch_bin<2, SF>(ctx, a, first); break;
+            default: rc = launch_bin<3, SF>(ctx, a, first); break;
+        }
+        if (rc) return rc;
+        first = false;
+    }
     return P265_OK;
 }
 
