@@ -13,7 +13,7 @@ ncu --set full --clock-control none --import-source on -k regex:'expand_kernel|r
 echo "full capture exit $?"
 KB="python tools/kbench.py --only deblock,recon --pics 8 --reps 3"
 $KB > $OUT/kb_plain_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'deblock_kernel|recon_kernel' -s 4 -c 2 -f -o $OUT/prof_other_$TAG $KB > $OUT/ncu_other_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'deblock_kernel|recon_kernel' -c 12 -f -o $OUT/prof_other_$TAG $KB > $OUT/ncu_other_$TAG.log 2>&1
 echo "other kernels capture exit $?"
 python bench.py --steps 20 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc $?"
 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_${TAG}_reference.json 2> $OUT/bench_${TAG}_reference.err; echo "ref rc $?"

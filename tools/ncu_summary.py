@@ -18,12 +18,11 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__t_sector_hit_rate.pct",
         "lts__t_sector_hit_rate.pct", "smsp__warps_eligible.avg.per_cycle_active",
         "local_load_requests", "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum"]
-seen = set()
+last = {}  # the last captured instance of every kernel (warm), in order of first appearance
 for r in rows[2:]:
-    name = r[idx["Kernel Name"]]
-    if name in seen:
-        continue
-    seen.add(name)
+    if len(r) > idx["Kernel Name"]:
+        last[r[idx["Kernel Name"]]] = r
+for name, r in last.items():
     print("=====", name[:80])
     for k in KEYS:
         if k in idx:
