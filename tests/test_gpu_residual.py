@@ -153,6 +153,38 @@ def test_bad_arguments_raise(engine):
         engine.residual(ResidualBatch(geom, tus, np.zeros(64, np.int16)))
 
 
+def test_descriptor_validation_cases(engine):
+    """One-pass check of caller data at the C-ABI (api.cu: check_tus): every rule, first offender named."""
+    geom = PicGeom(64, 64, 1, 8, 8)
+    co = np.zeros(4096, np.int16)
+
+    def one(**kw):
+        t = np.zeros(1, TU_DESC)
+        t["log2n"] = 2
+        for k, v in kw.items():
+            t[k] = v
+        return t
+
+    from p265_b200.residual_api import TU_PRESCALED
+    bad = [one(c_idx=3), one(x=2), one(pic=1), one(log2n=3, flags=TU_SKIP), one(c_idx=1, flags=TU_DST),
+           one(log2n=4, flags=TU_DST), one(qp=52), one(c_idx=1, x=32), one(log2n=5, y=48)]
+    for t in bad:
+        with pytest.raises(ValueError):
+            engine.residual(ResidualBatch(geom, t, co))
+    from p265_b200.scaling_list import default_scaling_factor
+    sf = pack_scaling_factor(default_scaling_factor())
+    with pytest.raises(ValueError):      # PRESCALED descriptors cannot be combined with a table
+        engine.residual(ResidualBatch(geom, one(flags=TU_PRESCALED), co, scaling_factor=sf))
+    # bin counts are caller data too: counts that do not match the list are rejected, never trusted
+    t = np.zeros(3, TU_DESC)
+    t["log2n"] = (3, 2, 2)
+    t["x"] = (0, 8, 12)
+    with pytest.raises(ValueError):
+        engine.residual(ResidualBatch(geom, t, co, bins=(0, 0, 2, 1)))
+    assert ResidualBatch(geom, t, co).bin_counts() == (0, 0, 1, 2)
+    engine.residual(ResidualBatch(geom, t, co, bins=(0, 0, 1, 2)))
+
+
 def test_dequant_matches_reference_outputs(engine, sanity_batch):
     """scaling.inverse_scaling: GPU d[] == the reference's own outputs on sanity.bin."""
     import os

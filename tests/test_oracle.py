@@ -324,3 +324,14 @@ def test_reconstruct_pinned_by_reference_function():
                                    reconstructed_samples=np.zeros((n, n), np.int64))
         ns.reconstruction.reconstruction(pu=pu, x0=0, y0=0, log2size=3)
         assert np.array_equal(pu.reconstructed_samples, so.reconstruct(pred, res, bd))
+
+
+def test_residual_batch_bin_counts_are_counted_once():
+    """bin counts are part of the packed batch (picture.ResidualBatch): counted on first use, then reused;
+    explicit counts (the packer's) are taken as they are -- the C-ABI validates them against the list."""
+    from p265_b200.picture import TU_DESC, PicGeom, ResidualBatch
+    t = np.zeros(7, TU_DESC)
+    t["log2n"] = (5, 4, 4, 3, 2, 2, 2)
+    b = ResidualBatch(PicGeom(64, 64, 1, 8, 8), t, np.zeros(16, np.int16))
+    assert b.bins is None and b.bin_counts() == (1, 2, 1, 3) and b.bins == (1, 2, 1, 3)
+    assert ResidualBatch(PicGeom(64, 64, 1, 8, 8), t, np.zeros(16, np.int16), bins=(1, 2, 1, 3)).bin_counts() == (1, 2, 1, 3)
