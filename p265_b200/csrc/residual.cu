@@ -115,7 +115,7 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
         if (gw + stride < n_items && tb1 < n_tb && tl == 0) copy16_async(&ring[RS], &xt[tb1]);
         cp_async_commit();
     }
-    const uint32_t out_row0 = (uint32_t)M::row(0, lane), out_part8 = (uint32_t)M::part(lane) * 8;
+    const uint32_t out_row0 = (uint32_t)M::row0(lane), out_part8 = (uint32_t)M::part(lane) * 8;
     int k = 0, k1 = 1, k2 = 2;  // ring slots of items it, it + stride, it + 2 * stride
     for (int it = gw; it < n_items; it += stride) {
         cp_async_wait<0>();  // tile k and descriptor k+1 have landed
@@ -165,20 +165,14 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
             stage2_call<LOG2N>(g, tl, 1 << (sh2 - 1), sh2);
         }
         __syncwarp();  // every result row of the item sits in g
-        // copy-out: store instruction i = 32 / (N/8) whole rows of TB i / IPT (32-bit element offsets:
-        // the launcher keeps a batch's planes below 2^32 elements)
-        const int n_here = n_tb - it * L::TBS;  // TBs of this item that exist (>= 1)
+        // copy-out: store instruction i = rows 4i .. 4i+3 of every TB of the item; the lane stays
+        // inside its own TB (32-bit element offsets: the launcher keeps a batch below 2^32 elements)
+        if (valid && !is_special) {
+            const uint32_t row_step = (uint32_t)xd_stride(d);
+            const uint32_t e0 = d.x + out_row0 * row_step + out_part8;
 #pragma unroll
-        for (int t = 0; t < L::TBS; t++) {
-            const uint2 dt = *reinterpret_cast<const uint2 *>(&ring0[RS * k + t]);  // .x, .y: same for every lane
-            const bool skip = t >= n_here || (dt.y & (P265_TU_SKIP | P265_TU_BYPASS));
-            const uint32_t row_step = (dt.y >> 15) << 3;
-            const uint32_t e0 = dt.x + out_row0 * row_step + out_part8;
-#pragma unroll
-            for (int j = 0; j < M::IPT; j++) {
-                const uint4 v = out_chunk_load<LOG2N>(g_base, t * M::IPT + j, lane);
-                if (!skip) *reinterpret_cast<uint4 *>(a.out + (e0 + (uint32_t)(j * M::RPI) * row_step)) = v;
-            }
+            for (int i = 0; i < M::ITERS; i++)
+                *reinterpret_cast<uint4 *>(a.out + (e0 + (uint32_t)(i * M::RPI) * row_step)) = out_chunk_load<LOG2N>(g, i, lane);
         }
         const int kk = k; k = k1; k1 = k2; k2 = kk;
     }

@@ -791,27 +791,27 @@ P265_HD void stage2_row_g(unsigned char *g, int row, int rnd2, int sh2) {
         *reinterpret_cast<uint4 *>(grow + ((q ^ sw) << 4)) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
 }
 
-// Copy-out of a finished item: store instruction `i` of the warp moves 32 consecutive 16-byte
-// chunks of the item's result rows, i.e. 32 / (N/8) whole rows of one TB (8 rows of 64 bytes for
-// 32x32, 16 rows of 32 bytes for 16x16) instead of one chunk of 32 different rows.
+// Copy-out of a finished item: store instruction `i` of the warp moves rows 4i .. 4i+3 of EVERY TB of
+// the item -- whole rows (64 bytes for 32x32, 32 bytes for 16x16) instead of one 16-byte chunk of 32
+// different rows -- and a lane only ever touches the TB it also computes (lane / TPB), so it needs
+// no other TB's record: destination = its own row pointer advanced by four rows per instruction.
 template <int LOG2N>
 struct OutMap {
     static constexpr int N = 1 << LOG2N;
     static constexpr int CPR = N / 8;                            // 16-byte chunks per row
-    static constexpr int RPI = 32 / CPR;                         // rows per store instruction
-    static constexpr int IPT = N / RPI;                          // store instructions per TB
-    static constexpr int ITERS = Layout<LOG2N>::TBS * IPT;       // per item
-    static P265_HD constexpr int tb(int i) { return i / IPT; }
-    static P265_HD int row(int i, int lane) { return (i % IPT) * RPI + lane / CPR; }
+    static constexpr int TPB = Layout<LOG2N>::TPB;               // lanes per TB
+    static constexpr int RPI = TPB / CPR;                        // rows per TB and store instruction (4)
+    static constexpr int ITERS = N / RPI;                        // store instructions per item
+    static P265_HD int row0(int lane) { return (lane % TPB) / CPR; }   // row inside instruction 0
     static P265_HD int part(int lane) { return lane % CPR; }
 };
+// chunk of the lane in store instruction i, read from the lane's own TB buffer `g`
 template <int LOG2N>
-P265_HD uint4 out_chunk_load(const unsigned char *g_base, int i, int lane) {
+P265_HD uint4 out_chunk_load(const unsigned char *g, int i, int lane) {
     using L = Layout<LOG2N>;
     using M = OutMap<LOG2N>;
-    const int row = M::row(i, lane);
-    return *reinterpret_cast<const uint4 *>(g_base + M::tb(i) * L::TB_BYTES + row * L::ROW_BYTES +
-                                            ((M::part(lane) ^ L::swz(row)) << 4));
+    const int row = i * M::RPI + M::row0(lane);
+    return *reinterpret_cast<const uint4 *>(g + row * L::ROW_BYTES + ((M::part(lane) ^ L::swz(row)) << 4));
 }
 
 // ======================================================================================

@@ -70,10 +70,10 @@ static void run_item_sf(const KernelArgs &a, int item) {
         using M = OutMap<LOG2N>;
         for (int i = 0; i < M::ITERS; i++)
             for (int lane = 0; lane < 32; lane++) {
-                const TbParams &q = t[M::tb(i) * L::TPB];  // any lane of that TB
+                const TbParams &q = t[lane];
                 if (!q.valid || (q.flags & (P265_TU_SKIP | P265_TU_BYPASS))) continue;
-                const uint4 v = out_chunk_load<LOG2N>(g_buf, i, lane);
-                std::memcpy(q.dst + (size_t)M::row(i, lane) * q.stride + M::part(lane) * 8, &v, 16);
+                const uint4 v = out_chunk_load<LOG2N>(g_buf + (lane / L::TPB) * L::TB_BYTES, i, lane);
+                std::memcpy(q.dst + (size_t)(i * M::RPI + M::row0(lane)) * q.stride + M::part(lane) * 8, &v, 16);
             }
     }
 }
