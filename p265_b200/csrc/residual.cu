@@ -47,27 +47,28 @@ __device__ __forceinline__ void cp_async_wait() {
 // by the two columns / rows a lane owns.  Inside a loop ptxas would hoist the ~90 packed
 // basis constants of the 32-point butterfly and need > 180 registers; as functions each
 // pass keeps a small allocation and fetches its constants just in time (LDCU).
-template <int LOG2N, int SF, bool SLOW>
-__device__ __noinline__ void stage1_call(const unsigned char *in, unsigned char *g, int x, int tl, int half,
-                                         const uint8_t *sf, int w, int rnd, int sh, int lsh, int dst_flag) {
-    stage1_column<LOG2N, SF, SLOW>(in, g, x, tl, half, sf, w, rnd, sh, lsh, dst_flag);
+// The hot wrappers take 32-bit SHARED-WINDOW addresses for the warp's buffers (and for the compact
+// ScalingFactor entry): a generic pointer costs a 64-bit argument plus the window-base arithmetic
+// (S2R / ULEA) on both sides of every call.
+__device__ __forceinline__ unsigned char *smem_ptr(uint32_t s) {
+    return static_cast<unsigned char *>(__cvta_shared_to_generic(s));
 }
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// sf: SF_REPLICATED -> shared address of the TB's compact matrix; SF_GENERAL -> global pointer; SF_NONE -> unused
 template <int LOG2N, int SF, bool SLOW>
-__device__ __noinline__ void stage1_pair_call(const unsigned char *in, unsigned char *g, int x0, int x1, int tl,
-                                              const uint8_t *sf, int w, int rnd, int sh, int lsh) {
-    stage1_pair<LOG2N, SF, SLOW>(in, g, x0, x1, tl, sf, w, rnd, sh, lsh);
+__device__ __noinline__ void stage1_pair_call(uint32_t in_s, uint32_t g_s, int x0, int x1, int tl, uint64_t sf, int w,
+                                              int rnd, int sh, int lsh) {
+    const uint8_t *sfp = SF == SF_REPLICATED ? smem_ptr((uint32_t)sf)
+                                             : reinterpret_cast<const uint8_t *>(static_cast<uintptr_t>(sf));
+    stage1_pair<LOG2N, SF, SLOW>(smem_ptr(in_s), smem_ptr(g_s), x0, x1, tl, sfp, w, rnd, sh, lsh);
 }
-#ifndef P265_PAIR16
-#define P265_PAIR16 1  // 16x16: both columns of a lane in lock step (stage1_pair): -6 % on that bin
-#endif
-#ifndef P265_PAIR32
-#define P265_PAIR32 1  // 32x32: lock-step form at 128 registers / 8 CTAs per SM: -10 % on that bin (12..16
-#endif                 // warps perform alike: the bin is bound by per-warp ILP, not by occupancy)
-// (the same lock-step form for the two rows of stage 2 was measured too: no gain on 32x32, -3 % on 16x16)
+// Stage 1 runs both columns of a lane in lock step (stage1_pair: -6 % on the 16x16 bin, -10 % on the
+// 32x32 bin at 128 registers); the same form for the two rows of stage 2 was measured twice: no gain.
 // Both rows of a lane in one call, one after the other (not unrolled: one copy of the pass).  The
 // result rows go back into g (stage2_row_g) and leave through the coalesced copy-out of run_bin.
 template <int LOG2N>
-__device__ __noinline__ void stage2_call(unsigned char *g, int row, int rnd2, int sh2) {
+__device__ __noinline__ void stage2_call(uint32_t g_s, int row, int rnd2, int sh2) {
+    unsigned char *g = smem_ptr(g_s);
 #pragma unroll 1
     for (int r = 0; r < 2; r++) {
         stage2_row_g<LOG2N>(g, row, rnd2, sh2);
@@ -103,6 +104,7 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
     uint4 *ring = ring0 + tb_l;  // the lane's own TB
     const unsigned char *in = in_base + tb_l * L::TB_BYTES;
     unsigned char *g = g_base + tb_l * L::TB_BYTES;
+    const uint32_t in_s = smem_addr(in), g_s = smem_addr(g), sfc_s = smem_addr(sfc);
     const int x0 = slot_index_rt(N, tl, 0), x1 = slot_index_rt(N, tl, 1);
     constexpr int kLines = N * N * 2 / 128;  // 128-byte lines per TB (<= lanes per TB)
     {   // prologue: first descriptor by plain load, its tile and the second descriptor async
@@ -132,10 +134,10 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
         // SF_REPLICATED: stage 1 reads the CTA's compact copy of this TB's matrix (matrixId from the record)
         // (always a valid shared-memory address -- no generic-pointer select: a lane without a TB runs
         // with w = 0 into its own unused part of g; matrixId 6 = prescaled TB = the all-ones entry)
-        const uint8_t *sf1 = nullptr;
-        if (SF == SF_REPLICATED) sf1 = sfc + (valid ? xd_mid(d) : 0u) * kSfcStride;
+        uint64_t sf1 = 0;
+        if (SF == SF_REPLICATED) sf1 = sfc_s + (valid ? xd_mid(d) : 0u) * kSfcStride;
         else if (SF == SF_GENERAL && valid && !(flags & P265_TU_PRESCALED))
-            sf1 = a.sf + sf_matrix_offset(LOG2N, 0, 1) + (xd_mid(d) << (2 * LOG2N));
+            sf1 = reinterpret_cast<uintptr_t>(a.sf + sf_matrix_offset(LOG2N, 0, 1) + (xd_mid(d) << (2 * LOG2N)));
         // rare, warp-uniform: transform-skip / bypass TBs, left-shift dequantisation
         const bool is_special = (flags & (P265_TU_SKIP | P265_TU_BYPASS)) != 0;
         bool slow = false;
@@ -143,16 +145,8 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
             slow = __any_sync(0xffffffffu, lsh != 0);
             if (__any_sync(0xffffffffu, is_special)) phase_special<LOG2N>(lane, params_from_x(a, d, valid, LOG2N), in_base);
         }
-        if ((P265_PAIR16 && LOG2N == 4) || (P265_PAIR32 && LOG2N == 5)) {
-            if (!slow) stage1_pair_call<LOG2N, SF, false>(in, g, x0, x1, tl, sf1, w, rnd, sh, 0);
-            else stage1_pair_call<LOG2N, SF, true>(in, g, x0, x1, tl, sf1, w, rnd, sh, lsh);
-        } else if (!slow) {
-            stage1_call<LOG2N, SF, false>(in, g, x0, tl, 0, sf1, w, rnd, sh, 0, 0);
-            stage1_call<LOG2N, SF, false>(in, g, x1, tl, 1, sf1, w, rnd, sh, 0, 0);
-        } else {  // rare
-            stage1_call<LOG2N, SF, true>(in, g, x0, tl, 0, sf1, w, rnd, sh, lsh, 0);
-            stage1_call<LOG2N, SF, true>(in, g, x1, tl, 1, sf1, w, rnd, sh, lsh, 0);
-        }
+        if (!slow) stage1_pair_call<LOG2N, SF, false>(in_s, g_s, x0, x1, tl, sf1, w, rnd, sh, 0);
+        else stage1_pair_call<LOG2N, SF, true>(in_s, g_s, x0, x1, tl, sf1, w, rnd, sh, lsh);  // rare
         __syncwarp();  // `in` is consumed, g is complete
         if (more) {
             tile_issue<LOG2N>(lane, a.coeffs + (size_t)ring[RS * k1].z * 16, v1, in_base);
@@ -162,7 +156,7 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
         cp_async_commit();
         if (valid && !is_special) {
             const int sh2 = xd_sh2(d);
-            stage2_call<LOG2N>(g, tl, 1 << (sh2 - 1), sh2);
+            stage2_call<LOG2N>(g_s, tl, 1 << (sh2 - 1), sh2);
         }
         __syncwarp();  // every result row of the item sits in g
         // copy-out: store instruction i = rows 4i .. 4i+3 of every TB of the item; the lane stays
