@@ -208,10 +208,10 @@ __device__ __forceinline__ const uint8_t *small_sf_ptr(const uint8_t *sfs, const
 }
 
 template <int SF, bool SLOW>
-__device__ __noinline__ void tb8_call(const KernelArgs &a, const uint4 d, bool valid, const unsigned char *tile,
-                                      int lane, const uint8_t *sfs) {
+__device__ __noinline__ void tb8_call(const KernelArgs &a, const uint4 d, bool valid, uint32_t tile_s, int lane,
+                                      uint32_t sfs_s) {  // shared-window addresses, like the big-bin wrappers
     const TbParams t = SmallDesc<SF, 3>::params(a, d, valid);
-    tb8_lane<SF, SLOW>(t, tile, lane, small_sf_ptr<SF, 3>(sfs, d));
+    tb8_lane<SF, SLOW>(t, smem_ptr(tile_s), lane, small_sf_ptr<SF, 3>(smem_ptr(sfs_s), d));
 }
 
 // 8x8 bin: 32 TBs per item; the lane's 128-byte TB is copied asynchronously into a
@@ -223,6 +223,7 @@ __device__ __forceinline__ void run_bin8(const KernelArgs &a, int gw, int stride
     const int n_tb = a.n_tb[2], first = a.first_tb[2];
     const int n_items = (n_tb + 31) >> 5;
     if (gw >= n_items) return;
+    const uint32_t wbase_s = smem_addr(wbase), sfs_s = smem_addr(sfs);
     uint4 *ring0 = reinterpret_cast<uint4 *>(wbase + 2 * kWarpSmemBytes);  // slot s, TB t at ring0[32 * s + t]
     uint4 *ring = ring0 + lane;
     // Cooperative tile copy: copy instruction i moves the 8 chunks (rows) of TBs 4i .. 4i+3, i.e. four
@@ -270,8 +271,8 @@ __device__ __forceinline__ void run_bin8(const KernelArgs &a, int gw, int stride
             slow_lane = ((qp * 43) >> 8) >= (c_idx ? a.bit_depth_c : a.bit_depth_y) - 2;
         }
         const bool slow = __any_sync(0xffffffffu, valid && slow_lane);
-        if (slow) tb8_call<SF, true>(a, d_cur, valid, wbase + k * kWarpSmemBytes, lane, sfs);
-        else tb8_call<SF, false>(a, d_cur, valid, wbase + k * kWarpSmemBytes, lane, sfs);
+        if (slow) tb8_call<SF, true>(a, d_cur, valid, wbase_s + k * kWarpSmemBytes, lane, sfs_s);
+        else tb8_call<SF, false>(a, d_cur, valid, wbase_s + k * kWarpSmemBytes, lane, sfs_s);
     }
     cp_async_wait<0>();
 }

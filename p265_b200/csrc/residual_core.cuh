@@ -342,7 +342,8 @@ P265_HD TbParams make_params(const KernelArgs &a, const uint4 d, bool valid) {
     TbParams t;
     t.valid = valid;
     if (!valid) {
-        t.src = nullptr; t.dst = nullptr; t.sf = nullptr; t.stride = 0; t.w = 0; t.rnd = 0; t.sh = 0;
+        t.src = a.coeffs; t.dst = a.out; t.sf = nullptr;  // never dereferenced; not nullptr so that the address space stays known
+        t.stride = 0; t.w = 0; t.rnd = 0; t.sh = 0;
         t.lsh = 0; t.rnd2 = 0; t.sh2 = 0; t.flags = 0;
         return t;
     }
@@ -427,7 +428,8 @@ P265_HD TbParams params_from_x(const KernelArgs &a, const uint4 x, bool valid, i
     TbParams t;
     t.valid = valid;
     if (!valid) {
-        t.src = nullptr; t.dst = nullptr; t.sf = nullptr; t.stride = 0; t.w = 0; t.rnd = 0; t.sh = 0;
+        t.src = a.coeffs; t.dst = a.out; t.sf = nullptr;  // never dereferenced; not nullptr so that the address space stays known
+        t.stride = 0; t.w = 0; t.rnd = 0; t.sh = 0;
         t.lsh = 0; t.rnd2 = 0; t.sh2 = 0; t.flags = 0;
         return t;
     }
