@@ -339,6 +339,22 @@ __global__ void __launch_bounds__(kDbkThreads, PACKED ? P265_DBK_CTAS : 1) deblo
     const int x0 = 8 * i - 4, y0 = 8 * j - 4;
     const bool has_l = i > 0, has_r = 8 * i < w;
 
+    // ---- packed path: the block's 16 loads go out before the segment set-up, which needs two
+    // more dependent global reads (CTB parameters, tC') and ~400 instructions: their latency
+    // hides behind that work instead of being waited for afterwards.
+    // W[r][k]: row r, samples (2k, 2k+1) of the shifted block
+    uint32_t W[8][4];
+    if constexpr (PACKED) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int y = y0 + r;
+            const bool row_ok = y >= 0 && y < h;
+            W[r][0] = W[r][1] = W[r][2] = W[r][3] = 0u;
+            if (row_ok && has_l) loadw<T>(base + (size_t)y * stride + x0, W[r][0], W[r][1]);
+            if (row_ok && has_r) loadw<T>(base + (size_t)y * stride + x0 + 4, W[r][2], W[r][3]);
+        }
+    }
+
     // ---- per-segment parameters ----------------------------------------------------------
     const uint32_t *cp = reinterpret_cast<const uint32_t *>(a.ctb) + (size_t)pic * a.ctbs_w * a.ctbs_h;
     auto ctb_of = [&](int bi, int bj) {
@@ -361,16 +377,6 @@ __global__ void __launch_bounds__(kDbkThreads, PACKED ? P265_DBK_CTAS : 1) deblo
 
     if constexpr (PACKED) {
         const uint32_t maxv2 = rep2(maxv);
-        // W[r][k]: row r, samples (2k, 2k+1) of the shifted block
-        uint32_t W[8][4];
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const int y = y0 + r;
-            const bool row_ok = y >= 0 && y < h;
-            W[r][0] = W[r][1] = W[r][2] = W[r][3] = 0u;
-            if (row_ok && has_l) loadw<T>(base + (size_t)y * stride + x0, W[r][0], W[r][1]);
-            if (row_ok && has_r) loadw<T>(base + (size_t)y * stride + x0 + 4, W[r][2], W[r][3]);
-        }
         // ---- vertical edge: pair rows (2rp, 2rp+1) -> X[col][rp], filter, transpose back -------
         if (sv[0].bs | sv[1].bs) {
             uint32_t X[8][4];

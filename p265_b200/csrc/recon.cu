@@ -30,37 +30,59 @@ __device__ __forceinline__ uint32_t prmt_r(uint32_t a, uint32_t b, uint32_t sel)
     return d;
 }
 
-// grid = (row chunks, 3 planes, pictures); a thread handles 8 consecutive samples of a row
+// grid = (vector chunks, 3 planes, pictures); a vector = 8 consecutive samples of a row.  A
+// thread handles kReconVecs vectors one CTA width apart (every warp access stays a run of
+// whole 128-byte lines) and issues all of its loads before the first use: the kernel is
+// latency-bound, so the bytes in flight per thread are what matters.
+constexpr int kReconThreads = 256;
+constexpr int kReconVecs = 4;
+
 template <typename T>
-__global__ void __launch_bounds__(256) recon_kernel(const __grid_constant__ ReconArgs a) {
+__global__ void __launch_bounds__(kReconThreads) recon_kernel(const __grid_constant__ ReconArgs a) {
     const int c = blockIdx.y, pic = blockIdx.z;
     const int w = c ? a.width >> 1 : a.width, h = c ? a.height >> 1 : a.height;
     const int stride = c ? a.stride_c : a.stride_y;
     const int bd = c ? a.bit_depth_c : a.bit_depth_y;
-    const int vec_per_row = (w + 7) >> 3;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)vec_per_row * h) return;
-    const int y = (int)(idx / vec_per_row), xv = (int)(idx - (int64_t)y * vec_per_row);
-    const int64_t off = (int64_t)pic * a.pic_stride + a.plane_off[c] + (int64_t)y * stride + xv * 8;
+    const uint32_t vec_per_row = (uint32_t)(w + 7) >> 3;
+    const uint32_t total = vec_per_row * (uint32_t)h;
+    const uint32_t first = blockIdx.x * (uint32_t)(kReconThreads * kReconVecs) + threadIdx.x;
+    if (first >= total) return;
+    const int64_t base = (int64_t)pic * a.pic_stride + a.plane_off[c];
     const uint32_t maxv2 = ((1u << bd) - 1u) * 0x00010001u;
     const uint32_t negmax2 = (0x10000u - ((1u << bd) - 1u)) * 0x00010001u;  // -maxVal in both halves
-    const uint4 r = *reinterpret_cast<const uint4 *>(a.res + off);
-    uint32_t p[4];
-    if (sizeof(T) == 2) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(a.pred) + off);
-        p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
-    } else {
-        const uint2 v = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(a.pred) + off);
-        p[0] = prmt_r(v.x, 0, 0x4140); p[1] = prmt_r(v.x, 0, 0x4342);
-        p[2] = prmt_r(v.y, 0, 0x4140); p[3] = prmt_r(v.y, 0, 0x4342);
+    int64_t off[kReconVecs];
+    bool ok[kReconVecs];
+    uint4 r[kReconVecs], v[kReconVecs];
+#pragma unroll
+    for (int k = 0; k < kReconVecs; k++) {
+        const uint32_t idx = first + (uint32_t)(k * kReconThreads);
+        ok[k] = idx < total;
+        const uint32_t y = idx / vec_per_row, xv = idx - y * vec_per_row;
+        off[k] = base + (int64_t)y * stride + xv * 8;
     }
-    const uint32_t o0 = recon_word(p[0], r.x, maxv2, negmax2), o1 = recon_word(p[1], r.y, maxv2, negmax2);
-    const uint32_t o2 = recon_word(p[2], r.z, maxv2, negmax2), o3 = recon_word(p[3], r.w, maxv2, negmax2);
-    if (sizeof(T) == 2)
-        *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(a.rec) + off) = make_uint4(o0, o1, o2, o3);
-    else
-        *reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(a.rec) + off) =
-            make_uint2(prmt_r(o0, o1, 0x6420), prmt_r(o2, o3, 0x6420));
+#pragma unroll
+    for (int k = 0; k < kReconVecs; k++) {
+        if (!ok[k]) continue;
+        r[k] = *reinterpret_cast<const uint4 *>(a.res + off[k]);
+        if (sizeof(T) == 2) {
+            v[k] = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(a.pred) + off[k]);
+        } else {
+            const uint2 t = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(a.pred) + off[k]);
+            v[k] = make_uint4(prmt_r(t.x, 0, 0x4140), prmt_r(t.x, 0, 0x4342), prmt_r(t.y, 0, 0x4140),
+                              prmt_r(t.y, 0, 0x4342));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kReconVecs; k++) {
+        if (!ok[k]) continue;
+        const uint32_t o0 = recon_word(v[k].x, r[k].x, maxv2, negmax2), o1 = recon_word(v[k].y, r[k].y, maxv2, negmax2);
+        const uint32_t o2 = recon_word(v[k].z, r[k].z, maxv2, negmax2), o3 = recon_word(v[k].w, r[k].w, maxv2, negmax2);
+        if (sizeof(T) == 2)
+            *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(a.rec) + off[k]) = make_uint4(o0, o1, o2, o3);
+        else
+            *reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(a.rec) + off[k]) =
+                make_uint2(prmt_r(o0, o1, 0x6420), prmt_r(o2, o3, 0x6420));
+    }
 }
 
 int launch_recon(p265_ctx *ctx, const void *d_pred, const int16_t *d_res, void *d_rec, const p265_pic_geom *g) {
@@ -78,9 +100,11 @@ int launch_recon(p265_ctx *ctx, const void *d_pred, const int16_t *d_res, void *
     a.bit_depth_c = g->bit_depth_c;
     if (g->n_pics > 65535) return set_error(P265_EINVAL, "too many pictures in one reconstruction batch");
     const int64_t vecs = (int64_t)((g->width + 7) >> 3) * g->height;  // luma plane is the largest
-    const dim3 grid((unsigned)((vecs + 255) / 256), 3, g->n_pics);
-    if (g->bit_depth_y > 8 || g->bit_depth_c > 8) recon_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(a);
-    else recon_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(a);
+    if (vecs >= (int64_t)1 << 31) return set_error(P265_EINVAL, "picture too large for the reconstruction kernel");
+    const int per_cta = kReconThreads * kReconVecs;
+    const dim3 grid((unsigned)((vecs + per_cta - 1) / per_cta), 3, g->n_pics);
+    if (g->bit_depth_y > 8 || g->bit_depth_c > 8) recon_kernel<uint16_t><<<grid, kReconThreads, 0, ctx->stream>>>(a);
+    else recon_kernel<uint8_t><<<grid, kReconThreads, 0, ctx->stream>>>(a);
     P265_CUDA(cudaGetLastError());
     ctx->launches++;
     return P265_OK;
