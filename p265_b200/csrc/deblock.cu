@@ -343,15 +343,28 @@ __global__ void __launch_bounds__(kDbkThreads, PACKED ? P265_DBK_CTAS : 1) deblo
     // more dependent global reads (CTB parameters, tC') and ~400 instructions: their latency
     // hides behind that work instead of being waited for afterwards.
     // W[r][k]: row r, samples (2k, 2k+1) of the shifted block
+    // Blocks that lie inside the picture (all but the first / last block row and column) take
+    // unpredicated loads and stores off one row pointer: the per-row bounds tests and address
+    // arithmetic were ~13 % of the kernel's instructions.
     uint32_t W[8][4];
+    const bool interior = has_l && has_r && y0 >= 0 && y0 + 8 <= h;
+    T *const blk0 = base + (ptrdiff_t)y0 * stride + x0;   // dereferenced only where the row / half exists
     if constexpr (PACKED) {
+        if (interior) {
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const int y = y0 + r;
-            const bool row_ok = y >= 0 && y < h;
-            W[r][0] = W[r][1] = W[r][2] = W[r][3] = 0u;
-            if (row_ok && has_l) loadw<T>(base + (size_t)y * stride + x0, W[r][0], W[r][1]);
-            if (row_ok && has_r) loadw<T>(base + (size_t)y * stride + x0 + 4, W[r][2], W[r][3]);
+            for (int r = 0; r < 8; r++) {
+                loadw<T>(blk0 + (ptrdiff_t)r * stride, W[r][0], W[r][1]);
+                loadw<T>(blk0 + (ptrdiff_t)r * stride + 4, W[r][2], W[r][3]);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int y = y0 + r;
+                const bool row_ok = y >= 0 && y < h;
+                W[r][0] = W[r][1] = W[r][2] = W[r][3] = 0u;
+                if (row_ok && has_l) loadw<T>(blk0 + (ptrdiff_t)r * stride, W[r][0], W[r][1]);
+                if (row_ok && has_r) loadw<T>(blk0 + (ptrdiff_t)r * stride + 4, W[r][2], W[r][3]);
+            }
         }
     }
 
@@ -454,12 +467,20 @@ __global__ void __launch_bounds__(kDbkThreads, PACKED ? P265_DBK_CTAS : 1) deblo
                 W[r][2 * sgm + 1] = w2[r];
             }
         }
+        if (interior) {
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const int y = y0 + r;
-            const bool row_ok = y >= 0 && y < h;
-            if (row_ok && has_l) storew<T>(base + (size_t)y * stride + x0, W[r][0], W[r][1]);
-            if (row_ok && has_r) storew<T>(base + (size_t)y * stride + x0 + 4, W[r][2], W[r][3]);
+            for (int r = 0; r < 8; r++) {
+                storew<T>(blk0 + (ptrdiff_t)r * stride, W[r][0], W[r][1]);
+                storew<T>(blk0 + (ptrdiff_t)r * stride + 4, W[r][2], W[r][3]);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int y = y0 + r;
+                const bool row_ok = y >= 0 && y < h;
+                if (row_ok && has_l) storew<T>(blk0 + (ptrdiff_t)r * stride, W[r][0], W[r][1]);
+                if (row_ok && has_r) storew<T>(blk0 + (ptrdiff_t)r * stride + 4, W[r][2], W[r][3]);
+            }
         }
     } else {
     // ---- load the shifted block --------------------------------------------------------
