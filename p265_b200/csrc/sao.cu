@@ -129,9 +129,10 @@ __device__ __forceinline__ uint32_t apply_offset(uint32_t c, uint32_t idx2, cons
 __device__ __forceinline__ uint32_t edge_word(uint32_t c, uint32_t a, uint32_t b, const ItemConst &k) {
     uint32_t da = c + 0x40004000u - a;  // 0x4000 + (c - a) per half, no cross-half borrow
     uint32_t db = c + 0x40004000u - b;
-    da = __vmins2(__vmaxs2(da, 0x3fff3fffu), 0x40014001u);  // 0x4000 + sign(c - a)
-    db = __vmins2(__vmaxs2(db, 0x3fff3fffu), 0x40014001u);
-    const uint32_t idx2 = da + db - 0x7ffe7ffeu;  // 2 + sign + sign: 0..4
+    // 1 + sign(c - a) = max(min((c - a) + 1, 2), 0): add, min and relu are one VIADDMNMX
+    da = __viaddmin_s16x2_relu(da, 0xc001c001u, 0x00020002u);
+    db = __viaddmin_s16x2_relu(db, 0xc001c001u, 0x00020002u);
+    const uint32_t idx2 = da + db;  // 2 + sign + sign: 0..4
     return apply_offset(c, idx2, k);               // LUT order folds the edgeIdx remap
 }
 
