@@ -41,7 +41,8 @@ struct SaoArgs {
     int32_t ctbs;        // ctbs_w * ctbs_h
     int32_t tiles_y, tiles_c;  // 1024-sample tiles per luma / chroma CTB
     int32_t items;       // n_pics * ctbs * (tiles_y + 2 * tiles_c)
-    int32_t pf_rows;     // L2 prefetch distance in CTB rows (0 = off)
+    int32_t pf_rows;     // L2 prefetch distance in CTB rows (0 = off), <= ctbs_h
+    int32_t pf_quota;    // 128-byte lines each CTA prefetches (covers one full CTB row of all three planes)
 };
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
@@ -396,25 +397,32 @@ __global__ void __launch_bounds__(kSaoWarpsPerCta * 32, P265_SAO_CTAS) sao_kerne
     // the pictures CTB row by CTB row: the CTAs of a CTB row prefetch, one 128-byte line per
     // thread, the input rows of the CTB row `pf_rows` further down (the next picture's when the
     // current one ends), so the demand loads of those later CTAs find their lines in L2.
-    if (a.pf_rows) {
-        const int r = blockIdx.z * a.ctbs_h + blockIdx.y + a.pf_rows;
-        if (r < a.n_pics * a.ctbs_h) {
-            const int pp = r / a.ctbs_h, rr = r - pp * a.ctbs_h;
+    // Only the first warp of a CTA prefetches (pf_quota lines per CTA, lane-strided), and the
+    // target row is found without a division (the launcher keeps pf_rows <= ctbs_h): when every
+    // thread derived its own line, this preamble was 16 % of the kernel's instructions.
+    if (a.pf_rows && threadIdx.x < 32) {
+        int rr = blockIdx.y + a.pf_rows, pp = blockIdx.z;
+        if (rr >= a.ctbs_h) {
+            rr -= a.ctbs_h;
+            pp++;
+        }
+        if (pp < a.n_pics) {
             const int ctb = 1 << a.ctb_log2;
             const int rows_y = min(ctb, a.height - rr * ctb), rows_c = min(ctb >> 1, (a.height >> 1) - rr * (ctb >> 1));
             const int lines_y = (rows_y * a.stride_y * (int)sizeof(T)) >> 7;
             const int lines_c = (rows_c * a.stride_c * (int)sizeof(T)) >> 7;
-            int t = blockIdx.x * blockDim.x + threadIdx.x;
-            const T *base = reinterpret_cast<const T *>(a.rec) + (int64_t)pp * a.pic_stride;
-            const char *q = nullptr;
-            if (t < lines_y) {
-                q = reinterpret_cast<const char *>(base + a.plane_off[0] + (int64_t)rr * ctb * a.stride_y) + ((int64_t)t << 7);
-            } else if ((t -= lines_y) < 2 * lines_c) {
-                const int c = t >= lines_c ? 2 : 1;
-                t -= c == 2 ? lines_c : 0;
-                q = reinterpret_cast<const char *>(base + a.plane_off[c] + (int64_t)rr * (ctb >> 1) * a.stride_c) + ((int64_t)t << 7);
+            const char *base = reinterpret_cast<const char *>(reinterpret_cast<const T *>(a.rec) + (int64_t)pp * a.pic_stride);
+            const char *py = base + (a.plane_off[0] + (int64_t)rr * ctb * a.stride_y) * (int64_t)sizeof(T);
+            const char *pcb = base + (a.plane_off[1] + (int64_t)rr * (ctb >> 1) * a.stride_c) * (int64_t)sizeof(T);
+            const char *pcr = base + (a.plane_off[2] + (int64_t)rr * (ctb >> 1) * a.stride_c) * (int64_t)sizeof(T);
+            const int t0 = blockIdx.x * a.pf_quota;
+            const int t1 = min(t0 + a.pf_quota, lines_y + 2 * lines_c);
+            for (int t = t0 + (int)threadIdx.x; t < t1; t += 32) {
+                const char *q = t < lines_y ? py + ((int64_t)t << 7)
+                                : (t < lines_y + lines_c ? pcb + ((int64_t)(t - lines_y) << 7)
+                                                         : pcr + ((int64_t)(t - lines_y - lines_c) << 7));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
             }
-            if (q) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
         }
     }
     const int lane = threadIdx.x & 31;
@@ -427,9 +435,14 @@ __global__ void __launch_bounds__(kSaoWarpsPerCta * 32, P265_SAO_CTAS) sao_kerne
 }
 
 template <typename T, bool NOFILT>
-static int launch_sao_t(p265_ctx *ctx, const SaoArgs &a, int n_pics) {
+static int launch_sao_t(p265_ctx *ctx, SaoArgs a, int n_pics) {
     const int per_ctb = a.tiles_y + 2 * a.tiles_c;  // 6 for 64x64 CTBs, 3 otherwise
     const dim3 grid((a.ctbs_w * per_ctb + kSaoWarpsPerCta - 1) / kSaoWarpsPerCta, a.ctbs_h, n_pics);
+    {
+        const int ctb = 1 << a.ctb_log2;
+        const int64_t lines = ((int64_t)ctb * a.stride_y + 2 * (int64_t)(ctb >> 1) * a.stride_c) * (int64_t)sizeof(T) >> 7;
+        a.pf_quota = (int)((lines + grid.x - 1) / grid.x);
+    }
     const int threads = kSaoWarpsPerCta * 32;
     if (per_ctb == 6) sao_kernel<T, NOFILT, 6><<<grid, threads, 0, ctx->stream>>>(a);
     else sao_kernel<T, NOFILT, 3><<<grid, threads, 0, ctx->stream>>>(a);
@@ -470,7 +483,7 @@ int launch_sao(p265_ctx *ctx, const void *d_rec, void *d_out, const p265_pic_geo
             pf = e ? atoi(e) : 4;  // measured on 4K 10-bit: 2..8 alike (0.87 of HBM), 0 = off 0.76, >= 24 worse
             if (pf < 0 || pf > 4096) pf = 4;
         }
-        a.pf_rows = pf;
+        a.pf_rows = pf < a.ctbs_h ? pf : a.ctbs_h;  // the kernel wraps into the next picture at most once
     }
     if (a.ctbs_h > 65535 || g->n_pics > 65535) return set_error(P265_EINVAL, "too many CTB rows / pictures in one SAO batch");
     const bool wide = g->bit_depth_y > 8 || g->bit_depth_c > 8;
