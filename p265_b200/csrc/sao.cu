@@ -335,6 +335,14 @@ __device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int r
             const int lyr = g.row0 + j;
             if (j < g.rows && g.active && lyr < g.vh) load8<T>(in + (int64_t)lyr * g.stride, wv[j]);
         }
+        if (type != 1) {  // off (warp-uniform): plain copy, no band arithmetic to select away
+#pragma unroll
+            for (int j = 0; j < kMaxRows; j++) {
+                const int lyr = g.row0 + j;
+                if (j < g.rows && g.active && lyr < g.vh) store8<T>(out + (int64_t)lyr * g.stride, wv[j]);
+            }
+            return;
+        }
 #pragma unroll
         for (int j = 0; j < kMaxRows; j++) {
             const int lyr = g.row0 + j;
@@ -347,7 +355,7 @@ __device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int r
                 skip[1] = nf_shift == 3 ? skip[0] : (nf_second && f[1] != 0);
             }
 #pragma unroll
-            for (int i = 0; i < 4; i++) o[i] = (type == 1 && !skip[i >> 1]) ? band_word(wv[j][i], k) : wv[j][i];
+            for (int i = 0; i < 4; i++) o[i] = skip[i >> 1] ? wv[j][i] : band_word(wv[j][i], k);
             store8<T>(out + (int64_t)lyr * g.stride, o);
         }
         return;
