@@ -174,7 +174,7 @@ __device__ __forceinline__ void row_mask(const MaskCtx &m, bool top, bool bot, u
     }
 }
 
-template <int CLS>
+template <int CLS, bool FULL = false>
 __device__ __forceinline__ void edge_row(const Row &P, const Row &C, const Row &N, const ItemConst &k,
                                          const uint32_t (&keep)[4], uint32_t (&out)[4]) {
 #pragma unroll
@@ -195,7 +195,7 @@ __device__ __forceinline__ void edge_row(const Row &P, const Row &C, const Row &
             b = prmt(N.e[i], N.e[i + 1], 0x5432);
         }
         const uint32_t r = edge_word(c, a, b, k);
-        out[i] = (c & keep[i]) | (r & ~keep[i]);
+        out[i] = FULL ? r : ((c & keep[i]) | (r & ~keep[i]));
     }
 }
 
@@ -207,7 +207,9 @@ struct Geo {
     bool active;             // lane covers valid columns
 };
 
-template <typename T, int CLS, bool NOFILT>
+// FULL: the CTB lies inside the picture with all eight neighbours available and no no-filter map
+// (nine CTBs out of ten of a 4K picture): every sample is filtered, no keep masks at all.
+template <typename T, int CLS, bool NOFILT, bool FULL = false>
 __device__ __forceinline__ void edge_strip(const T *in, T *out, const Geo &g, const Strip &s, const MaskCtx &m,
                                            const ItemConst &k, const uint8_t *nf_row, int nf_stride, int nf_shift, bool nf_second) {
     // `in` / `out` point at (row y0, lane's first column)
@@ -225,6 +227,17 @@ __device__ __forceinline__ void edge_strip(const T *in, T *out, const Geo &g, co
 #pragma unroll
     for (int j = 0; j < kMaxRows + 2; j++)
         if (j < g.rows + 2) row_finish<HALO>(rw[j], s);
+    if (FULL) {
+#pragma unroll
+        for (int j = 0; j < kMaxRows; j++) {
+            if (j >= g.rows) break;  // warp-uniform
+            uint32_t o[4];
+            const uint32_t none[4] = {0u, 0u, 0u, 0u};
+            edge_row<CLS, true>(rw[j], rw[j + 1], rw[j + 2], k, none, o);
+            if (g.active) store8<T>(out + (int64_t)(g.row0 + j) * g.stride, o);
+        }
+        return;
+    }
     uint32_t mid[4];
     row_mask<CLS>(m, false, false, mid);
 #pragma unroll
@@ -255,7 +268,8 @@ __device__ __forceinline__ void edge_strip(const T *in, T *out, const Geo &g, co
 template <typename T, bool NOFILT>
 __device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int rx, int ry, int tile, int lane) {
     // field-by-field reads (a by-value copy indexed by `c` would live in local memory)
-    const p265_sao_ctb *qp = &a.params[((int64_t)pic * a.ctbs_h + ry) * a.ctbs_w + rx];
+    // 32-bit CTB index (the launcher rejects batches with 2^31 or more CTBs): one IMAD.WIDE
+    const p265_sao_ctb *qp = a.params + ((uint32_t)(pic * a.ctbs_h + ry) * (uint32_t)a.ctbs_w + (uint32_t)rx);
     struct {
         int band_pos, eo_class, avail;
         int offset_val[4];
@@ -367,6 +381,15 @@ __device__ __forceinline__ void sao_item(const SaoArgs &a, int pic, int c, int r
     MaskCtx m;
     const uint32_t av = q.avail;
     const bool has_l = x0 > 0, has_r = x0 + cs < w, has_u = g.y0 > 0, has_d = g.y0 + cs < h;
+    if (!NOFILT && has_l && has_r && has_u && has_d && (av & 0x1efu) == 0x1efu) {  // warp-uniform; vw == vh == cs follows
+        switch (q.eo_class) {
+            case 0: edge_strip<T, 0, false, true>(in, out, g, s, m, k, nullptr, 0, 3, true); break;
+            case 1: edge_strip<T, 1, false, true>(in, out, g, s, m, k, nullptr, 0, 3, true); break;
+            case 2: edge_strip<T, 2, false, true>(in, out, g, s, m, k, nullptr, 0, 3, true); break;
+            default: edge_strip<T, 3, false, true>(in, out, g, s, m, k, nullptr, 0, 3, true); break;
+        }
+        return;
+    }
     m.aUL = has_u && has_l && (av >> 0 & 1);
     m.aU = has_u && (av >> 1 & 1);
     m.aUR = has_u && has_r && (av >> 2 & 1);
@@ -494,6 +517,7 @@ int launch_sao(p265_ctx *ctx, const void *d_rec, void *d_out, const p265_pic_geo
         a.pf_rows = pf < a.ctbs_h ? pf : a.ctbs_h;  // the kernel wraps into the next picture at most once
     }
     if (a.ctbs_h > 65535 || g->n_pics > 65535) return set_error(P265_EINVAL, "too many CTB rows / pictures in one SAO batch");
+    if ((int64_t)a.ctbs * g->n_pics >= ((int64_t)1 << 31)) return set_error(P265_EINVAL, "too many CTBs in one SAO batch");
     const bool wide = g->bit_depth_y > 8 || g->bit_depth_c > 8;
     if (wide) return d_no_filter ? launch_sao_t<uint16_t, true>(ctx, a, g->n_pics) : launch_sao_t<uint16_t, false>(ctx, a, g->n_pics);
     return d_no_filter ? launch_sao_t<uint8_t, true>(ctx, a, g->n_pics) : launch_sao_t<uint8_t, false>(ctx, a, g->n_pics);
