@@ -215,6 +215,7 @@ __device__ __forceinline__ void edge_strip(const T *in, T *out, const Geo &g, co
     // `in` / `out` point at (row y0, lane's first column)
     constexpr bool HALO = CLS != 1;
     auto rowptr = [&](int ly) {
+        if (FULL) return in + (int64_t)ly * g.stride;  // rows -1 .. cs exist: no clamping
         int y = g.y0 + ly;
         y = y < 0 ? 0 : (y >= g.h ? g.h - 1 : y);
         return in + (int64_t)(y - g.y0) * g.stride;
