@@ -10,12 +10,13 @@
 // independent loads in flight -- the kernel is bandwidth-, not latency-limited.
 // Horizontal neighbours come through warp shuffles, vertical ones from the lane's own
 // registers; no shared memory.  All arithmetic is packed 2 x 16 bit in one 32-bit register:
-//   sign(c - n)      : (c + 0x4000_4000 - n) clamped to [0x3fff, 0x4001] per half-word
-//                      (VIMNMX.S16x2 twice)
+//   1 + sign(c - n)  : (c + 0x4000_4000 - n), then add -0x3fff, min 2, relu in one
+//                      VIADDMNMX.S16x2.RELU
 //   SaoOffsetVal[..] : byte-permute LUT (PRMT with sign replication) over the CTB's four
 //                      int8 offsets
 //   Clip1(c + off)   : VIADDMNMX.S16x2.RELU
 // Type / class / offsets are uniform per warp, so every branch is warp-uniform.
+// CTBs inside the picture whose eight neighbours are all available take a mask-free edge path.
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
