@@ -45,6 +45,25 @@ def test_config4_two_slices_no_filter_across(engine, c_oracle):
     assert_planes_equal(geom, got, c_oracle.sao_batch(rec, geom, 6, params))
 
 
+@pytest.mark.parametrize("bit_depth", [8, 10, 12])
+@pytest.mark.parametrize("ctb_log2", [4, 5, 6])
+def test_all_edge_interior_ctbs(engine, c_oracle, bit_depth, ctb_log2):
+    """Every CTB edge-filtered, all classes, every neighbour available: the CTBs that do not touch
+    the picture border take the kernel's mask-free path, the border CTBs the masked one; one CTB in
+    the middle has a neighbour switched off and must fall back to the masked path."""
+    geom, rec, params = synth.sao_batch(448, 320, bit_depth, n_pics=2, ctb_log2=ctb_log2, seed=300 + ctb_log2)
+    rng = np.random.default_rng(301 + bit_depth)
+    params["type"][:] = 2
+    params["eo_class"][:] = rng.integers(0, 4, params["eo_class"].shape)
+    params["offset_val"][:] = (7, 2, -2, -7)
+    params["avail"][:] = AVAIL_ALL
+    params["avail"][0, 2, 3] = AVAIL_ALL & ~(1 << 5)   # right neighbour of one interior CTB unavailable
+    got = engine.sao(rec, geom, ctb_log2, params)
+    ref = c_oracle.sao_batch(rec, geom, ctb_log2, params)
+    assert_planes_equal(geom, got, ref)
+    assert not np.array_equal(geom.plane_view(ref, 0, 0), geom.plane_view(rec, 0, 0))
+
+
 @pytest.mark.parametrize("bit_depth", [8, 10])
 def test_random_availability_masks(engine, c_oracle, bit_depth):
     geom, rec, params = synth.sao_batch(320, 256, bit_depth, n_pics=2, ctb_log2=5, seed=77)
