@@ -58,6 +58,39 @@ P265_HD int dp2a_hi(int a, int b, int c) {
            (int)(int16_t)((uint32_t)a >> 16) * (int)(int8_t)((b >> 24) & 0xff);
 #endif
 }
+// signed int16 pair x UNSIGNED byte pair (ScalingFactor bytes reach 255): IDP.2A.{LO,HI}.S16.U8
+P265_HD int dp2a_lo_su(int a, uint32_t b, int c) {
+#if defined(__CUDA_ARCH__)
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+#else
+    return c + (int)(int16_t)(a & 0xffff) * (int)(b & 0xff) + (int)(int16_t)((uint32_t)a >> 16) * (int)((b >> 8) & 0xff);
+#endif
+}
+P265_HD int dp2a_hi_su(int a, uint32_t b, int c) {
+#if defined(__CUDA_ARCH__)
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+#else
+    return c + (int)(int16_t)(a & 0xffff) * (int)((b >> 16) & 0xff) + (int)(int16_t)((uint32_t)a >> 16) * (int)(b >> 24);
+#endif
+}
+// (f0, 0, 0, f1): bytes 2p and 2p+1 (p = 0, 1) of a word of four ScalingFactor bytes, placed so that
+// dp2a_lo_su / dp2a_hi_su of a packed coefficient pair give level_lo * f0 and level_hi * f1 -- the
+// extraction of both coefficients, of both factors and the two multiplications in three instructions
+P265_HD uint32_t sf_pair(uint32_t m4, int p) {
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(m4), "r"(0u), "r"(p ? 0x3442u : 0x1440u));
+    return d;
+#else
+    const uint32_t f0 = (m4 >> (16 * p)) & 0xff, f1 = (m4 >> (16 * p + 8)) & 0xff;
+    return f0 | (f1 << 24);
+#endif
+}
+
 // {lo, hi} int32 -> s16x2 with signed saturation
 P265_HD int pack_sat(int lo, int hi) {
 #if defined(__CUDA_ARCH__)
@@ -873,15 +906,30 @@ P265_HD void tb4_lane(const TbParams &t, const uint32_t (&w)[8], const uint8_t *
         mrow[0] = mv.x; mrow[1] = mv.y; mrow[2] = mv.z; mrow[3] = mv.w;
     }
     int d[4][4];  // [y][x]
-    P265_UNROLL
-    for (int y = 0; y < 4; y++) {
+    if (SF != SF_NONE) {
+        // level * factor by mixed-sign dp2a straight from the packed words (sf_pair), then * w:
+        // (level * f) * w == level * (f * w), all below 2^30
+        if (!sfm) mrow[0] = mrow[1] = mrow[2] = mrow[3] = 0x01010101u;  // host only: the device always has a matrix
         P265_UNROLL
-        for (int x = 0; x < 4; x++) {
-            const uint32_t ww = w[y * 2 + (x >> 1)];
-            const int lv = (x & 1) ? sx_hi(ww) : sx_lo(ww);
-            int m = t.w;
-            if (SF != SF_NONE && sfm) m *= (int)((mrow[y] >> (8 * x)) & 0xff);
-            d[y][x] = SLOW ? dequant(lv, m, t) : dequant_fast(lv, m, t);
+        for (int y = 0; y < 4; y++) {
+            P265_UNROLL
+            for (int pr = 0; pr < 2; pr++) {
+                const int ww = (int)w[y * 2 + pr];
+                const uint32_t f = sf_pair(mrow[y], pr);
+                const int v0 = dp2a_lo_su(ww, f, 0), v1 = dp2a_hi_su(ww, f, 0);
+                d[y][2 * pr] = SLOW ? dequant(v0, t.w, t) : dequant_fast(v0, t.w, t);
+                d[y][2 * pr + 1] = SLOW ? dequant(v1, t.w, t) : dequant_fast(v1, t.w, t);
+            }
+        }
+    } else {
+        P265_UNROLL
+        for (int y = 0; y < 4; y++) {
+            P265_UNROLL
+            for (int x = 0; x < 4; x++) {
+                const uint32_t ww = w[y * 2 + (x >> 1)];
+                const int lv = (x & 1) ? sx_hi(ww) : sx_lo(ww);
+                d[y][x] = SLOW ? dequant(lv, t.w, t) : dequant_fast(lv, t.w, t);
+            }
         }
     }
     // stage 1: four columns in lock step; slot 0 = rows (0,2), slot 1 = rows (1,3)
@@ -942,17 +990,29 @@ P265_HD void tb8_lane(const TbParams &t, const unsigned char *tile, int lane, co
             const uint2 vb = *reinterpret_cast<const uint2 *>(sfm + y1 * 8);
             ma[0] = va.x; ma[1] = va.y; mb[0] = vb.x; mb[1] = vb.y;
         }
-        P265_UNROLL
-        for (int x = 0; x < 8; x++) {
-            const int la = (x & 1) ? sx_hi(aw[x >> 1]) : sx_lo(aw[x >> 1]);
-            const int lb = (x & 1) ? sx_hi(bw[x >> 1]) : sx_lo(bw[x >> 1]);
-            int m0 = t.w, m1 = t.w;
-            if (SF != SF_NONE && sfm) {
-                m0 *= (int)((ma[x >> 2] >> (8 * (x & 3))) & 0xff);
-                m1 *= (int)((mb[x >> 2] >> (8 * (x & 3))) & 0xff);
+        if (SF != SF_NONE) {
+            if (!sfm) ma[0] = ma[1] = mb[0] = mb[1] = 0x01010101u;  // host only: the device always has a matrix
+            P265_UNROLL
+            for (int pr = 0; pr < 4; pr++) {  // columns 2 pr, 2 pr + 1: level * factor by mixed-sign dp2a (sf_pair)
+                const uint32_t fa = sf_pair(ma[pr >> 1], pr & 1), fb = sf_pair(mb[pr >> 1], pr & 1);
+                const int a0 = dp2a_lo_su((int)aw[pr], fa, 0), a1 = dp2a_hi_su((int)aw[pr], fa, 0);
+                const int b0 = dp2a_lo_su((int)bw[pr], fb, 0), b1 = dp2a_hi_su((int)bw[pr], fb, 0);
+                if (!SLOW) {
+                    P[2 * pr][s] = pack_sat(dequant_fast(a0, t.w, t), dequant_fast(b0, t.w, t));
+                    P[2 * pr + 1][s] = pack_sat(dequant_fast(a1, t.w, t), dequant_fast(b1, t.w, t));
+                } else {
+                    P[2 * pr][s] = pack_sat(dequant(a0, t.w, t), dequant(b0, t.w, t));
+                    P[2 * pr + 1][s] = pack_sat(dequant(a1, t.w, t), dequant(b1, t.w, t));
+                }
             }
-            if (!SLOW) P[x][s] = pack_sat(dequant_fast(la, m0, t), dequant_fast(lb, m1, t));
-            else P[x][s] = pack_sat(dequant(la, m0, t), dequant(lb, m1, t));
+        } else {
+            P265_UNROLL
+            for (int x = 0; x < 8; x++) {
+                const int la = (x & 1) ? sx_hi(aw[x >> 1]) : sx_lo(aw[x >> 1]);
+                const int lb = (x & 1) ? sx_hi(bw[x >> 1]) : sx_lo(bw[x >> 1]);
+                if (!SLOW) P[x][s] = pack_sat(dequant_fast(la, t.w, t), dequant_fast(lb, t.w, t));
+                else P[x][s] = pack_sat(dequant(la, t.w, t), dequant(lb, t.w, t));
+            }
         }
     }
     // stage 1: column pairs = stage-2 slots (0,4), (2,6), (1,3), (5,7)
