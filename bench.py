@@ -191,7 +191,7 @@ def run_gpu(args):
     def residual():
         eng.residual_dev(d_tus.data_ptr(), bins, d_co.data_ptr(), d_sf.data_ptr() if d_sf is not None else None,
                          res.geom, d_res.data_ptr(), zero_fill=not res.covers_all,
-                         sf_replicated=bool(res.sf_replicated))
+                         sf_replicated=bool(res.sf_replicated), dense_arena=res.dense_small_bins())
 
     def sao():
         eng.sao_dev(d_rec.data_ptr(), d_sao.data_ptr(), sgeom, 6, d_par.data_ptr())
@@ -263,7 +263,7 @@ def run_gpu(args):
 
         def residual_c2():
             eng.residual_dev(c_tus.data_ptr(), c_bins, c_co.data_ptr(), None, c2.geom, c_out.data_ptr(),
-                             zero_fill=not c2.covers_all, sf_replicated=False)
+                             zero_fill=not c2.covers_all, sf_replicated=False, dense_arena=c2.dense_small_bins())
         for _ in range(3):
             residual_c2()
         ms = timed(residual_c2, args.steps) / args.steps

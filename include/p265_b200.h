@@ -112,6 +112,11 @@ typedef struct p265_dbk_ctb {
                                     7.4.5 up-sampling of an 8x8 list (+ DC at [0][0]), as
                                     every conformant stream has them: enables the fast
                                     per-column factor path.  Unset: any table works.   */
+#define P265_RES_DENSE_ARENA 4 /* device entry point only (the host entry point finds out by
+                                  itself): inside the 8x8 bin and inside the 4x4 bin the
+                                  coefficients of descriptor i directly follow those of
+                                  descriptor i-1 (coeff_off grows by 4 / by 1), as the packer
+                                  emits them: tile copies start without their descriptors */
 
 /* ---- context ------------------------------------------------------------------ */
 int p265_abi_version(void);

@@ -64,16 +64,20 @@ static int check_geom(const p265_pic_geom *g, int elem_align) {
 }
 
 // host-side validation of a descriptor list (host entry points only)
+// *dense_small = inside the 8x8 bin and inside the 4x4 bin every TB's coefficients directly follow
+// the previous TB's (what P265_RES_DENSE_ARENA asserts on the device entry point)
 static int check_tus(const p265_tu_desc *tus, const int32_t bin_counts[4], size_t n_coeffs, const p265_pic_geom *g,
-                     bool have_table) {
+                     bool have_table, bool *dense_small) {
     // one pass over caller data, on the latency path of every host call: plane limits and the qP
     // bound are hoisted per component, the rare diagnostics are formatted only on failure
     const int wmax[3] = {g->width, g->width / 2, g->width / 2}, hmax[3] = {g->height, g->height / 2, g->height / 2};
     const int qmax[3] = {51 + 6 * (g->bit_depth_y - 8), 51 + 6 * (g->bit_depth_c - 8), 51 + 6 * (g->bit_depth_c - 8)};
     int64_t k = 0;
+    uint32_t not_dense = 0;
     for (int b = 0; b < 4; b++) {
         if (bin_counts[b] < 0) return set_error(P265_EINVAL, "negative bin count");
         const int log2n = 5 - b, n = 1 << log2n;
+        const uint32_t units = (uint32_t)(n * n) / 16, z0 = bin_counts[b] ? tus[k].coeff_off : 0u;
         const unsigned bad_flags = (log2n != 2 ? (P265_TU_SKIP | P265_TU_DST) : 0u) | (have_table ? P265_TU_PRESCALED : 0u);
         for (int32_t i = 0; i < bin_counts[b]; i++, k++) {
             const p265_tu_desc &t = tus[k];
@@ -82,6 +86,7 @@ static int check_tus(const p265_tu_desc *tus, const int32_t bin_counts[4], size_
                             t.y + n <= hmax[c] && t.pic < g->n_pics &&
                             (size_t)t.coeff_off * 16 + (size_t)n * n <= n_coeffs && !(t.flags & bad_flags) &&
                             !((t.flags & P265_TU_DST) && t.c_idx != 0) && t.qp <= qmax[c];
+            if (b >= 2) not_dense |= t.coeff_off ^ (z0 + (uint32_t)i * units);
             if (ok) continue;
             if (t.log2n != log2n)
                 return set_error(P265_EINVAL, "descriptor %lld: log2n %d where bin expects %d (list must be sorted "
@@ -102,6 +107,7 @@ static int check_tus(const p265_tu_desc *tus, const int32_t bin_counts[4], size_
             return set_error(P265_EINVAL, "descriptor %lld: qP %d out of range", (long long)k, t.qp);
         }
     }
+    *dense_small = not_dense == 0;
     return P265_OK;
 }
 
@@ -220,7 +226,9 @@ int p265_residual_batch(p265_ctx *ctx, const p265_tu_desc *tus, const int32_t bi
     int64_t n = 0;
     for (int b = 0; b < 4; b++) n += bin_counts[b] > 0 ? bin_counts[b] : 0;
     if (n && (!tus || !coeffs)) return set_error(P265_EINVAL, "descriptor / coefficient pointer is NULL");
-    if ((rc = check_tus(tus, bin_counts, n_coeffs, geom, scaling_factor != nullptr))) return rc;
+    bool dense_small = false;
+    if ((rc = check_tus(tus, bin_counts, n_coeffs, geom, scaling_factor != nullptr, &dense_small))) return rc;
+    flags = dense_small ? (flags | P265_RES_DENSE_ARENA) : (flags & ~P265_RES_DENSE_ARENA);  // found out here, not asserted
     P265_CUDA(cudaSetDevice(ctx->device));
     void *d_tus, *d_co, *d_sf = nullptr, *d_out;
     const size_t out_bytes = sizeof(int16_t) * (size_t)geom->pic_stride * geom->n_pics;

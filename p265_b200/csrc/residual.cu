@@ -229,22 +229,30 @@ __device__ __forceinline__ void run_bin8(const KernelArgs &a, int gw, int stride
     // Cooperative tile copy: copy instruction i moves the 8 chunks (rows) of TBs 4i .. 4i+3, i.e. four
     // whole 128-byte lines when the arena is dense, instead of one 16-byte chunk of 32 different TBs
     // (32 LSU wavefronts per instruction).  The TB's arena offset comes from its ring entry.
+    // Dense arena (P265_RES_DENSE_ARENA): TB i of the bin sits 64 coefficients behind TB i-1, so a
+    // tile's address follows from the bin's first offset and the copy does not wait for descriptors:
+    // a warp sees only a handful of items, its two-deep start-up chain (descriptor -> tile) was a
+    // large part of its lifetime.
+    const bool dense = a.dense_arena != 0;
+    const uint32_t z0 = dense ? a.tus[first].coeff_off : 0u;
     auto issue = [&](int slot, int item, unsigned char *tile) {
         const int n_here = n_tb - item * 32;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int t = (lane >> 3) + 4 * i;
-            if (t < n_here)
-                copy16_async(tile + tb8_chunk_off(t, lane & 7),
-                             a.coeffs + (size_t)ring0[32 * slot + t].z * 16 + (lane & 7) * 8);
+            if (t < n_here) {
+                const uint32_t z = dense ? z0 + (uint32_t)(item * 32 + t) * 4u : ring0[32 * slot + t].z;
+                copy16_async(tile + tb8_chunk_off(t, lane & 7), a.coeffs + (size_t)z * 16 + (lane & 7) * 8);
+            }
         }
     };
     bool valid = gw * 32 + lane < n_tb;
     {
+        if (dense) issue(0, gw, wbase);
         const uint4 d0 = SmallDesc<SF, 3>::load(a, first + gw * 32 + lane, valid);
         ring[0] = d0;
         __syncwarp();
-        issue(0, gw, wbase);
+        if (!dense) issue(0, gw, wbase);
         const int i1 = (gw + stride) * 32 + lane;
         if (gw + stride < n_items && i1 < n_tb) copy16_async(&ring[32], SmallDesc<SF, 3>::ptr(a, first + i1));
         cp_async_commit();
@@ -302,10 +310,12 @@ __device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride
         const int i = item * 32 + lane;
         if (item < n_items && i < n_tb) copy16_async(&ring[32 * slot], SmallDesc<SF, 2>::ptr(a, first + i));
     };
+    const bool dense = a.dense_arena != 0;  // see run_bin8: a 4x4 TB is one 16-coefficient unit
+    const uint32_t z0 = dense ? a.tus[first].coeff_off : 0u;
     auto tile_async = [&](int item, const uint4 d, int stage) {
         const int i = item * 32 + lane;
         if (item < n_items && i < n_tb) {
-            const int16_t *src = a.coeffs + (size_t)d.z * 16;
+            const int16_t *src = a.coeffs + (size_t)(dense ? z0 + (uint32_t)i : d.z) * 16;
             unsigned char *dst = tiles + stage * 1024;
             copy16_async(dst + tb4_slot_off(lane, 0), src);
             copy16_async(dst + tb4_slot_off(lane, 1), src + 8);
@@ -313,16 +323,27 @@ __device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride
     };
     // cp.async groups: G0 = {tile 0}, G_j = {tile j, descriptor j+2} for j >= 1.  At item k
     // all groups but the newest (G_{k+1}) are complete: tile k and descriptors <= k+2.
-    {   // prologue: descriptors 0..2 by plain loads (paid once per warp and bin)
+    {   // prologue: descriptors 0..2 by plain loads (paid once per warp and bin); with a dense arena
+        // the first two tiles are requested before them
+        const uint4 none = make_uint4(0, 0, 0, 0);
+        if (dense) {
+            tile_async(gw, none, 0);
+            cp_async_commit();
+            tile_async(gw + stride, none, 1);
+            desc_async(gw + 3 * stride, 3);
+            cp_async_commit();
+        }
         for (int j = 0; j < 3; j++) {
             const int i = (gw + j * stride) * 32 + lane;
             ring[32 * j] = SmallDesc<SF, 2>::load(a, first + i, gw + j * stride < n_items && i < n_tb);
         }
-        tile_async(gw, ring[0], 0);
-        cp_async_commit();
-        tile_async(gw + stride, ring[32], 1);
-        desc_async(gw + 3 * stride, 3);
-        cp_async_commit();
+        if (!dense) {
+            tile_async(gw, ring[0], 0);
+            cp_async_commit();
+            tile_async(gw + stride, ring[32], 1);
+            desc_async(gw + 3 * stride, 3);
+            cp_async_commit();
+        }
     }
     int k = 0;  // item counter: tile stage k % 3, descriptor slot k % 4
 #pragma unroll 1
@@ -508,6 +529,7 @@ static int fill_args(KernelArgs &a, const p265_tu_desc *d_tus, const int32_t bin
     a.coeffs = d_coeffs;
     a.sf = d_sf;
     a.sf_replicated = 0;
+    a.dense_arena = 0;
     a.out = d_out;
     for (int c = 0; c < 3; c++) a.plane_off[c] = g->plane_off[c];
     a.pic_stride = g->pic_stride;
@@ -619,6 +641,7 @@ int launch_residual(p265_ctx *ctx, const p265_tu_desc *d_tus, const int32_t bin_
     int rc = fill_args(a, d_tus, bin_counts, d_coeffs, d_sf, g, d_out);
     if (rc) return rc;
     a.sf_replicated = (flags & P265_RES_SF_REPLICATED) != 0;
+    a.dense_arena = (flags & P265_RES_DENSE_ARENA) != 0;
     if (flags & P265_RES_ZERO_FILL)
         P265_CUDA(cudaMemsetAsync(d_out, 0, sizeof(int16_t) * (size_t)g->pic_stride * g->n_pics, ctx->stream));
     if (a.first_item[4] == 0) return P265_OK;

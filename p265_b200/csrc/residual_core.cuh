@@ -331,6 +331,7 @@ struct KernelArgs {
     const int16_t *coeffs;
     const uint8_t *sf;  // P265_SF_BYTES or nullptr
     int32_t sf_replicated;  // 16x16 / 32x32 matrices obey the 7.4.5 up-sampling (+ DC at [0][0])
+    int32_t dense_arena;    // P265_RES_DENSE_ARENA: inside the 8x8 and 4x4 bins, TB i's coefficients follow TB i-1's
     int16_t *out;
     int64_t plane_off[3];
     int64_t pic_stride;

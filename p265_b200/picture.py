@@ -134,6 +134,35 @@ class ResidualBatch:
     def samples(self) -> int:
         return int((1 << (2 * self.tus["log2n"].astype(np.int64))).sum())
 
+    def densified(self) -> "ResidualBatch":
+        """The same batch with the arena re-laid in descriptor order (TB after TB, as sorted): the
+        layout P265_RES_DENSE_ARENA describes.  A packer that emits coefficients while it sorts
+        produces this directly; here it is one gather over 16-coefficient units."""
+        units = (1 << (2 * self.tus["log2n"].astype(np.int64))) >> 4
+        new_off = np.concatenate(([0], np.cumsum(units)[:-1])) if len(units) else np.zeros(0, np.int64)
+        total = int(units.sum())
+        src = np.repeat(self.tus["coeff_off"].astype(np.int64) - new_off, units) + np.arange(total, dtype=np.int64)
+        n_units = self.coeffs.size // 16
+        arena = np.ascontiguousarray(self.coeffs[:n_units * 16].reshape(n_units, 16)[src]).reshape(-1)
+        tus = self.tus.copy()
+        tus["coeff_off"] = new_off.astype(np.uint32)
+        return ResidualBatch(self.geom, tus, arena, self.scaling_factor, self.covers_all, self.sf_replicated, self.bins)
+
+    def dense_small_bins(self) -> bool:
+        """True when, inside the 8x8 bin and inside the 4x4 bin, every TB's coefficients directly
+        follow the previous TB's in the arena (what P265_RES_DENSE_ARENA asserts for the device
+        entry point; the host entry point checks it itself).  Computed once per batch."""
+        if getattr(self, "_dense", None) is None:
+            b = self.bin_counts()
+            ok, k = True, b[0] + b[1]
+            for n_tb, units in ((b[2], 4), (b[3], 1)):
+                off = self.tus["coeff_off"][k:k + n_tb].astype(np.int64)
+                if n_tb and not np.array_equal(off, off[0] + units * np.arange(n_tb, dtype=np.int64)):
+                    ok = False
+                k += n_tb
+            self._dense = ok
+        return self._dense
+
 
 def sort_by_size(tus: np.ndarray) -> np.ndarray:
     """Stable sort, largest TBs first -- the order `p265_residual_*` requires."""

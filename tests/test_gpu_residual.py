@@ -42,6 +42,43 @@ def test_config2_full_1080p(engine, c_oracle):
     assert_planes_equal(batch.geom, got, c_oracle.residual_batch(batch, zero_fill=False))
 
 
+@pytest.mark.parametrize("name", ["1080p8", "4k10"])
+@pytest.mark.parametrize("stress", [False, True])
+def test_dense_arena_layout(engine, c_oracle, name, stress):
+    """Arena re-laid in descriptor order: the host entry point detects it and the small bins
+    address their tiles by index (P265_RES_DENSE_ARENA); results equal the scattered layout's."""
+    batch = synth.residual_batch(name, n_pics=2, stress=stress)
+    dense = batch.densified()
+    assert dense.dense_small_bins() and not batch.dense_small_bins()
+    ref = c_oracle.residual_batch(batch, zero_fill=False)
+    assert_planes_equal(batch.geom, engine.residual(dense), ref)
+    # ragged: drop TBs so that the last items of the small bins are partial, then re-lay
+    keep = np.ones(len(batch.tus), bool)
+    keep[-37:] = False
+    keep[np.flatnonzero(batch.tus["log2n"] == 3)[-5:]] = False
+    from p265_b200.picture import ResidualBatch
+    part = ResidualBatch(batch.geom, np.ascontiguousarray(batch.tus[keep]), batch.coeffs, batch.scaling_factor,
+                         covers_all=False).densified()
+    assert part.dense_small_bins()
+    assert_planes_equal(batch.geom, engine.residual(part), c_oracle.residual_batch(part, zero_fill=True))
+
+
+def test_dense_arena_flag_on_device_entry(engine, c_oracle):
+    import torch
+    batch = synth.residual_batch("4k10", n_pics=1).densified()
+    dev = torch.device("cuda", 0)
+    to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+    d_tus, d_co, d_sf = to_dev(batch.tus), to_dev(batch.coeffs), to_dev(batch.scaling_factor)
+    ref = c_oracle.residual_batch(batch, zero_fill=False)
+    for dense in (True, False):
+        d_out = torch.zeros(batch.geom.total_elems() * 2, dtype=torch.uint8, device=dev)
+        engine.residual_dev(d_tus.data_ptr(), batch.bin_counts(), d_co.data_ptr(), d_sf.data_ptr(), batch.geom,
+                            d_out.data_ptr(), zero_fill=False, sf_replicated=bool(batch.sf_replicated),
+                            dense_arena=dense)
+        engine.sync()
+        assert_planes_equal(batch.geom, d_out.cpu().numpy().view(np.int16), ref)
+
+
 def test_config3_full_4k(engine, c_oracle):
     batch = synth.residual_batch("4k10", n_pics=1)
     got = engine.residual(batch)

@@ -172,6 +172,16 @@ def test_sat16_is_lossless_for_reconstruction():
         assert np.array_equal(a, b)
 
 
+def test_densified_batch_is_the_same_batch():
+    """ResidualBatch.densified(): arena re-laid in descriptor order, same TBs, same residual."""
+    from oracle import c_oracle
+    batch = synth.residual_batch("1080p8", n_pics=1)
+    dense = batch.densified()
+    assert dense.dense_small_bins() and not batch.dense_small_bins()
+    assert dense.coeffs.size == batch.samples()
+    assert np.array_equal(c_oracle.residual_batch(batch), c_oracle.residual_batch(dense))
+
+
 @pytest.mark.parametrize("name", ["1080p8", "4k10"])
 @pytest.mark.parametrize("stress", [False, True])
 def test_c_oracle_equals_numpy_oracle(c_oracle, name, stress):

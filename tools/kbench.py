@@ -35,10 +35,11 @@ def main():
         d_out = torch.empty(batch.geom.total_elems() * 2, dtype=torch.uint8, device=dev)
         bins = batch.bin_counts()
         rep = bool(batch.sf_replicated) and not force_general
+        dense = batch.dense_small_bins() and not os.environ.get("P265_KB_NO_DENSE")
 
         def run():
             eng.residual_dev(d_tus.data_ptr(), bins, d_co.data_ptr(), d_sf.data_ptr() if d_sf is not None else None,
-                             batch.geom, d_out.data_ptr(), zero_fill=False, sf_replicated=rep)
+                             batch.geom, d_out.data_ptr(), zero_fill=False, sf_replicated=rep, dense_arena=dense)
         for _ in range(3):
             run()
         torch.cuda.synchronize()
@@ -152,6 +153,8 @@ def bench_overlap(args, eng, dev, stream, to_dev):
 
 def bench_residual(args, time_residual):
     full = synth.residual_batch("4k10", n_pics=args.pics, n_unique=min(2, args.pics))
+    if not os.environ.get("P265_KB_NO_DENSE"):
+        full = full.densified()   # arena in descriptor order: P265_RES_DENSE_ARENA applies
     time_residual(full, "4k10 mix, SF replicated")
     if not args.quick:
         time_residual(full, "4k10 mix, SF general", force_general=True)
