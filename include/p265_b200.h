@@ -10,8 +10,9 @@
  * re-cut at picture granularity: the host packs every coded TB of
  * a batch of pictures into a descriptor list + coefficient arena and one call
  * produces the residual planes; a second call applies SAO to reconstructed planes.
- * p265_b200/{scaling,transform,sao}.py bind these entry points with ctypes and keep
- * the reference's per-TB names on top.
+ * p265_b200/{_lib,engine}.py bind these entry points with ctypes; the drop-in modules
+ * p265_b200/dropin/{scaling,transform,reconstruction,sao,sld}.py keep the reference's
+ * per-TB names on top.
  *
  * All entry points return 0 on success or a negative p265_status; the message of
  * the last failure on the calling thread is available from p265_last_error().
@@ -30,7 +31,7 @@
 extern "C" {
 #endif
 
-#define P265_ABI_VERSION 1
+#define P265_ABI_VERSION 2
 
 typedef enum p265_status {
     P265_OK = 0,
@@ -61,6 +62,21 @@ typedef struct p265_tu_desc {
 #define P265_TU_INTRA 8u  /* selects matrixId (scaling.py:33-42)                     */
 #define P265_TU_PRESCALED 16u /* arena already holds d[] (pu.scaled_samples): skip 8.6.3;
                                  only with scaling_factor == NULL                      */
+#define P265_TU_LEVELS8 32u   /* packed coefficient stream only: this TB's levels are int8 */
+
+/* Packed coefficient stream -- the compact host -> device transport of TransCoeffLevel
+ * (p265_residual_batch_packed).  The parser's natural output is sparse: it knows every
+ * significant position when it stores a level (tu.py:331).  One record per coded TB, at byte
+ * offset 4 * coeff_off of the stream:
+ *     significance bitmap   N*N bits, bit y*N + x of the TB in byte (y*N + x) >> 3, bit
+ *                           (y*N + x) & 7 (least significant bit first)
+ *     levels                the non-zero TransCoeffLevel values in raster order of their
+ *                           bitmap bits: int8 each when the descriptor has P265_TU_LEVELS8
+ *                           (every |level| of the TB <= 127), little-endian int16 otherwise
+ *     padding               to the next multiple of 4 bytes
+ * A 4K 10-bit picture of the benchmark mix is 25.1 MB as a dense int16 arena and 3.7 MB as a
+ * stream.  The device expands it (unpack_kernel) into its own dense arena in descriptor
+ * order and runs the same residual kernels on it.                                          */
 
 /* Planes of a batch of 4:2:0 pictures inside ONE buffer: picture p, component c
  * starts at element p * pic_stride + plane_off[c]; rows are stride_{y,c} elements
@@ -126,11 +142,23 @@ int p265_device_count(void);
 int p265_ctx_create(int device, void *stream, p265_ctx **out);
 int p265_ctx_destroy(p265_ctx *ctx);
 int p265_sync(p265_ctx *ctx);
-/* enable != 0: the host-buffer batch entry points (p265_residual_batch, p265_sao_batch,
- * p265_reconstruct_batch, p265_deblock_batch) return as soon as their copies and kernels are
- * queued on the context's stream; results are valid after p265_sync().  The caller keeps the
- * host buffers alive (and, for real overlap, page-locked) until then.  Several asynchronous
- * contexts let the H2D copy of one picture overlap the D2H copy of another.               */
+/* enable != 0: the host-buffer batch entry points (p265_residual_batch[_packed],
+ * p265_sao_batch, p265_loop_filter_batch, p265_reconstruct_batch, p265_deblock_batch) return as
+ * soon as their copies and kernels are queued on the context's stream; results are valid
+ * after p265_sync().  Contract of an asynchronous context:
+ *   - every host buffer passed in (inputs AND outputs) stays alive and unmodified until the
+ *     next p265_sync() on this context; page-locked memory is needed for real overlap
+ *     (pageable memory makes the copies synchronous, not wrong);
+ *   - the context owns ONE stream and ONE set of grow-only device scratch buffers which the
+ *     entry points share (the descriptor / parameter slot, the plane slots): calls queued on
+ *     one context are serialised by that stream, which is what keeps the sharing correct --
+ *     a call never starts before the previous call's kernels and copies have finished.  A
+ *     scratch buffer that has to grow while work is queued is released only after the stream
+ *     has drained (the call that grows it synchronises first);
+ *   - p265_dequant_batch, p265_ref_literal_batch and p265_idct_1d (parity helpers) are always
+ *     synchronous;
+ *   - overlap between pictures comes from SEVERAL contexts (one per in-flight picture): the
+ *     H2D copy of one picture then overlaps the kernels and the D2H copy of another.        */
 int p265_ctx_set_async(p265_ctx *ctx, int enable);
 int p265_sm_count(p265_ctx *ctx);
 /* kernels launched through this context so far (bench.py reports it as gpu_launches) */
@@ -143,6 +171,20 @@ int p265_residual_batch(p265_ctx *ctx, const p265_tu_desc *tus, const int32_t bi
                         const uint8_t *scaling_factor /* P265_SF_BYTES or NULL = flat 16 */,
                         const p265_pic_geom *geom, int16_t *residual /* host out */,
                         int flags);
+/* same result from the packed coefficient stream (see P265_TU_LEVELS8 above): tus[i].coeff_off
+ * is the record's offset in units of 4 bytes.  What a parser that emits (position, level)
+ * pairs hands over; 4-7x fewer host -> device bytes than the dense arena.                  */
+int p265_residual_batch_packed(p265_ctx *ctx, const p265_tu_desc *tus, const int32_t bin_counts[4],
+                               const uint8_t *stream, size_t stream_bytes,
+                               const uint8_t *scaling_factor, const p265_pic_geom *geom,
+                               int16_t *residual /* host out */, int flags);
+/* device-resident variant: d_arena (>= sum of N*N int16 over all TBs, + 32 bytes) and d_tus_out
+ * (n descriptors) receive the expanded arena and the descriptors that index it             */
+int p265_residual_batch_packed_dev(p265_ctx *ctx, const p265_tu_desc *d_tus,
+                                   const int32_t bin_counts[4], const uint8_t *d_stream,
+                                   const uint8_t *d_scaling_factor, const p265_pic_geom *geom,
+                                   int16_t *d_arena, p265_tu_desc *d_tus_out, int16_t *d_residual,
+                                   int flags);
 /* same, every pointer already resident in device memory; asynchronous on the stream */
 int p265_residual_batch_dev(p265_ctx *ctx, const p265_tu_desc *d_tus,
                             const int32_t bin_counts[4], const int16_t *d_coeffs,
@@ -168,6 +210,9 @@ int p265_idct_1d(p265_ctx *ctx, const int32_t *x, int log2size, int tr_type, int
  * no_filter: NULL or n_pics * ceil(h/8) * ceil(w/8) bytes, non-zero = luma 8x8 block
  * (and its 4x4 chroma blocks) keeps its samples (pcm + pcm_loop_filter_disabled,
  * cu_transquant_bypass).                                                           */
+/* out == rec is allowed for the host entry point (the device works out of place): with
+ * page-locked memory only the CTBs that SAO modifies are then written back.  out != rec: the
+ * plane rows of `out` are written, row padding and inter-plane gaps are left untouched.      */
 int p265_sao_batch(p265_ctx *ctx, const void *rec /* host in */, void *out /* host out */,
                    const p265_pic_geom *geom, int ctb_log2, const p265_sao_ctb *params,
                    const uint8_t *no_filter);
@@ -194,10 +239,26 @@ int p265_deblock_batch(p265_ctx *ctx, void *planes /* host in/out */, const p265
 int p265_deblock_batch_dev(p265_ctx *ctx, void *d_planes, const p265_pic_geom *geom, int ctb_log2,
                            const p265_dbk_blk *d_blk, const p265_dbk_ctb *d_ctb);
 
+/* ---- loop filters in one call (8.7.2 then 8.7.3) --------------------------------- */
+/* Deblocking in place, then SAO, on reconstructed planes: ONE host -> device copy of the planes
+ * and ONE copy back instead of the two round trips of p265_deblock_batch + p265_sao_batch.
+ * The reference parses the controls (pps.py:121-131, slice.py:170-179) and has neither filter.
+ * blk / dbk_ctb == NULL skips deblocking (slice_deblocking_filter_disabled_flag everywhere),
+ * sao == NULL skips SAO.  `planes` is read and overwritten with the final samples.           */
+int p265_loop_filter_batch(p265_ctx *ctx, void *planes /* host in/out */, const p265_pic_geom *geom,
+                           int ctb_log2, const p265_dbk_blk *blk, const p265_dbk_ctb *dbk_ctb,
+                           const p265_sao_ctb *sao, const uint8_t *no_filter);
+
 /* ---- measurement helpers ------------------------------------------------------- */
 /* Register-resident integer-pipe microbenchmark; kind: 0 IMAD, 1 IADD3, 2 IMAD+IADD3
  * interleaved, 3 DP2A, 4 SHF, 5 DP2A+IADD3.  Returns lane-ops per second.           */
 int p265_int_peak(p265_ctx *ctx, int kind, double *ops_per_s, double *ms);
+/* Plain page-locked host <-> device copies on two streams at once (what the host entry points
+ * are made of): `bytes` per direction and repetition, both directions concurrently.  Returns
+ * the two rates in bytes per second -- the ceiling bench.py compares its end-to-end number
+ * with (e2e.pcie_frac).  One direction alone: pass NULL for the other rate.                   */
+int p265_pcie_probe(p265_ctx *ctx, size_t bytes, int reps, double *h2d_bytes_per_s,
+                    double *d2h_bytes_per_s);
 
 #ifdef __cplusplus
 }

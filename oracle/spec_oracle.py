@@ -567,3 +567,36 @@ def deblock_picture(planes, blk, ctb, ctb_log2, bit_depth_y, bit_depth_c):
                     for x in range(0, wc, 4):
                         _deblock_chroma_segment(out[c], blk, ctb, ctb_log2, bit_depth_c, False, x, y, c)
     return [o.astype(np.asarray(p).dtype) for o, p in zip(out, planes)]
+
+
+# ------------------------------------------------------- packed coefficient stream (transport)
+# Independent restatement of the record format documented in include/p265_b200.h (per TB:
+# significance bitmap, N*N bits, bit y*N + x, least significant bit first; then the non-zero
+# TransCoeffLevel values in raster order, int8 when the descriptor carries the LEVELS8 flag, else
+# little-endian int16; records start at 4 * coeff_off).  It is how the parser's (position, level)
+# stores (tu.py:331) travel; TB by TB, plain loops -- checker only.
+_TU_LEVELS8 = 32
+
+
+def unpack_stream(tus, stream):
+    """(descriptors indexing a packed stream, stream bytes) -> (descriptors indexing a dense arena,
+    int16 arena): TB i's N*N levels, row-major [y][x], at 16 * coeff_off of the result."""
+    stream = np.asarray(stream, dtype=np.uint8)
+    out_tus = np.array(tus, copy=True)
+    sizes = 1 << (2 * out_tus["log2n"].astype(np.int64))
+    offs = np.concatenate(([0], np.cumsum(sizes)[:-1])) if len(sizes) else np.zeros(0, np.int64)
+    arena = np.zeros(int(sizes.sum()), dtype=np.int16)
+    for i, t in enumerate(tus):
+        nn = int(sizes[i])
+        rec = int(t["coeff_off"]) * 4
+        bits = np.unpackbits(stream[rec:rec + nn // 8], bitorder="little")[:nn].astype(bool)
+        k = int(bits.sum())
+        lv0 = rec + nn // 8
+        if int(t["flags"]) & _TU_LEVELS8:
+            lv = stream[lv0:lv0 + k].view(np.int8).astype(np.int16)
+        else:
+            lv = stream[lv0:lv0 + 2 * k].copy().view("<i2").astype(np.int16)
+        arena[int(offs[i]):int(offs[i]) + nn][bits] = lv
+    out_tus["coeff_off"] = (offs >> 4).astype(np.uint32)
+    out_tus["flags"] = out_tus["flags"] & np.uint8(0xFF ^ _TU_LEVELS8)
+    return out_tus, arena

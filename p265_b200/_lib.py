@@ -28,7 +28,10 @@ SYMBOLS = (
     "p265_ref_literal_batch", "p265_idct_1d", "p265_sao_batch", "p265_sao_batch_dev",
     "p265_reconstruct_batch", "p265_reconstruct_batch_dev", "p265_deblock_batch",
     "p265_deblock_batch_dev", "p265_int_peak",
+    "p265_residual_batch_packed", "p265_residual_batch_packed_dev", "p265_loop_filter_batch",
+    "p265_pcie_probe",
 )
+ABI_VERSION = 2
 
 
 class Geom(C.Structure):
@@ -80,6 +83,10 @@ def load():
     lib.p265_deblock_batch.argtypes = [vp, vp, C.POINTER(Geom), C.c_int, vp, vp]
     lib.p265_deblock_batch_dev.argtypes = [vp, vp, C.POINTER(Geom), C.c_int, vp, vp]
     lib.p265_int_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.p265_residual_batch_packed.argtypes = [vp, vp, i64p, vp, C.c_size_t, vp, C.POINTER(Geom), vp, C.c_int]
+    lib.p265_residual_batch_packed_dev.argtypes = [vp, vp, i64p, vp, vp, C.POINTER(Geom), vp, vp, vp, C.c_int]
+    lib.p265_loop_filter_batch.argtypes = [vp, vp, C.POINTER(Geom), C.c_int, vp, vp, vp, vp]
+    lib.p265_pcie_probe.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = lib
     return lib
 

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libp265b200.so")
-SOURCES = ["api.cu", "residual.cu", "sao.cu", "recon.cu", "deblock.cu", "peak.cu"]
+SOURCES = ["api.cu", "residual.cu", "coeffs.cu", "transport.cu", "sao.cu", "recon.cu", "deblock.cu", "peak.cu"]
 HEADERS = ["internal.h", "residual_core.cuh", os.path.join(REPO, "include", "p265_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "internal.h"
@@ -66,8 +67,10 @@ static int check_geom(const p265_pic_geom *g, int elem_align) {
 // host-side validation of a descriptor list (host entry points only)
 // *dense_small = inside the 8x8 bin and inside the 4x4 bin every TB's coefficients directly follow
 // the previous TB's (what P265_RES_DENSE_ARENA asserts on the device entry point)
+// stream != nullptr: the descriptors index a packed coefficient stream of n_coeffs BYTES (records of
+// significance bitmap + levels, include/p265_b200.h) instead of a dense arena of n_coeffs int16
 static int check_tus(const p265_tu_desc *tus, const int32_t bin_counts[4], size_t n_coeffs, const p265_pic_geom *g,
-                     bool have_table, bool *dense_small) {
+                     bool have_table, bool *dense_small, const uint8_t *stream = nullptr) {
     // one pass over caller data, on the latency path of every host call: plane limits and the qP
     // bound are hoisted per component, the rare diagnostics are formatted only on failure
     const int wmax[3] = {g->width, g->width / 2, g->width / 2}, hmax[3] = {g->height, g->height / 2, g->height / 2};
@@ -78,13 +81,36 @@ static int check_tus(const p265_tu_desc *tus, const int32_t bin_counts[4], size_
         if (bin_counts[b] < 0) return set_error(P265_EINVAL, "negative bin count");
         const int log2n = 5 - b, n = 1 << log2n;
         const uint32_t units = (uint32_t)(n * n) / 16, z0 = bin_counts[b] ? tus[k].coeff_off : 0u;
-        const unsigned bad_flags = (log2n != 2 ? (P265_TU_SKIP | P265_TU_DST) : 0u) | (have_table ? P265_TU_PRESCALED : 0u);
+        const unsigned bad_flags = (log2n != 2 ? (P265_TU_SKIP | P265_TU_DST) : 0u) | (have_table ? P265_TU_PRESCALED : 0u) |
+                                   (stream ? 0u : P265_TU_LEVELS8) | 0xc0u;
+        const size_t bm_bytes = (size_t)(n * n) / 8;
         for (int32_t i = 0; i < bin_counts[b]; i++, k++) {
             const p265_tu_desc &t = tus[k];
             const unsigned c = t.c_idx < 3 ? t.c_idx : 0;
+            bool in_range;
+            if (stream) {  // record = bitmap + one level per set bit, inside the stream
+                const size_t off = (size_t)t.coeff_off * 4;
+                in_range = off + bm_bytes <= n_coeffs;
+                if (in_range) {
+                    size_t nnz = 0;
+                    if (bm_bytes >= 8) {
+                        for (size_t w = 0; w < bm_bytes; w += 8) {
+                            uint64_t v;
+                            memcpy(&v, stream + off + w, 8);
+                            nnz += (size_t)__builtin_popcountll(v);
+                        }
+                    } else {
+                        uint16_t v;
+                        memcpy(&v, stream + off, 2);
+                        nnz = (size_t)__builtin_popcount(v);
+                    }
+                    in_range = off + bm_bytes + nnz * ((t.flags & P265_TU_LEVELS8) ? 1 : 2) <= n_coeffs;
+                }
+            } else {
+                in_range = (size_t)t.coeff_off * 16 + (size_t)n * n <= n_coeffs;
+            }
             const bool ok = t.log2n == log2n && t.c_idx <= 2 && ((t.x | t.y) & (n - 1)) == 0 && t.x + n <= wmax[c] &&
-                            t.y + n <= hmax[c] && t.pic < g->n_pics &&
-                            (size_t)t.coeff_off * 16 + (size_t)n * n <= n_coeffs && !(t.flags & bad_flags) &&
+                            t.y + n <= hmax[c] && t.pic < g->n_pics && in_range && !(t.flags & bad_flags) &&
                             !((t.flags & P265_TU_DST) && t.c_idx != 0) && t.qp <= qmax[c];
             if (b >= 2) not_dense |= t.coeff_off ^ (z0 + (uint32_t)i * units);
             if (ok) continue;
@@ -96,8 +122,12 @@ static int check_tus(const p265_tu_desc *tus, const int32_t bin_counts[4], size_
                 return set_error(P265_EINVAL, "descriptor %lld: %dx%d block at (%d,%d) outside the %dx%d plane or "
                                  "unaligned", (long long)k, n, n, t.x, t.y, wmax[c], hmax[c]);
             if (t.pic >= g->n_pics) return set_error(P265_EINVAL, "descriptor %lld: picture %d", (long long)k, t.pic);
-            if ((size_t)t.coeff_off * 16 + (size_t)n * n > n_coeffs)
-                return set_error(P265_EINVAL, "descriptor %lld: coefficients beyond the arena", (long long)k);
+            if (!in_range)
+                return set_error(P265_EINVAL, "descriptor %lld: coefficients beyond the %s", (long long)k,
+                                 stream ? "packed stream" : "arena");
+            if (t.flags & (stream ? 0xc0u : (0xc0u | P265_TU_LEVELS8)))
+                return set_error(P265_EINVAL, "descriptor %lld: flags 0x%02x not defined for this entry point", (long long)k,
+                                 t.flags);
             if ((t.flags & P265_TU_SKIP) && log2n != 2)
                 return set_error(P265_EINVAL, "descriptor %lld: transform_skip on a %dx%d block", (long long)k, n, n);
             if ((t.flags & P265_TU_DST) && (log2n != 2 || t.c_idx != 0))
@@ -170,7 +200,7 @@ int p265_ctx_destroy(p265_ctx *ctx) {
     if (!ctx) return P265_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < p265_ctx::kScratchSlots; i++)
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->xtus) cudaFree(ctx->xtus);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
@@ -229,6 +259,9 @@ int p265_residual_batch(p265_ctx *ctx, const p265_tu_desc *tus, const int32_t bi
     bool dense_small = false;
     if ((rc = check_tus(tus, bin_counts, n_coeffs, geom, scaling_factor != nullptr, &dense_small))) return rc;
     flags = dense_small ? (flags | P265_RES_DENSE_ARENA) : (flags & ~P265_RES_DENSE_ARENA);  // found out here, not asserted
+    // the whole buffer travels back to the host (row padding and inter-plane gaps included) and the
+    // scratch slot is shared with other entry points: never return stale bytes of an earlier call
+    flags |= P265_RES_ZERO_FILL;
     P265_CUDA(cudaSetDevice(ctx->device));
     void *d_tus, *d_co, *d_sf = nullptr, *d_out;
     const size_t out_bytes = sizeof(int16_t) * (size_t)geom->pic_stride * geom->n_pics;
@@ -250,17 +283,83 @@ int p265_residual_batch(p265_ctx *ctx, const p265_tu_desc *tus, const int32_t bi
     return finish(ctx);
 }
 
+static int64_t dense_elems(const int32_t bin_counts[4]) {
+    int64_t e = 0;
+    for (int b = 0; b < 4; b++) e += (int64_t)(bin_counts[b] > 0 ? bin_counts[b] : 0) << (2 * (5 - b));
+    return e;
+}
+
+int p265_residual_batch_packed_dev(p265_ctx *ctx, const p265_tu_desc *d_tus, const int32_t bin_counts[4],
+                                   const uint8_t *d_stream, const uint8_t *d_sf, const p265_pic_geom *geom,
+                                   int16_t *d_arena, p265_tu_desc *d_tus_out, int16_t *d_residual, int flags) {
+    if (!ctx || !bin_counts || !d_residual) return set_error(P265_EINVAL, "p265_residual_batch_packed_dev: NULL argument");
+    int rc = check_geom(geom, 8);
+    if (rc) return rc;
+    int64_t n = 0;
+    for (int b = 0; b < 4; b++) {
+        if (bin_counts[b] < 0) return set_error(P265_EINVAL, "negative bin count");
+        n += bin_counts[b];
+    }
+    if (n && (!d_tus || !d_stream || !d_arena || !d_tus_out))
+        return set_error(P265_EINVAL, "descriptor / stream / arena pointer is NULL");
+    P265_CUDA(cudaSetDevice(ctx->device));
+    if ((rc = launch_unpack(ctx, d_tus, bin_counts, d_stream, d_arena, d_tus_out))) return rc;
+    // the arena comes out in descriptor order: the small bins are dense by construction
+    return launch_residual(ctx, d_tus_out, bin_counts, d_arena, d_sf, geom, d_residual, flags | P265_RES_DENSE_ARENA);
+}
+
+int p265_residual_batch_packed(p265_ctx *ctx, const p265_tu_desc *tus, const int32_t bin_counts[4], const uint8_t *stream,
+                               size_t stream_bytes, const uint8_t *scaling_factor, const p265_pic_geom *geom,
+                               int16_t *residual, int flags) {
+    if (!ctx || !bin_counts || !residual) return set_error(P265_EINVAL, "p265_residual_batch_packed: NULL argument");
+    int rc = check_geom(geom, 8);
+    if (rc) return rc;
+    int64_t n = 0;
+    for (int b = 0; b < 4; b++) n += bin_counts[b] > 0 ? bin_counts[b] : 0;
+    if (n && (!tus || !stream)) return set_error(P265_EINVAL, "descriptor / stream pointer is NULL");
+    bool dense_small = false;
+    if ((rc = check_tus(tus, bin_counts, stream_bytes, geom, scaling_factor != nullptr, &dense_small, stream ? stream : (const uint8_t *)""))) return rc;
+    flags |= P265_RES_ZERO_FILL;  // see p265_residual_batch
+    P265_CUDA(cudaSetDevice(ctx->device));
+    void *d_tus, *d_st, *d_sf = nullptr, *d_out, *d_arena, *d_tus2;
+    const size_t out_bytes = sizeof(int16_t) * (size_t)geom->pic_stride * geom->n_pics;
+    if ((rc = ensure(ctx, 0, sizeof(p265_tu_desc) * (size_t)n, &d_tus))) return rc;
+    if ((rc = ensure(ctx, 1, stream_bytes + 64, &d_st))) return rc;
+    if ((rc = ensure(ctx, 2, out_bytes, &d_out))) return rc;
+    if ((rc = ensure(ctx, 8, sizeof(int16_t) * (size_t)dense_elems(bin_counts) + 64, &d_arena))) return rc;
+    if ((rc = ensure(ctx, 9, sizeof(p265_tu_desc) * (size_t)n, &d_tus2))) return rc;
+    if (scaling_factor) {
+        if ((rc = ensure(ctx, 3, P265_SF_BYTES, &d_sf))) return rc;
+        P265_CUDA(cudaMemcpyAsync(d_sf, scaling_factor, P265_SF_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (n) {
+        P265_CUDA(cudaMemcpyAsync(d_tus, tus, sizeof(p265_tu_desc) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        P265_CUDA(cudaMemcpyAsync(d_st, stream, stream_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = launch_unpack(ctx, (const p265_tu_desc *)d_tus, bin_counts, (const uint8_t *)d_st, (int16_t *)d_arena,
+                                (p265_tu_desc *)d_tus2)))
+            return rc;
+    }
+    rc = launch_residual(ctx, (const p265_tu_desc *)d_tus2, bin_counts, (const int16_t *)d_arena, (const uint8_t *)d_sf,
+                         geom, (int16_t *)d_out, flags | P265_RES_DENSE_ARENA);
+    if (rc) return rc;
+    P265_CUDA(cudaMemcpyAsync(residual, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return finish(ctx);
+}
+
 int p265_dequant_batch(p265_ctx *ctx, const p265_tu_desc *tus, int32_t n_tus, const int16_t *coeffs, size_t n_coeffs,
                        const uint8_t *scaling_factor, int bit_depth_y, int bit_depth_c, int16_t *scaled) {
     if (!ctx || n_tus < 0 || (n_tus && (!tus || !coeffs || !scaled)))
         return set_error(P265_EINVAL, "p265_dequant_batch: bad argument");
     if (bit_depth_y < 8 || bit_depth_y > 12 || bit_depth_c < 8 || bit_depth_c > 12)
         return set_error(P265_EINVAL, "bit depths %d/%d outside 8..12", bit_depth_y, bit_depth_c);
+    const int qmax[3] = {51 + 6 * (bit_depth_y - 8), 51 + 6 * (bit_depth_c - 8), 51 + 6 * (bit_depth_c - 8)};
     for (int32_t i = 0; i < n_tus; i++) {
         const int n = 1 << tus[i].log2n;
         if (tus[i].log2n < 2 || tus[i].log2n > 5 || tus[i].c_idx > 2 ||
             (size_t)tus[i].coeff_off * 16 + (size_t)n * n > n_coeffs)
             return set_error(P265_EINVAL, "descriptor %d is malformed", i);
+        if (tus[i].qp > qmax[tus[i].c_idx])  // same bound as check_tus: keeps make_params' qp / 6 and shifts defined
+            return set_error(P265_EINVAL, "descriptor %d: qP %d out of range", i, tus[i].qp);
     }
     if (n_tus == 0) return P265_OK;
     P265_CUDA(cudaSetDevice(ctx->device));
@@ -290,7 +389,8 @@ int p265_ref_literal_batch(p265_ctx *ctx, const p265_tu_desc *tus, int32_t n_tus
         return set_error(P265_EINVAL, "p265_ref_literal_batch: bad argument");
     for (int32_t i = 0; i < n_tus; i++) {
         const int n = 1 << tus[i].log2n;
-        if (tus[i].log2n < 2 || tus[i].log2n > 5 || (size_t)tus[i].coeff_off * 16 + (size_t)n * n > n_coeffs)
+        if (tus[i].log2n < 2 || tus[i].log2n > 5 || tus[i].c_idx > 2 ||
+            (size_t)tus[i].coeff_off * 16 + (size_t)n * n > n_coeffs)
             return set_error(P265_EINVAL, "descriptor %d is malformed", i);
     }
     if (n_tus == 0) return P265_OK;
@@ -355,18 +455,61 @@ int p265_sao_batch_dev(p265_ctx *ctx, const void *d_rec, void *d_out, const p265
     return launch_sao(ctx, d_rec, d_out, geom, ctb_log2, d_params, d_no_filter);
 }
 
-int p265_sao_batch(p265_ctx *ctx, const void *rec, void *out, const p265_pic_geom *geom, int ctb_log2,
-                   const p265_sao_ctb *params, const uint8_t *no_filter) {
-    if (!ctx || !rec || !out || !params || !geom) return set_error(P265_EINVAL, "p265_sao_batch: NULL argument");
-    int bytes;
-    int rc = check_sao(geom, ctb_log2, &bytes);
-    if (rc) return rc;
+// Device-visible address of a host buffer when it is page-locked and mapped (cudaHostAlloc / cudaHostRegister
+// memory under unified addressing), nullptr for pageable memory.  P265_NO_ZERO_COPY=1 disables the direct
+// write-back (A/B measurements).
+static void *mapped_host_pointer(const void *p) {
+    static int off = -1;
+    if (off < 0) {
+        const char *e = getenv("P265_NO_ZERO_COPY");
+        off = (e && *e && *e != '0') ? 1 : 0;
+    }
+    if (off) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
+// D2H of the plane rows only (row padding and inter-plane gaps of the host buffer stay untouched)
+static int copy_planes_to_host(p265_ctx *ctx, void *host, const void *dev, const p265_pic_geom *g, int bytes) {
+    for (int p = 0; p < g->n_pics; p++)
+        for (int c = 0; c < 3; c++) {
+            const size_t off = ((size_t)p * g->pic_stride + g->plane_off[c]) * bytes;
+            const size_t pitch = (size_t)(c ? g->stride_c : g->stride_y) * bytes;
+            const size_t row = (size_t)(c ? g->width / 2 : g->width) * bytes;
+            const size_t rows = (size_t)(c ? g->height / 2 : g->height);
+            if (row == pitch) {
+                P265_CUDA(cudaMemcpyAsync((char *)host + off, (const char *)dev + off, row * rows, cudaMemcpyDeviceToHost, ctx->stream));
+            } else {
+                P265_CUDA(cudaMemcpy2DAsync((char *)host + off, pitch, (const char *)dev + off, pitch, row, rows,
+                                            cudaMemcpyDeviceToHost, ctx->stream));
+            }
+        }
+    return P265_OK;
+}
+
+static int check_sao_params(const p265_pic_geom *geom, int ctb_log2, const p265_sao_ctb *params, size_t *n_ctbs) {
     const int ctb = 1 << ctb_log2;
     const size_t ctbs = (size_t)((geom->width + ctb - 1) / ctb) * ((geom->height + ctb - 1) / ctb) * geom->n_pics;
     for (size_t i = 0; i < ctbs; i++)
         for (int c = 0; c < 3; c++)
             if (params[i].type[c] > 2 || params[i].eo_class[c] > 3 || params[i].band_pos[c] > 31)
                 return set_error(P265_EINVAL, "SAO parameters of CTB %zu component %d out of range", i, c);
+    *n_ctbs = ctbs;
+    return P265_OK;
+}
+
+int p265_sao_batch(p265_ctx *ctx, const void *rec, void *out, const p265_pic_geom *geom, int ctb_log2,
+                   const p265_sao_ctb *params, const uint8_t *no_filter) {
+    if (!ctx || !rec || !out || !params || !geom) return set_error(P265_EINVAL, "p265_sao_batch: NULL argument");
+    int bytes;
+    int rc = check_sao(geom, ctb_log2, &bytes);
+    if (rc) return rc;
+    size_t ctbs;
+    if ((rc = check_sao_params(geom, ctb_log2, params, &ctbs))) return rc;
     P265_CUDA(cudaSetDevice(ctx->device));
     const size_t plane_bytes = (size_t)bytes * geom->pic_stride * geom->n_pics;
     const size_t nf_bytes = (size_t)((geom->width + 7) / 8) * ((geom->height + 7) / 8) * geom->n_pics;
@@ -380,11 +523,15 @@ int p265_sao_batch(p265_ctx *ctx, const void *rec, void *out, const p265_pic_geo
         if ((rc = ensure(ctx, 7, nf_bytes, &d_nf))) return rc;
         P265_CUDA(cudaMemcpyAsync(d_nf, no_filter, nf_bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
-    // row padding and inter-plane gaps of `out` keep the caller's content of `rec`
-    P265_CUDA(cudaMemcpyAsync(d_out, d_rec, plane_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     if ((rc = launch_sao(ctx, d_rec, d_out, geom, ctb_log2, (const p265_sao_ctb *)d_par, (const uint8_t *)d_nf)))
         return rc;
-    P265_CUDA(cudaMemcpyAsync(out, d_out, plane_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    // In place on a page-locked host buffer: the host already holds every sample SAO leaves alone, so only
+    // the CTB components with sao type != 0 cross the bus again, stored by a kernel straight into the
+    // caller's buffer.  Otherwise: the plane rows by the copy engine.
+    void *h_dev = out == rec ? mapped_host_pointer(out) : nullptr;
+    if (h_dev) rc = launch_sao_writeback(ctx, d_out, h_dev, geom, ctb_log2, (const p265_sao_ctb *)d_par);
+    else rc = copy_planes_to_host(ctx, out, d_out, geom, bytes);
+    if (rc) return rc;
     return finish(ctx);
 }
 
@@ -428,6 +575,24 @@ static int check_deblock(const p265_pic_geom *geom, int ctb_log2, int *bytes) {
     return P265_OK;
 }
 
+static int check_deblock_maps(const p265_pic_geom *geom, int ctb_log2, const p265_dbk_blk *blk, const p265_dbk_ctb *ctb,
+                              size_t *n_blk_out, size_t *n_ctb_out) {
+    const int cs = 1 << ctb_log2;
+    const size_t n_blk = (size_t)(geom->width / 8) * (geom->height / 8) * geom->n_pics;
+    const size_t n_ctb = (size_t)((geom->width + cs - 1) / cs) * ((geom->height + cs - 1) / cs) * geom->n_pics;
+    for (size_t i = 0; i < n_blk; i++)
+        if ((blk[i] & 3) == 3 || ((blk[i] >> 2) & 3) == 3 || ((blk[i] >> 4) & 3) == 3 || ((blk[i] >> 6) & 3) == 3)
+            return set_error(P265_EINVAL, "edge map entry %zu holds a boundary strength of 3", i);
+    for (size_t i = 0; i < n_ctb; i++)
+        if (ctb[i].beta_offset_div2 < -6 || ctb[i].beta_offset_div2 > 6 || ctb[i].tc_offset_div2 < -6 ||
+            ctb[i].tc_offset_div2 > 6 || ctb[i].cb_qp_offset < -12 || ctb[i].cb_qp_offset > 12 ||
+            ctb[i].cr_qp_offset < -12 || ctb[i].cr_qp_offset > 12)
+            return set_error(P265_EINVAL, "deblocking parameters of CTB %zu out of range", i);
+    *n_blk_out = n_blk;
+    *n_ctb_out = n_ctb;
+    return P265_OK;
+}
+
 int p265_deblock_batch_dev(p265_ctx *ctx, void *d_planes, const p265_pic_geom *geom, int ctb_log2,
                            const p265_dbk_blk *d_blk, const p265_dbk_ctb *d_ctb) {
     if (!ctx || !d_planes || !d_blk || !d_ctb || !geom)
@@ -445,17 +610,8 @@ int p265_deblock_batch(p265_ctx *ctx, void *planes, const p265_pic_geom *geom, i
     int bytes;
     int rc = check_deblock(geom, ctb_log2, &bytes);
     if (rc) return rc;
-    const int cs = 1 << ctb_log2;
-    const size_t n_blk = (size_t)(geom->width / 8) * (geom->height / 8) * geom->n_pics;
-    const size_t n_ctb = (size_t)((geom->width + cs - 1) / cs) * ((geom->height + cs - 1) / cs) * geom->n_pics;
-    for (size_t i = 0; i < n_blk; i++)
-        if ((blk[i] & 3) == 3 || ((blk[i] >> 2) & 3) == 3 || ((blk[i] >> 4) & 3) == 3 || ((blk[i] >> 6) & 3) == 3)
-            return set_error(P265_EINVAL, "edge map entry %zu holds a boundary strength of 3", i);
-    for (size_t i = 0; i < n_ctb; i++)
-        if (ctb[i].beta_offset_div2 < -6 || ctb[i].beta_offset_div2 > 6 || ctb[i].tc_offset_div2 < -6 ||
-            ctb[i].tc_offset_div2 > 6 || ctb[i].cb_qp_offset < -12 || ctb[i].cb_qp_offset > 12 ||
-            ctb[i].cr_qp_offset < -12 || ctb[i].cr_qp_offset > 12)
-            return set_error(P265_EINVAL, "deblocking parameters of CTB %zu out of range", i);
+    size_t n_blk, n_ctb;
+    if ((rc = check_deblock_maps(geom, ctb_log2, blk, ctb, &n_blk, &n_ctb))) return rc;
     P265_CUDA(cudaSetDevice(ctx->device));
     const size_t plane_bytes = (size_t)bytes * geom->pic_stride * geom->n_pics;
     void *d_pix, *d_blk, *d_ctb;
@@ -469,6 +625,60 @@ int p265_deblock_batch(p265_ctx *ctx, void *planes, const p265_pic_geom *geom, i
         return rc;
     P265_CUDA(cudaMemcpyAsync(planes, d_pix, plane_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return finish(ctx);
+}
+
+int p265_loop_filter_batch(p265_ctx *ctx, void *planes, const p265_pic_geom *geom, int ctb_log2, const p265_dbk_blk *blk,
+                           const p265_dbk_ctb *dbk_ctb, const p265_sao_ctb *sao, const uint8_t *no_filter) {
+    if (!ctx || !planes || !geom) return set_error(P265_EINVAL, "p265_loop_filter_batch: NULL argument");
+    if ((blk == nullptr) != (dbk_ctb == nullptr))
+        return set_error(P265_EINVAL, "p265_loop_filter_batch: edge map and per-CTB deblocking parameters go together");
+    if (!blk && !sao) return set_error(P265_EINVAL, "p265_loop_filter_batch: neither deblocking nor SAO requested");
+    int bytes;
+    int rc = blk ? check_deblock(geom, ctb_log2, &bytes) : P265_OK;
+    if (!rc && sao) rc = check_sao(geom, ctb_log2, &bytes);
+    if (rc) return rc;
+    size_t n_blk = 0, n_ctb = 0, n_sao = 0;
+    if (blk && (rc = check_deblock_maps(geom, ctb_log2, blk, dbk_ctb, &n_blk, &n_ctb))) return rc;
+    if (sao && (rc = check_sao_params(geom, ctb_log2, sao, &n_sao))) return rc;
+    P265_CUDA(cudaSetDevice(ctx->device));
+    const size_t plane_bytes = (size_t)bytes * geom->pic_stride * geom->n_pics;
+    const size_t nf_bytes = (size_t)((geom->width + 7) / 8) * ((geom->height + 7) / 8) * geom->n_pics;
+    void *d_pix, *d_out = nullptr, *d_blk = nullptr, *d_ctb = nullptr, *d_par = nullptr, *d_nf = nullptr;
+    if ((rc = ensure(ctx, 2, plane_bytes, &d_pix))) return rc;
+    P265_CUDA(cudaMemcpyAsync(d_pix, planes, plane_bytes, cudaMemcpyHostToDevice, ctx->stream));  // the one H2D of the planes
+    if (blk) {
+        if ((rc = ensure(ctx, 0, sizeof(p265_dbk_blk) * n_blk, &d_blk))) return rc;
+        if ((rc = ensure(ctx, 7, sizeof(p265_dbk_ctb) * n_ctb, &d_ctb))) return rc;
+        P265_CUDA(cudaMemcpyAsync(d_blk, blk, sizeof(p265_dbk_blk) * n_blk, cudaMemcpyHostToDevice, ctx->stream));
+        P265_CUDA(cudaMemcpyAsync(d_ctb, dbk_ctb, sizeof(p265_dbk_ctb) * n_ctb, cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = launch_deblock(ctx, d_pix, geom, ctb_log2, (const p265_dbk_blk *)d_blk, (const p265_dbk_ctb *)d_ctb)))
+            return rc;
+    }
+    const void *d_final = d_pix;
+    if (sao) {
+        if ((rc = ensure(ctx, 6, plane_bytes, &d_out))) return rc;
+        if ((rc = ensure(ctx, 10, sizeof(p265_sao_ctb) * n_sao, &d_par))) return rc;
+        P265_CUDA(cudaMemcpyAsync(d_par, sao, sizeof(p265_sao_ctb) * n_sao, cudaMemcpyHostToDevice, ctx->stream));
+        if (no_filter) {
+            if ((rc = ensure(ctx, 11, nf_bytes, &d_nf))) return rc;
+            P265_CUDA(cudaMemcpyAsync(d_nf, no_filter, nf_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        if ((rc = launch_sao(ctx, d_pix, d_out, geom, ctb_log2, (const p265_sao_ctb *)d_par, (const uint8_t *)d_nf)))
+            return rc;
+        d_final = d_out;
+    }
+    // the one copy back.  Without deblocking the host still holds every sample SAO leaves alone (see p265_sao_batch)
+    void *h_dev = (!blk && sao) ? mapped_host_pointer(planes) : nullptr;
+    if (h_dev) rc = launch_sao_writeback(ctx, d_final, h_dev, geom, ctb_log2, (const p265_sao_ctb *)d_par);
+    else rc = copy_planes_to_host(ctx, planes, d_final, geom, bytes);
+    if (rc) return rc;
+    return finish(ctx);
+}
+
+int p265_pcie_probe(p265_ctx *ctx, size_t bytes, int reps, double *h2d_bytes_per_s, double *d2h_bytes_per_s) {
+    if (!ctx || (!h2d_bytes_per_s && !d2h_bytes_per_s)) return set_error(P265_EINVAL, "p265_pcie_probe: NULL argument");
+    P265_CUDA(cudaSetDevice(ctx->device));
+    return run_pcie_probe(ctx, bytes, reps, h2d_bytes_per_s, d2h_bytes_per_s);
 }
 
 int p265_int_peak(p265_ctx *ctx, int kind, double *ops_per_s, double *ms) {

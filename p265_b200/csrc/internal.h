@@ -16,8 +16,10 @@ struct p265_ctx {
     bool async_mode = false;  // host entry points return after enqueueing (p265_ctx_set_async)
     uint64_t launches = 0;  // kernels launched by this context (bench.py: gpu_launches)
     // grow-only device scratch for the host-buffer entry points
-    void *scratch[8] = {nullptr};
-    size_t scratch_bytes[8] = {0};
+    // (slots are shared between entry points; the context's single stream serialises their use)
+    enum { kScratchSlots = 12 };
+    void *scratch[kScratchSlots] = {nullptr};
+    size_t scratch_bytes[kScratchSlots] = {0};
     void *xtus = nullptr;  // expanded TU descriptors of the current residual launch (grow-only)
     size_t xtus_bytes = 0;
 };
@@ -35,6 +37,13 @@ int cuda_error(cudaError_t e, const char *what, const char *file, int line);
 
 int launch_residual(p265_ctx *ctx, const p265_tu_desc *d_tus, const int32_t bin_counts[4], const int16_t *d_coeffs,
                     const uint8_t *d_sf, const p265_pic_geom *g, int16_t *d_out, int flags);
+int launch_unpack(p265_ctx *ctx, const p265_tu_desc *d_tus, const int32_t bin_counts[4], const uint8_t *d_stream,
+                  int16_t *d_arena, p265_tu_desc *d_tus_out);
+// SAO write-back into page-locked host memory: only the CTB components with sao type != 0 (h_out is the
+// device-visible address of the caller's buffer, which already holds the unfiltered samples)
+int launch_sao_writeback(p265_ctx *ctx, const void *d_out, void *h_out, const p265_pic_geom *g, int ctb_log2,
+                         const p265_sao_ctb *d_params);
+int run_pcie_probe(p265_ctx *ctx, size_t bytes, int reps, double *h2d, double *d2h);
 int launch_dequant(p265_ctx *ctx, const p265_tu_desc *d_tus, int n_tus, const int16_t *d_coeffs, const uint8_t *d_sf,
                    int bit_depth_y, int bit_depth_c, int16_t *d_scaled);
 int launch_ref_literal(p265_ctx *ctx, const p265_tu_desc *d_tus, int n_tus, const int16_t *d_scaled, int32_t *d_out);

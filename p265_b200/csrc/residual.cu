@@ -423,6 +423,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, BinCfg<BIN>::ctas) residual
     else if (BIN == 1) run_bin<4, SF>(a, gw, stride, lane, wbase, smem);
     else if (BIN == 2) run_bin8<SF>(a, gw, stride, lane, wbase, smem);
     else run_bin4<SF>(a, gw, stride, lane, wbase, smem);
+    // Make the chain transitive: a bin launched with programmatic stream serialization may start
+    // (and finish) before its predecessor has finished, so "the last bin is complete" would not
+    // imply "every bin is complete" for whatever follows on the stream (the D2H copy of the planes,
+    // SAO, the next call's expand_kernel overwriting the expanded records).  Every bin therefore
+    // waits for its predecessor grid before it exits -- after its own work, so the overlap is kept
+    // (a no-op for a grid launched without the attribute; the first bin already waited above).
+    if (!a.wait_prev) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // One thread per TB: public descriptor -> expanded record (residual_core.cuh: expand_desc).

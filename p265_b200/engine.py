@@ -13,13 +13,13 @@ import threading
 import numpy as np
 
 from . import _lib
-from .picture import DBK_CTB, SAO_CTB, SF_BYTES, TU_DESC, PicGeom, ResidualBatch
+from .picture import DBK_CTB, SAO_CTB, SF_BYTES, TU_DESC, PackedResidualBatch, PicGeom, ResidualBatch
 
 
 class Engine:
     def __init__(self, device: int = 0, stream: int | None = None):
         lib = _lib.load()
-        if lib.p265_abi_version() != 1:
+        if lib.p265_abi_version() != _lib.ABI_VERSION:
             raise RuntimeError("libp265b200.so ABI mismatch")
         handle = C.c_void_p()
         _lib.check(lib.p265_ctx_create(int(device), C.c_void_p(stream) if stream else None,
@@ -63,13 +63,16 @@ class Engine:
         return int(self._lib.p265_launch_count(self._ctx))
 
     # ------------------------------------------------------------------- residual
-    def residual(self, batch: ResidualBatch, out: np.ndarray | None = None) -> np.ndarray:
-        """Residual planes (flat int16 buffer laid out by `batch.geom`) of a batch."""
+    def residual(self, batch, out: np.ndarray | None = None) -> np.ndarray:
+        """Residual planes (flat int16 buffer laid out by `batch.geom`) of a batch: a
+        `ResidualBatch` (dense coefficient arena) or a `PackedResidualBatch` (packed stream)."""
         g = batch.geom
         if out is None:
             out = np.empty(g.total_elems(), dtype=np.int16)
         elif out.dtype != np.int16 or out.size < g.total_elems():
             raise ValueError("out must be int16 with at least geom.total_elems() elements")
+        if isinstance(batch, PackedResidualBatch):
+            return self._residual_packed(batch, out)
         tus = _lib.as_array(batch.tus, TU_DESC)
         co = _lib.as_array(batch.coeffs, np.int16)
         sf = None
@@ -86,6 +89,33 @@ class Engine:
             _lib.ptr(sf), C.byref(gs), _lib.ptr(out), flags))
         self._hold(tus, co, sf, out)
         return out
+
+    def _residual_packed(self, batch: PackedResidualBatch, out: np.ndarray) -> np.ndarray:
+        tus = _lib.as_array(batch.tus, TU_DESC)
+        st = _lib.as_array(batch.stream, np.uint8)
+        sf = None
+        if batch.scaling_factor is not None:
+            sf = _lib.as_array(batch.scaling_factor, np.uint8)
+            if sf.size != SF_BYTES:
+                raise ValueError("scaling_factor table must have %d bytes" % SF_BYTES)
+        gs = _lib.geom_struct(batch.geom)
+        flags = _lib.RES_SF_REPLICATED if (sf is not None and batch.sf_replicated) else 0
+        _lib.check(self._lib.p265_residual_batch_packed(
+            self._ctx, _lib.ptr(tus), _lib.bins(batch.bin_counts()), _lib.ptr(st), st.size,
+            _lib.ptr(sf), C.byref(gs), _lib.ptr(out), flags))
+        self._hold(tus, st, sf, out)
+        return out
+
+    def residual_packed_dev(self, d_tus: int, bin_counts, d_stream: int, d_sf: int | None, geom: PicGeom,
+                            d_arena: int, d_tus_out: int, d_out: int, zero_fill: bool = False,
+                            sf_replicated: bool = False):
+        """Device-resident packed batch: unpack_kernel into `d_arena` / `d_tus_out`, then the residual kernels."""
+        gs = _lib.geom_struct(geom)
+        flags = (_lib.RES_ZERO_FILL if zero_fill else 0) | (_lib.RES_SF_REPLICATED if (d_sf and sf_replicated) else 0)
+        _lib.check(self._lib.p265_residual_batch_packed_dev(
+            self._ctx, C.c_void_p(d_tus), _lib.bins(bin_counts), C.c_void_p(d_stream),
+            C.c_void_p(d_sf) if d_sf else None, C.byref(gs), C.c_void_p(d_arena), C.c_void_p(d_tus_out),
+            C.c_void_p(d_out), flags))
 
     def residual_dev(self, d_tus: int, bin_counts, d_coeffs: int, d_sf: int | None, geom: PicGeom,
                      d_out: int, zero_fill: bool = False, sf_replicated: bool = False, dense_arena: bool = False):
@@ -131,13 +161,22 @@ class Engine:
 
     # ------------------------------------------------------------------------ SAO
     def sao(self, rec: np.ndarray, geom: PicGeom, ctb_log2: int, params: np.ndarray,
-            no_filter: np.ndarray | None = None, out: np.ndarray | None = None) -> np.ndarray:
+            no_filter: np.ndarray | None = None, out: np.ndarray | None = None,
+            inplace: bool = False) -> np.ndarray:
+        """SAO (8.7.3) of reconstructed planes.  `inplace` (or out is rec): the host buffer `rec` itself
+        receives the result -- with page-locked memory only the CTBs SAO modifies are written back.
+        Otherwise `out` (a copy of `rec` when not given, so that row padding carries over) gets the
+        plane rows."""
         dtype = np.uint8 if max(geom.bit_depth_y, geom.bit_depth_c) <= 8 else np.uint16
         rec = _lib.as_array(rec, dtype).reshape(-1)
         if rec.size < geom.total_elems():
             raise ValueError("rec buffer smaller than the geometry")
-        if out is None:
-            out = np.empty_like(rec)
+        if inplace:
+            if not rec.flags.writeable:
+                raise ValueError("inplace SAO needs a writable rec buffer")
+            out = rec
+        elif out is None:
+            out = rec.copy()
         par = _lib.as_array(params, SAO_CTB)
         ctb = 1 << ctb_log2
         ctbs = ((geom.width + ctb - 1) // ctb) * ((geom.height + ctb - 1) // ctb) * geom.n_pics
@@ -212,7 +251,54 @@ class Engine:
         _lib.check(self._lib.p265_deblock_batch_dev(self._ctx, C.c_void_p(d_planes), C.byref(gs), int(ctb_log2),
                                                     C.c_void_p(d_blk), C.c_void_p(d_ctb)))
 
+    # ---------------------------------------------------------- loop filters, fused
+    def loop_filter(self, planes: np.ndarray, geom: PicGeom, ctb_log2: int, blk=None, dbk_ctb=None,
+                    sao_params=None, no_filter=None) -> np.ndarray:
+        """Deblocking (8.7.2, when `blk` / `dbk_ctb` are given) then SAO (8.7.3, when `sao_params` is
+        given) in ONE host round trip, in place on `planes` (one H2D + one D2H of the planes instead of
+        two of each through deblock() + sao())."""
+        dtype = np.uint8 if max(geom.bit_depth_y, geom.bit_depth_c) <= 8 else np.uint16
+        if not (isinstance(planes, np.ndarray) and planes.dtype == dtype and planes.flags["C_CONTIGUOUS"]
+                and planes.flags.writeable):
+            raise ValueError("planes must be a writable C-contiguous %s array (filtered in place)" % np.dtype(dtype).name)
+        buf = planes.reshape(-1)
+        if buf.size < geom.total_elems():
+            raise ValueError("planes buffer smaller than the geometry")
+        cs = 1 << ctb_log2
+        n_ctb = ((geom.width + cs - 1) // cs) * ((geom.height + cs - 1) // cs) * geom.n_pics
+        b = c = par = nf = None
+        if (blk is None) != (dbk_ctb is None):
+            raise ValueError("edge map and per-CTB deblocking parameters go together")
+        if blk is not None:
+            b = _lib.as_array(blk, np.uint16).reshape(-1)
+            c = _lib.as_array(dbk_ctb, DBK_CTB).reshape(-1)
+            if geom.width % 8 or geom.height % 8:
+                raise ValueError("picture size must be a multiple of 8")
+            if b.size != (geom.width // 8) * (geom.height // 8) * geom.n_pics or c.size != n_ctb:
+                raise ValueError("edge map / CTB parameter tables do not match the geometry")
+        if sao_params is not None:
+            par = _lib.as_array(sao_params, SAO_CTB).reshape(-1)
+            if par.size != n_ctb:
+                raise ValueError("expected %d SAO CTB records, got %d" % (n_ctb, par.size))
+            if no_filter is not None:
+                nf = _lib.as_array(no_filter, np.uint8).reshape(-1)
+                if nf.size != ((geom.width + 7) // 8) * ((geom.height + 7) // 8) * geom.n_pics:
+                    raise ValueError("no_filter map does not match the geometry")
+        gs = _lib.geom_struct(geom)
+        _lib.check(self._lib.p265_loop_filter_batch(self._ctx, _lib.ptr(buf), C.byref(gs), int(ctb_log2), _lib.ptr(b),
+                                                    _lib.ptr(c), _lib.ptr(par), _lib.ptr(nf)))
+        self._hold(buf, b, c, par, nf)
+        return planes
+
     # ---------------------------------------------------------------- measurement
+    def pcie_probe(self, n_bytes: int = 256 << 20, reps: int = 8, h2d: bool = True, d2h: bool = True):
+        """(H2D, D2H) bytes per second of plain page-locked copies, both directions at once when both
+        are requested (None for a direction that was not)."""
+        a, b = C.c_double(), C.c_double()
+        _lib.check(self._lib.p265_pcie_probe(self._ctx, int(n_bytes), int(reps), C.byref(a) if h2d else None,
+                                             C.byref(b) if d2h else None))
+        return (a.value if h2d else None), (b.value if d2h else None)
+
     def int_peak(self, kind: int):
         ops, ms = C.c_double(), C.c_double()
         _lib.check(self._lib.p265_int_peak(self._ctx, int(kind), C.byref(ops), C.byref(ms)))

@@ -26,6 +26,8 @@ TU_DST = 1        # trType = 1: 4x4 luma intra (8.6.4.2; transform.py:97)
 TU_SKIP = 2       # transform_skip_flag (tu.py:142-143)
 TU_BYPASS = 4     # cu_transquant_bypass_flag (cu.py:102-105)
 TU_INTRA = 8      # CuPredMode == MODE_INTRA -> matrixId (scaling.py:33-42)
+TU_PRESCALED = 16  # arena holds d[] already (pu.scaled_samples)
+TU_LEVELS8 = 32   # packed coefficient stream: this TB's levels are int8
 
 #: mirrors `p265_sao_ctb` (24 bytes)
 SAO_CTB = np.dtype([("type", "u1", 3), ("band_pos", "u1", 3), ("eo_class", "u1", 3),
@@ -164,10 +166,17 @@ class ResidualBatch:
         return self._dense
 
 
+def size_kind_order(tus: np.ndarray) -> np.ndarray:
+    """Permutation that sorts descriptors largest TBs first -- the order `p265_residual_*`
+    requires -- and, inside a size, clusters the kinds (normal, DST, transform-skip, bypass) so
+    that a warp's lanes take the same path; stable otherwise (picture / decoding order kept).
+    The one ordering rule of the packed format: the packer and the synthetic workloads share it."""
+    key = (-(tus["log2n"].astype(np.int32)) * 16 + (tus["flags"] & (TU_DST | TU_SKIP | TU_BYPASS)))
+    return np.argsort(key, kind="stable")
+
+
 def sort_by_size(tus: np.ndarray) -> np.ndarray:
-    """Stable sort, largest TBs first -- the order `p265_residual_*` requires."""
-    order = np.argsort(-tus["log2n"].astype(np.int16), kind="stable")
-    return np.ascontiguousarray(tus[order])
+    return np.ascontiguousarray(tus[size_kind_order(tus)])
 
 
 def sf_offset(size_id: int, matrix_id: int) -> int:
@@ -208,3 +217,79 @@ def pack_scaling_factor(sf: dict) -> np.ndarray:
         off = sf_offset(s, m)
         out[off:off + n * n] = f.T.reshape(-1)
     return out
+
+
+# ------------------------------------------------------------- packed coefficient stream
+@dataclass
+class PackedResidualBatch:
+    """A residual batch whose coefficients travel as the packed stream of include/p265_b200.h
+    (per TB: significance bitmap + non-zero levels, int8 when they fit) instead of a dense int16
+    arena.  `tus[i].coeff_off` = byte offset of TB i's record / 4.  This is what a parser emits
+    naturally -- it stores (position, level) pairs (tu.py:331) -- and what crosses PCIe."""
+    geom: PicGeom
+    tus: np.ndarray                         # TU_DESC sorted like ResidualBatch.tus; flags may carry TU_LEVELS8
+    stream: np.ndarray                      # uint8
+    scaling_factor: np.ndarray | None = None
+    covers_all: bool = False
+    sf_replicated: bool | None = None
+    bins: tuple | None = None
+
+    def __post_init__(self):
+        if self.scaling_factor is not None and self.sf_replicated is None:
+            self.sf_replicated = sf_is_replicated(self.scaling_factor)
+
+    bin_counts = ResidualBatch.bin_counts
+    samples = ResidualBatch.samples
+
+
+def pack_coefficients(tus: np.ndarray, coeffs: np.ndarray):
+    """(descriptors indexing a dense arena, arena) -> (descriptors indexing a packed stream, stream).
+    Records are laid out in descriptor order.  Vectorised per TB size; the parser-side emitter
+    (emit.PictureSink) writes the same format TB by TB."""
+    tus = tus.copy()
+    n_tb = len(tus)
+    l2 = tus["log2n"].astype(np.int64)
+    nnz = np.zeros(n_tb, np.int64)
+    wide = np.zeros(n_tb, bool)
+    per_size = {}
+    for k in (5, 4, 3, 2):
+        idx = np.nonzero(l2 == k)[0]
+        if not idx.size:
+            continue
+        nn = 1 << (2 * k)
+        blocks = coeffs[(tus["coeff_off"][idx].astype(np.int64) * 16)[:, None] + np.arange(nn, dtype=np.int64)[None, :]]
+        nz = blocks != 0
+        nnz[idx] = nz.sum(axis=1)
+        wide[idx] = ((blocks > 127) | (blocks < -128)).any(axis=1)
+        per_size[k] = (idx, blocks, nz)
+    bm_bytes = (1 << (2 * l2)) >> 3
+    rec = (bm_bytes + nnz * np.where(wide, 2, 1) + 3) & ~3
+    rec_off = np.concatenate(([0], np.cumsum(rec)[:-1])) if n_tb else np.zeros(0, np.int64)
+    stream = np.zeros(int(rec.sum()), np.uint8)
+    for k, (idx, blocks, nz) in per_size.items():
+        nn = 1 << (2 * k)
+        bm = np.packbits(nz, axis=1, bitorder="little")
+        stream[(rec_off[idx][:, None] + np.arange(nn // 8, dtype=np.int64)[None, :]).ravel()] = bm.ravel()
+        vals = blocks[nz]                                    # TB after TB, raster order inside a TB
+        cnt = nnz[idx]
+        start = np.concatenate(([0], np.cumsum(cnt)[:-1]))
+        rank = np.arange(int(cnt.sum()), dtype=np.int64) - np.repeat(start, cnt)
+        w_rep = np.repeat(wide[idx], cnt)
+        pos = np.repeat(rec_off[idx] + nn // 8, cnt) + rank * np.where(w_rep, 2, 1)
+        u = vals.astype(np.int16).view(np.uint16)
+        stream[pos] = (u & 0xFF).astype(np.uint8)
+        stream[pos[w_rep] + 1] = (u[w_rep] >> 8).astype(np.uint8)
+    if stream.size >> 2 > 0xFFFFFFFF:
+        raise ValueError("packed stream too large for 32-bit record offsets")
+    tus["coeff_off"] = (rec_off >> 2).astype(np.uint32)
+    tus["flags"] = (tus["flags"] & ~np.uint8(TU_LEVELS8)) | np.where(wide, 0, TU_LEVELS8).astype(np.uint8)
+    return tus, stream
+
+
+def _packed(self) -> PackedResidualBatch:
+    """The same batch with its coefficients as a packed stream (host -> device transport)."""
+    tus, stream = pack_coefficients(self.tus, self.coeffs)
+    return PackedResidualBatch(self.geom, tus, stream, self.scaling_factor, self.covers_all, self.sf_replicated, self.bins)
+
+
+ResidualBatch.packed = _packed

@@ -19,7 +19,7 @@ from __future__ import annotations
 import numpy as np
 
 from .picture import (AVAIL_ALL, SAO_CTB, TU_BYPASS, TU_DESC, TU_DST, TU_INTRA, TU_SKIP,
-                      PicGeom, ResidualBatch, pack_scaling_factor)
+                      PicGeom, ResidualBatch, pack_scaling_factor, sort_by_size)
 from .scaling_list import default_scaling_factor
 
 CONFIGS = {
@@ -145,11 +145,8 @@ def residual_batch(name: str, n_pics: int = 1, seed: int | None = None, stress: 
         off += a.size
     geom = PicGeom(cfg["width"], cfg["height"], n_pics, cfg["bit_depth"], cfg["bit_depth"])
     sf = pack_scaling_factor(default_scaling_factor()) if cfg["scaling_lists"] else None
-    # kinds cluster inside a size bin (normal, DST, TS, bypass) so warps stay uniform
-    all_t = np.concatenate(tus)
-    key = (-(all_t["log2n"].astype(np.int32)) * 16 + (all_t["flags"] & (TU_SKIP | TU_BYPASS | TU_DST)))
-    order = np.argsort(key, kind="stable")
-    return ResidualBatch(geom=geom, tus=np.ascontiguousarray(all_t[order]),
+    # same ordering rule as the product packer (picture.sort_by_size: size, then kind)
+    return ResidualBatch(geom=geom, tus=sort_by_size(np.concatenate(tus)),
                          coeffs=np.concatenate(arenas), scaling_factor=sf, covers_all=True)
 
 

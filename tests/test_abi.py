@@ -19,7 +19,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), "libp265b200.so does not export %s" % name
     assert declared == set(_lib.SYMBOLS)
-    assert lib.p265_abi_version() == 1
+    assert lib.p265_abi_version() == _lib.ABI_VERSION
 
 
 def test_struct_layouts_match_the_header():
