@@ -12,9 +12,14 @@ classes, per-CTB parameters).  Metric: Mpixel/s, pixel = luma sample position of
   value     device-resident inputs/outputs, CUDA events on the launching stream, max
             over ranks (N > 1: one process per GPU, pictures/streams partitioned by
             rank, no data-path collective -> weak scaling)
-  e2e       same step through the public host API (Engine.residual / Engine.sao ->
-            C-ABI p265_residual_batch / p265_sao_batch) from pinned host buffers,
-            H2D and D2H copies inside the timed region
+  e2e       same step through the public host API (Engine.residual on the packed
+            coefficient stream / Engine.sao in place -> C-ABI p265_residual_batch_packed /
+            p265_sao_batch) from pinned host buffers, H2D and D2H inside the timed region;
+            e2e.pcie = plain pinned copies both ways at once on the same box (all ranks
+            together), e2e.pcie_frac = how close the step is to that ceiling
+  sustained the same device-resident step repeated for >= 2 s (clocks and power sampled)
+  verify    after the timed region, pictures of the timed device buffers are compared
+            with oracle/spec_oracle.c (checker only; --no-verify skips it)
   roofline  dominant kernel vs measured HBM bandwidth (MEASURED_PEAKS.json), dense
             algorithmic bytes: residual 4 B/sample + 16 B/TB, SAO
             4 B/sample at 10 bits
@@ -90,7 +95,11 @@ class ClockSampler(threading.Thread):
                     reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.samples.append((float(mhz), int(reasons)))
+                try:
+                    mw = nv.nvmlDeviceGetPowerUsage(self.h)
+                except Exception:
+                    mw = 0
+                self.samples.append((float(mhz), int(reasons), mw / 1000.0))
             except Exception as e:  # pragma: no cover
                 self.err = repr(e)
                 break
@@ -103,11 +112,41 @@ class ClockSampler(threading.Thread):
                 "sw_power_cap": 0x4}
         sm = [s[0] for s in self.samples]
         reasons = sorted(n for n, b in bits.items() if any(s[1] & b for s in self.samples))
+        pw = [s[2] for s in self.samples if s[2] > 0]
         out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
-               "reasons": reasons, "samples": len(sm), "how": "NVML, every 2 ms during the timed region"}
+               "reasons": reasons, "samples": len(sm), "power_w": round(float(np.median(pw)), 1) if pw else None,
+               "how": "NVML, every 2 ms during the timed region"}
         if self.err:
             out["error"] = self.err
         return out
+
+
+def host_placement(local: int):
+    """Pin this rank to the CPUs next to its GPU (sysfs local_cpulist / numa_node of the PCI
+    device) so that page-locked buffers are first-touched on that NUMA node.  Best effort: a
+    VM that exposes one node (numa_node = -1) leaves nothing to choose."""
+    info = {"numa_node": None, "cpus": None, "pinned": False}
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        devn = torch.cuda.get_device_properties(local).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0" % (dom, bus, devn)
+        node = int(open(path + "/numa_node").read())
+        cpus = open(path + "/local_cpulist").read().strip()
+        info["numa_node"], info["cpus"] = node, cpus
+        ids = set()
+        for part in cpus.split(","):
+            if part:
+                lo, _, hi = part.partition("-")
+                ids.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        if node >= 0 and ids and (ids & allowed) and (ids & allowed) != allowed:
+            os.sched_setaffinity(0, ids & allowed)
+            info["pinned"] = True
+    except Exception as e:  # pragma: no cover
+        info["error"] = repr(e)
+    return info
 
 
 def pinned(n_bytes):
@@ -139,12 +178,41 @@ def alg_int_ops(res):
     return float(sum(ops[k] * int((l2 == k).sum()) * (1 << (2 * k)) for k in (2, 3, 4, 5)))
 
 
+def verify_device_buffers(res, d_res, sgeom, rec, params, d_sao):
+    """Compare pictures of the buffers the timed launches wrote with oracle/spec_oracle.c: the first
+    two (the two distinct synthetic pictures) and the last one of the batch.  Raises on a mismatch."""
+    from oracle import c_oracle
+    from p265_b200.picture import PicGeom, ResidualBatch
+    c_oracle.build()
+    g = res.geom
+    pics = sorted({0, min(1, g.n_pics - 1), g.n_pics - 1})
+    one = PicGeom(g.width, g.height, 1, g.bit_depth_y, g.bit_depth_c)
+    got_res = d_res.cpu().numpy().view(np.int16)
+    got_sao = d_sao.cpu().numpy().view(rec.dtype)
+    sg1 = PicGeom(sgeom.width, sgeom.height, 1, sgeom.bit_depth_y, sgeom.bit_depth_c)
+    for p in pics:
+        t = np.ascontiguousarray(res.tus[res.tus["pic"] == p])
+        t["pic"] = 0
+        sub = ResidualBatch(one, t, res.coeffs, res.scaling_factor, res.covers_all, res.sf_replicated)
+        want = c_oracle.residual_batch(sub, zero_fill=False)
+        have = got_res[p * g.pic_stride:(p + 1) * g.pic_stride]
+        for c in range(3):
+            if not np.array_equal(one.plane_view(have, 0, c), one.plane_view(want, 0, c)):
+                raise SystemExit("bench.py --verify: residual planes of picture %d differ from the oracle" % p)
+        r1 = rec[p * sgeom.pic_stride:(p + 1) * sgeom.pic_stride]
+        want = c_oracle.sao_batch(r1, sg1, 6, params[p:p + 1])
+        have = got_sao[p * sgeom.pic_stride:(p + 1) * sgeom.pic_stride]
+        for c in range(3):
+            if not np.array_equal(sg1.plane_view(have, 0, c), sg1.plane_view(want, 0, c)):
+                raise SystemExit("bench.py --verify: SAO planes of picture %d differ from the oracle" % p)
+    return {"pictures": pics, "residual_equal_oracle": True, "sao_equal_oracle": True,
+            "oracle": "oracle/spec_oracle.c (checker; after the timed region)"}
+
+
 # ------------------------------------------------------------------ GPU arm
 def run_gpu(args):
-    # NCCL prints its version banner (and NCCL_DEBUG output) to the C-level stdout; rank 0's stdout must
-    # hold the JSON line only: everything written to fd 1 before the final print goes to stderr
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # rank 0's stdout must hold the JSON line only: everything written to fd 1 before the final print
+    # (library banners included) goes to stderr
     sys.stdout.flush()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
@@ -165,9 +233,12 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    # The path has no collective (north star: no NCCL): the ranks only meet for the benchmark's barrier
+    # and the MAX over ranks of the timed region -- host scalars, exchanged over gloo (TCP, 127.0.0.1)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("gloo")
     dev = torch.device("cuda", local)
+    host = host_placement(local)   # CPU affinity / NUMA node of this rank's GPU, before any pinned allocation
 
     # stream s -> GPU s mod G: with G streams on G GPUs every rank owns
     # exactly one synthetic stream (seed 26510 + s); per-GPU work is fixed -> weak scaling
@@ -229,6 +300,27 @@ def run_gpu(args):
     ms_res = timed(residual, args.steps) / args.steps
     ms_sao = timed(sao, args.steps) / args.steps
     clocks = sampler.stop()
+    # ---- sustained leg: the same step back to back for >= args.sustain seconds (INT-bound kernels follow
+    # the SM clock: this shows what the burst number is worth under a seconds-long load)
+    sustained = None
+    if args.sustain > 0:
+        per_chunk = max(args.steps, int(0.25 / max(ms_total / args.steps * 1e-3, 1e-6)))
+        sam2 = ClockSampler(local)
+        sam2.start()
+        t_ms, n_steps = 0.0, 0
+        while t_ms < args.sustain * 1e3:
+            t_ms += timed(step, per_chunk)
+            n_steps += per_chunk
+        c2 = sam2.stop()
+        sustained = {"seconds": round(t_ms / 1e3, 3), "steps": n_steps, "ms_per_step": round(t_ms / n_steps, 4),
+                     "value": round(PIC_W * PIC_H * args.pics * n_steps / (t_ms * 1e-3) / 1e6, 1),
+                     "sm_mhz_median": c2["sm_mhz"], "power_w_median": c2["power_w"], "reasons": c2["reasons"],
+                     "what": "this rank's device-resident step repeated back to back (events per ~0.25 s chunk, "
+                             "no host synchronisation inside a chunk)"}
+    # ---- verify: the buffers the timed kernels wrote, against the oracle (checker only, after the timing)
+    verify = None
+    if args.verify:
+        verify = verify_device_buffers(res, d_res, sgeom, rec, params, d_sao)
     # the neighbouring kernels of the path (reconstruction, deblocking), rank 0 only,
     # outside the metric: same pictures, device resident, in place / out of place as they run
     other = {}
@@ -275,17 +367,19 @@ def run_gpu(args):
             "alg_int_ops": alg_int_ops(c2)}
         del c_tus, c_co, c_out
 
-    ms_total_max = partition.max_over_ranks(ms_total, dev)
+    ms_total_max = partition.max_over_ranks(ms_total)
     pixels_step = PIC_W * PIC_H * args.pics * world
     value = pixels_step * args.steps / (ms_total_max * 1e-3) / 1e6
 
     # ---- end to end through the host API (pinned host buffers, copies timed) ----
-    # A decoder hands pictures over one at a time, so every picture is its own host call:
-    # Engine.residual (H2D descriptors + coefficients -> residual kernels -> D2H planes) then
-    # Engine.sao (H2D reconstructed planes + parameters -> SAO kernel -> D2H planes).  The
-    # calls go round-robin to a few ASYNCHRONOUS contexts (p265_ctx_set_async: one stream
-    # each), so the H2D copy of one picture overlaps the D2H copy of another on the two copy
-    # engines; every context is synchronised before the step ends.
+    # A decoder hands pictures over one at a time, so every picture is its own pair of host calls:
+    #   Engine.residual(packed batch)  H2D descriptors + packed coefficient stream -> unpack + residual
+    #                                  kernels -> D2H residual planes
+    #   Engine.sao(..., inplace=True)  H2D reconstructed planes + parameters -> SAO kernel -> the CTBs SAO
+    #                                  modified are written back into the same page-locked buffer
+    # The calls go round-robin to a few ASYNCHRONOUS contexts (p265_ctx_set_async: one stream each), so
+    # the H2D copy of one picture overlaps the D2H copy of another; every context is synchronised before
+    # the step ends.  --e2e-dense times the round-1 transport (dense arena, out-of-place SAO) instead.
     e2e_pics = max(1, args.e2e_pics)
     n_ctx = max(1, min(args.e2e_ctx, e2e_pics))
     engs = [Engine(local) for _ in range(n_ctx)]
@@ -299,36 +393,86 @@ def run_gpu(args):
         v[...] = a
         return t_, v
 
-    from p265_b200.picture import ResidualBatch
+    from p265_b200.picture import PackedResidualBatch, ResidualBatch
     keep, uniq = [], []
     for u in range(min(2, e2e_pics)):           # two distinct pictures, inputs shared read-only
         r1, g1, rec1, par1 = make_workload(1, 26510 + stream_id + 100 * (u + 1))
-        k_tus, h_tus = pin(r1.tus)
-        k_co, h_co = pin(r1.coeffs)
-        k_rec, h_rec = pin(rec1)
+        if args.e2e_dense:
+            k_tus, h_tus = pin(r1.tus)
+            k_co, h_co = pin(r1.coeffs)
+            hb = ResidualBatch(r1.geom, h_tus, h_co, r1.scaling_factor, r1.covers_all)
+        else:
+            p1 = r1.packed()
+            k_tus, h_tus = pin(p1.tus)
+            k_co, h_co = pin(p1.stream)
+            hb = PackedResidualBatch(r1.geom, h_tus, h_co, r1.scaling_factor, r1.covers_all, bins=p1.bins)
         k_par, h_par = pin(par1)
-        keep += [k_tus, k_co, k_rec, k_par]
-        uniq.append((ResidualBatch(r1.geom, h_tus, h_co, r1.scaling_factor, r1.covers_all), g1, h_rec, h_par))
+        keep += [k_tus, k_co, k_par]
+        uniq.append((hb, g1, rec1, h_par, r1))
     items = []
     for p in range(e2e_pics):
-        hb, g1, h_rec, h_par = uniq[p % len(uniq)]
+        hb, g1, rec1, h_par, r1 = uniq[p % len(uniq)]
         k_ro = pinned(hb.geom.total_elems() * 2)
-        k_so = pinned(h_rec.nbytes)
-        keep += [k_ro, k_so]
-        items.append((hb, g1, h_rec, h_par, k_ro.numpy().view(np.int16), k_so.numpy().view(h_rec.dtype)))
+        k_rec, h_rec = pin(rec1)                # SAO works in place: every picture owns its planes
+        keep += [k_ro, k_rec]
+        h_so = None
+        if args.e2e_dense:
+            k_so = pinned(h_rec.nbytes)
+            keep.append(k_so)
+            h_so = k_so.numpy().view(h_rec.dtype)
+        items.append((hb, g1, h_rec, h_par, k_ro.numpy().view(np.int16), h_so))
+
+    pool = None
+    if args.e2e_pool:
+        # the in-process dispatcher (p265_b200/pool.py): one host thread per visible GPU, picture p -> GPU
+        # p mod G; single-process runs only (under torchrun every rank already owns one GPU)
+        from p265_b200.pool import EnginePool
+        if world > 1:
+            raise SystemExit("--e2e-pool is the single-process multi-GPU mode; do not combine it with torchrun")
+        pool = EnginePool(contexts_per_device=n_ctx)
 
     def e2e_step():
+        if pool is not None:
+            futs = []
+            for p, (hb, g1, h_rec, h_par, h_ro, h_so) in enumerate(items):
+                futs.append(pool.residual(hb, h_ro, picture=p))
+                futs.append(pool.sao(h_rec, g1, 6, h_par, out=h_so, inplace=h_so is None, picture=p))
+            for f in futs:
+                f.result()
+            return
         for p, (hb, g1, h_rec, h_par, h_ro, h_so) in enumerate(items):
             e = engs[p % n_ctx]
             e.residual(hb, h_ro)
-            e.sao(h_rec, g1, 6, h_par, out=h_so)
+            if h_so is None:
+                e.sao(h_rec, g1, 6, h_par, inplace=True)
+            else:
+                e.sao(h_rec, g1, 6, h_par, out=h_so)
         for e in engs:
             e.sync()
 
+    # the pipelined outputs of a first step on pristine inputs are the synchronous call's outputs and the
+    # oracle's (outside the timed region; later steps filter their own output again, which changes sample
+    # values but not the work: SAO's cost does not depend on them)
+    e2e_step()
+    chk = Engine(local)
+    hb, g1, h_rec, h_par, h_ro, h_so = items[-1]
+    rec_first = uniq[(e2e_pics - 1) % len(uniq)][2]
+    want_sao = chk.sao(rec_first, g1, 6, h_par)
+    if not (np.array_equal(chk.residual(hb), h_ro) and np.array_equal(want_sao, h_so if h_so is not None else h_rec)):
+        raise SystemExit("bench.py: asynchronous end-to-end outputs differ from the synchronous call")
+    if args.verify:
+        from oracle import c_oracle
+        r1 = uniq[(e2e_pics - 1) % len(uniq)][4]
+        if not (np.array_equal(c_oracle.residual_batch(r1, zero_fill=False), h_ro)
+                and np.array_equal(c_oracle.sao_batch(rec_first, g1, 6, np.asarray(h_par)), want_sao)):
+            raise SystemExit("bench.py: end-to-end outputs differ from the oracle")
+        verify["e2e_outputs_equal_oracle"] = True
+    del chk
+
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
-    for _ in range(2):
-        e2e_step()
+    e2e_step()
     barrier()
+    l_e2e = sum(e.launch_count for e in engs)
     # every step ends with all contexts synchronised, so steps are timed one by one and the
     # MEDIAN step time is reported (one PCIe hiccup on a shared host does not decide the number)
     step_s = []
@@ -337,17 +481,47 @@ def run_gpu(args):
         e2e_step()
         step_s.append(time.perf_counter() - t0)
     torch.cuda.synchronize()
+    e2e_launches = (sum(e.launch_count for e in engs) - l_e2e) // e2e_steps
+    if pool is not None:
+        e2e_launches = sum(pool.launch_counts().values()) // (e2e_steps + 2)
     dt = float(np.median(step_s))
-    e2e_value = PIC_W * PIC_H * e2e_pics * world / partition.max_over_ranks(dt, dev) / 1e6
-    h2d = sum(it[0].tus.nbytes + it[0].coeffs.nbytes + it[2].nbytes + it[3].nbytes +
-              (it[0].scaling_factor.nbytes if it[0].scaling_factor is not None else 0) for it in items)
-    d2h = sum(it[4].nbytes + it[5].nbytes for it in items)
-    # the pipelined outputs are the synchronous call's outputs (outside the timed region)
-    chk = Engine(local)
-    hb, g1, h_rec, h_par, h_ro, h_so = items[-1]
-    if not (np.array_equal(chk.residual(hb), h_ro) and np.array_equal(chk.sao(h_rec, g1, 6, h_par), h_so)):
-        raise SystemExit("bench.py: asynchronous end-to-end outputs differ from the synchronous call")
-    e2e_launches = sum(e.launch_count for e in engs) // (e2e_steps + 2)
+    dt_max = partition.max_over_ranks(dt)
+    e2e_value = PIC_W * PIC_H * e2e_pics * world / dt_max / 1e6
+
+    def sao_writeback_bytes(g1, par):
+        """Bytes p265_sao_batch writes back in place: the CTB components with sao type != 0."""
+        total = 0
+        par = np.asarray(par).reshape(-1, (g1.height + 63) // 64, (g1.width + 63) // 64)
+        for c in range(3):
+            h, w = g1.plane_shape(c)
+            cs = 64 >> (1 if c else 0)
+            ys = np.minimum(cs, h - np.arange(par.shape[1]) * cs)
+            xs = np.minimum(cs, w - np.arange(par.shape[2]) * cs)
+            area = ys[:, None] * xs[None, :]
+            total += int((area[None] * (par["type"][..., c] != 0)).sum()) * 2
+        return total
+
+    h2d = d2h = 0
+    for hb, g1, h_rec, h_par, h_ro, h_so in items:
+        h2d += hb.tus.nbytes + (hb.coeffs.nbytes if args.e2e_dense else hb.stream.nbytes) + h_rec.nbytes + h_par.nbytes
+        h2d += hb.scaling_factor.nbytes if hb.scaling_factor is not None else 0
+        d2h += h_ro.nbytes + (h_so.nbytes if h_so is not None else sao_writeback_bytes(g1, h_par))
+    # ---- the box's ceiling: plain pinned copies in both directions at once, every rank at the same time
+    barrier()
+    pc_h2d, pc_d2h = eng.pcie_probe(256 << 20, reps=8)
+    barrier()
+    pc_h2d_min = -partition.max_over_ranks(-pc_h2d)
+    pc_d2h_min = -partition.max_over_ranks(-pc_d2h)
+    pc_h2d_sum, pc_d2h_sum = partition.sum_over_ranks(pc_h2d), partition.sum_over_ranks(pc_d2h)
+    # time the step's own bytes would need at the probed rates (the slower direction decides)
+    t_floor = max(h2d / pc_h2d, d2h / pc_d2h)
+    pcie_frac = partition.max_over_ranks(t_floor) / dt_max
+    for e in engs:
+        e.close()
+    pool_info = None
+    if pool is not None:
+        pool_info = {"devices": pool.devices, "launches_per_device": pool.launch_counts(), "calls_per_device": pool.calls()}
+        pool.close()
 
     if rank != 0:
         if world > 1:
@@ -401,15 +575,34 @@ def run_gpu(args):
         "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "pics_per_step_per_gpu": e2e_pics, "steps": e2e_steps,
                 "contexts": n_ctx, "gpu_launches_per_step": int(e2e_launches),
+                "ms_per_step": round(dt_max * 1e3, 3),
+                "transport": "dense int16 arena, out-of-place SAO (round 1)" if args.e2e_dense else
+                             "packed coefficient stream (bitmap + int8/int16 levels), SAO in place with "
+                             "write-back of the modified CTBs only",
+                "pcie": {"h2d_gbs": round(pc_h2d / 1e9, 2), "d2h_gbs": round(pc_d2h / 1e9, 2),
+                         "min_over_ranks_gbs": [round(pc_h2d_min / 1e9, 2), round(pc_d2h_min / 1e9, 2)],
+                         "sum_over_ranks_gbs": [round(pc_h2d_sum / 1e9, 2), round(pc_d2h_sum / 1e9, 2)],
+                         "what": "p265_pcie_probe: 8 x 256 MB page-locked H2D and D2H copies at the same time "
+                                 "on two streams, all ranks at once (rank 0's rates; min / sum over ranks)"},
+                "pcie_frac": round(pcie_frac, 4),
+                "pcie_frac_def": "max(h2d_bytes / probed H2D rate, d2h_bytes / probed D2H rate) / step time, "
+                                 "slowest rank",
+                "achieved_gbs": {"h2d": round(h2d / dt / 1e9, 2), "d2h": round(d2h / dt / 1e9, 2)},
+                "host": host, "pool": pool_info,
                 "timing": "median of the per-step wall times (min %.2f ms, max %.2f ms)" % (
                     min(step_s) * 1e3, max(step_s) * 1e3),
                 "how": "one Engine.residual + one Engine.sao call per picture (C-ABI host entry points "
-                       "p265_residual_batch / p265_sao_batch), round-robin over asynchronous contexts "
-                       "(p265_ctx_set_async), pinned host buffers, every H2D / D2H copy inside the timed "
-                       "region, all contexts synchronised before the step ends"},
+                       "p265_residual_batch_packed / p265_sao_batch), round-robin over asynchronous contexts "
+                       "(p265_ctx_set_async), pinned host buffers, every H2D / D2H byte inside the timed "
+                       "region, all contexts synchronised before the step ends; first step on pristine "
+                       "inputs checked against the synchronous call" + (" and the oracle" if args.verify else "")},
         "gpu_launches": int(launches),
         "gpu_launches_per_step": {"expand_kernel": 1, "residual_kernel<bin 32/16/8/4>": 4, "sao_kernel": 1},
         "clocks": clocks,
+        "sustained": sustained,
+        "verify": verify,
+        "ranks": {"backend": "gloo (barrier + MAX of host scalars only)" if world > 1 else None,
+                  "collective_on_data_path": None},
         "other_kernels": other,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1),
                      "peak": peaks["hbm_gbs"], "peak_source": peak_kind, "unit": "GB/s",
@@ -579,6 +772,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-other", action="store_true", help="skip the deblocking / reconstruction kernel timings")
+    ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the sustained leg (0 = off)")
+    ap.add_argument("--no-verify", dest="verify", action="store_false",
+                    help="skip the oracle comparison of the timed buffers")
+    ap.add_argument("--e2e-dense", action="store_true", help="e2e leg with the round-1 transport (A/B)")
+    ap.add_argument("--e2e-pool", action="store_true",
+                    help="e2e leg through EnginePool over every visible GPU in this one process")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

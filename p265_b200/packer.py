@@ -33,39 +33,45 @@ def iter_tbs(img, sps):
     (N, N) row-major [y][x] view of the reference's [x][y] array."""
     for addr in sorted(img.ctus):
         for cu in _leaf_cus(img.ctus[addr]):
-            root = getattr(cu, "tu", None)
-            if root is None:
-                continue
-            intra = cu.pred_mode == MODE_INTRA
-            bypass = bool(getattr(cu, "cu_transquant_bypass_flag", 0))
-            qps = (cu.qp_y + sps.qp_bd_offset_y, cu.qp_cb + sps.qp_bd_offset_c,
-                   cu.qp_cr + sps.qp_bd_offset_c)
-            base = (TU_INTRA if intra else 0) | (TU_BYPASS if bypass else 0)
-            for leaf in root.get_leaves():
-                levels = getattr(leaf, "trans_coeff_level", None)
-                if levels is None:
-                    continue
-                ts = getattr(leaf, "transform_skip_flag", (0, 0, 0))
-                if getattr(leaf, "cbf_luma", 1):
-                    fl = base | (TU_SKIP if ts[0] else 0)
-                    if leaf.log2size == 2 and intra:
-                        fl |= TU_DST
-                    yield 0, leaf.x, leaf.y, leaf.log2size, qps[0], fl, levels[0].T
-                if leaf.log2size > 2:
-                    cx, cy, cl2 = leaf.x >> 1, leaf.y >> 1, leaf.log2size - 1
-                    cbf = (leaf.cbf_cb, leaf.cbf_cr)
-                elif getattr(leaf, "idx", 0) == 3 and leaf.parent is not None:
-                    # four 4x4 luma TBs share one 4x4 Cb + Cr pair, parsed with the 4th
-                    # sibling at the first sibling's position (tu.py:128-135)
-                    first = leaf.parent.children[0]
-                    cx, cy, cl2 = first.x >> 1, first.y >> 1, 2
-                    cbf = (first.cbf_cb, first.cbf_cr)
-                else:
-                    continue
-                for c in (1, 2):
-                    if cbf[c - 1]:
-                        fl = base | (TU_SKIP if ts[c] else 0)
-                        yield c, cx, cy, cl2, qps[c], fl, levels[c].T
+            yield from iter_cu_tbs(cu, sps)
+
+
+def iter_cu_tbs(cu, sps):
+    """The coded TBs of ONE leaf CU (same tuples as iter_tbs): what the parser-side emitter
+    (emit.PictureSink) consumes the moment the CU's QP is known (cu.py:487)."""
+    root = getattr(cu, "tu", None)
+    if root is None:
+        return
+    intra = cu.pred_mode == MODE_INTRA
+    bypass = bool(getattr(cu, "cu_transquant_bypass_flag", 0))
+    qps = (cu.qp_y + sps.qp_bd_offset_y, cu.qp_cb + sps.qp_bd_offset_c,
+           cu.qp_cr + sps.qp_bd_offset_c)
+    base = (TU_INTRA if intra else 0) | (TU_BYPASS if bypass else 0)
+    for leaf in root.get_leaves():
+        levels = getattr(leaf, "trans_coeff_level", None)
+        if levels is None:
+            continue
+        ts = getattr(leaf, "transform_skip_flag", (0, 0, 0))
+        if getattr(leaf, "cbf_luma", 1):
+            fl = base | (TU_SKIP if ts[0] else 0)
+            if leaf.log2size == 2 and intra:
+                fl |= TU_DST
+            yield 0, leaf.x, leaf.y, leaf.log2size, qps[0], fl, levels[0].T
+        if leaf.log2size > 2:
+            cx, cy, cl2 = leaf.x >> 1, leaf.y >> 1, leaf.log2size - 1
+            cbf = (leaf.cbf_cb, leaf.cbf_cr)
+        elif getattr(leaf, "idx", 0) == 3 and leaf.parent is not None:
+            # four 4x4 luma TBs share one 4x4 Cb + Cr pair, parsed with the 4th
+            # sibling at the first sibling's position (tu.py:128-135)
+            first = leaf.parent.children[0]
+            cx, cy, cl2 = first.x >> 1, first.y >> 1, 2
+            cbf = (first.cbf_cb, first.cbf_cr)
+        else:
+            continue
+        for c in (1, 2):
+            if cbf[c - 1]:
+                fl = base | (TU_SKIP if ts[c] else 0)
+                yield c, cx, cy, cl2, qps[c], fl, levels[c].T
 
 
 def geom_from_sps(sps, n_pics: int = 1) -> PicGeom:
@@ -90,7 +96,14 @@ def pack_pictures(imgs, sps, scaling_factor=None) -> ResidualBatch:
     tus = np.array(recs, dtype=TU_DESC) if recs else np.zeros(0, dtype=TU_DESC)
     coeffs = np.concatenate(blocks) if blocks else np.zeros(0, dtype=np.int16)
     return ResidualBatch(geom=geom, tus=sort_by_size(tus), coeffs=coeffs,
-                         scaling_factor=scaling_factor, covers_all=False)
+                         scaling_factor=scaling_factor, covers_all=tbs_cover_planes(tus, geom))
+
+
+def tbs_cover_planes(tus, geom) -> bool:
+    """True when the (non-overlapping) TBs tile every plane of every picture completely, so the
+    residual launch needs no zero fill (P265_RES_ZERO_FILL)."""
+    area = int((1 << (2 * tus["log2n"].astype(np.int64))).sum())
+    return area == geom.n_pics * (geom.width * geom.height + 2 * geom.width_c * geom.height_c)
 
 
 # ------------------------------------------------------------------------- SAO

@@ -3,7 +3,8 @@
 Intra pictures and separate streams share nothing, so the path shards by picture or
 stream with no data-path collective: stream s -> rank s mod world.  The
 only inter-rank traffic is the benchmark's barrier and the MAX reduction of the timed
-region, through torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+region: host scalars over torch.distributed's gloo backend -- no NCCL anywhere.  Inside one
+process the same partition is what `pool.EnginePool` dispatches by."""
 from __future__ import annotations
 
 

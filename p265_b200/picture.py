@@ -286,6 +286,49 @@ def pack_coefficients(tus: np.ndarray, coeffs: np.ndarray):
     return tus, stream
 
 
+def unpack_coefficients(tus: np.ndarray, stream: np.ndarray):
+    """Inverse of pack_coefficients: (descriptors indexing a dense arena laid out in descriptor order,
+    int16 arena).  Host-side format conversion only (the per-TB drop-in keeps a d[] cache that is
+    indexed like a dense arena); the device does its own expansion (csrc/coeffs.cu)."""
+    tus = tus.copy()
+    stream = np.asarray(stream, dtype=np.uint8)
+    l2 = tus["log2n"].astype(np.int64)
+    nn_all = 1 << (2 * l2)
+    off = np.concatenate(([0], np.cumsum(nn_all)[:-1])) if len(tus) else np.zeros(0, np.int64)
+    arena = np.zeros(int(nn_all.sum()), np.int16)
+    rec = tus["coeff_off"].astype(np.int64) * 4
+    narrow = (tus["flags"] & TU_LEVELS8) != 0
+    for k in (5, 4, 3, 2):
+        idx = np.nonzero(l2 == k)[0]
+        if not idx.size:
+            continue
+        nn = 1 << (2 * k)
+        bm = stream[rec[idx][:, None] + np.arange(nn // 8, dtype=np.int64)[None, :]]
+        mask = np.unpackbits(bm, axis=1, bitorder="little").astype(bool)
+        cnt = mask.sum(axis=1)
+        start = np.concatenate(([0], np.cumsum(cnt)[:-1]))
+        rank = np.arange(int(cnt.sum()), dtype=np.int64) - np.repeat(start, cnt)
+        nar = np.repeat(narrow[idx], cnt)
+        pos = np.repeat(rec[idx] + nn // 8, cnt) + rank * np.where(nar, 1, 2)
+        lo = stream[pos].astype(np.uint16)
+        hi = np.where(nar, np.where(lo & 0x80, 0xFF, 0), stream[np.minimum(pos + 1, stream.size - 1)]).astype(np.uint16)
+        vals = (lo | (hi << 8)).astype(np.uint16).view(np.int16)
+        blocks = np.zeros((idx.size, nn), np.int16)
+        blocks[mask] = vals
+        arena[(off[idx][:, None] + np.arange(nn, dtype=np.int64)[None, :]).ravel()] = blocks.ravel()
+    tus["coeff_off"] = (off >> 4).astype(np.uint32)
+    tus["flags"] = tus["flags"] & np.uint8(0xFF ^ TU_LEVELS8)
+    return tus, arena
+
+
+def _unpacked(self) -> ResidualBatch:
+    tus, arena = unpack_coefficients(self.tus, self.stream)
+    return ResidualBatch(self.geom, tus, arena, self.scaling_factor, self.covers_all, self.sf_replicated, self.bins)
+
+
+PackedResidualBatch.unpacked = _unpacked
+
+
 def _packed(self) -> PackedResidualBatch:
     """The same batch with its coefficients as a packed stream (host -> device transport)."""
     tus, stream = pack_coefficients(self.tus, self.coeffs)

@@ -21,12 +21,11 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import packer
+from . import emit, packer
 from .engine import get_engine
-from .picture import (TU_BYPASS, TU_DESC, TU_DST, TU_INTRA, TU_SKIP, PicGeom, ResidualBatch,
+from .picture import (TU_BYPASS, TU_DESC, TU_DST, TU_INTRA, TU_PRESCALED, TU_SKIP, PicGeom, ResidualBatch,
                       pack_scaling_factor)
 
-TU_PRESCALED = 16
 
 #: "spec" = H.265 8.6.2-8.6.4 (default).  "ref_literal" = transform.py:89-109 exactly as
 #: written -- parity tests only, never benchmarked.
@@ -86,8 +85,16 @@ def flush_picture(img, sps, device: int = 0, pps=None) -> PictureResidual:
     """Batched path: one residual launch (+ one dequant launch for `scaled_samples`) for
     all coded TBs of a parsed picture; the result is attached to `img`."""
     eng = get_engine(device)
-    batch = packer.pack_pictures([img], sps, sps_scaling_table(sps, pps))
-    planes = eng.residual(batch)
+    table = sps_scaling_table(sps, pps)
+    packed = emit.take(img, sps, table)
+    if packed is not None:
+        # the parser was hooked (emit.hook_parser): the picture's packed stream is already there --
+        # no walk over the finished tree; the stream is what crosses PCIe
+        planes = eng.residual(packed)
+        batch = packed.unpacked()          # the d[] cache of the per-TB drop-in is indexed like a dense arena
+    else:
+        batch = packer.pack_pictures([img], sps, table)
+        planes = eng.residual(batch)
     scaled = eng.dequant(batch)
     img._p265_b200_residual = PictureResidual(batch, planes, scaled)
     return img._p265_b200_residual
