@@ -53,7 +53,8 @@ typedef struct p265_tu_desc {
     uint8_t flags;       /* P265_TU_*                                               */
     uint32_t coeff_off;  /* offset into the coefficient arena, units of 16 coeffs   */
     uint16_t pic;        /* picture index inside the batch                          */
-    uint16_t rsvd;
+    uint16_t rsvd;       /* dense arena: ignored.  Packed stream: number of non-zero
+                            levels in the TB's record (= set bits of its bitmap)     */
 } p265_tu_desc;
 
 #define P265_TU_DST 1u    /* trType 1: 4x4 luma of an intra CU (transform.py:97)     */
@@ -74,6 +75,9 @@ typedef struct p265_tu_desc {
  *                           bitmap bits: int8 each when the descriptor has P265_TU_LEVELS8
  *                           (every |level| of the TB <= 127), little-endian int16 otherwise
  *     padding               to the next multiple of 4 bytes
+ * The descriptor's `rsvd` field holds the number of levels, so a record's extent follows from
+ * its descriptor alone (validation needs no pass over the stream; the device never reads more
+ * than `rsvd` levels of a TB).
  * A 4K 10-bit picture of the benchmark mix is 25.1 MB as a dense int16 arena and 3.7 MB as a
  * stream.  The device expands it (unpack_kernel) into its own dense arena in descriptor
  * order and runs the same residual kernels on it.                                          */

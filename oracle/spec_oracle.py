@@ -591,6 +591,8 @@ def unpack_stream(tus, stream):
         rec = int(t["coeff_off"]) * 4
         bits = np.unpackbits(stream[rec:rec + nn // 8], bitorder="little")[:nn].astype(bool)
         k = int(bits.sum())
+        if k != int(t["rsvd"]):
+            raise ValueError("TB %d: descriptor announces %d levels, bitmap has %d bits set" % (i, int(t["rsvd"]), k))
         lv0 = rec + nn // 8
         if int(t["flags"]) & _TU_LEVELS8:
             lv = stream[lv0:lv0 + k].view(np.int8).astype(np.int16)
@@ -599,4 +601,5 @@ def unpack_stream(tus, stream):
         arena[int(offs[i]):int(offs[i]) + nn][bits] = lv
     out_tus["coeff_off"] = (offs >> 4).astype(np.uint32)
     out_tus["flags"] = out_tus["flags"] & np.uint8(0xFF ^ _TU_LEVELS8)
+    out_tus["rsvd"] = 0
     return out_tus, arena

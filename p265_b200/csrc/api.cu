@@ -67,14 +67,74 @@ static int check_geom(const p265_pic_geom *g, int elem_align) {
 // host-side validation of a descriptor list (host entry points only)
 // *dense_small = inside the 8x8 bin and inside the 4x4 bin every TB's coefficients directly follow
 // the previous TB's (what P265_RES_DENSE_ARENA asserts on the device entry point)
-// stream != nullptr: the descriptors index a packed coefficient stream of n_coeffs BYTES (records of
-// significance bitmap + levels, include/p265_b200.h) instead of a dense arena of n_coeffs int16
+// packed: the descriptors index a packed coefficient stream of n_coeffs BYTES (records of significance
+// bitmap + levels, include/p265_b200.h; `rsvd` = number of levels) instead of a dense arena of n_coeffs
+// int16.  A record is bounded by its descriptor alone (bitmap size + rsvd levels): the device never reads
+// more than rsvd levels of a TB whatever its bitmap says, so no pass over the stream is needed here.
+struct TuLimits {
+    int wmax[3], hmax[3], qmax[3];
+    int n_pics;
+    size_t n_coeffs;
+};
+
+template <bool PACKED>
+static inline unsigned tu_bad(const p265_tu_desc &t, int log2n, unsigned bad_flags, const TuLimits &L) {
+    const int n = 1 << log2n;
+    const unsigned c = t.c_idx < 3 ? t.c_idx : 0;
+    unsigned bad = (unsigned)(t.log2n != log2n) | (unsigned)(t.c_idx > 2) | (unsigned)(((t.x | t.y) & (n - 1)) != 0) |
+                   (unsigned)(t.x + n > L.wmax[c]) | (unsigned)(t.y + n > L.hmax[c]) | (unsigned)(t.pic >= L.n_pics) |
+                   (unsigned)((t.flags & bad_flags) != 0) | (unsigned)(((t.flags & P265_TU_DST) != 0) & (t.c_idx != 0)) |
+                   (unsigned)(t.qp > L.qmax[c]);
+    if (PACKED) {
+        const size_t end = (size_t)t.coeff_off * 4 + (size_t)(n * n) / 8 + (size_t)t.rsvd * ((t.flags & P265_TU_LEVELS8) ? 1 : 2);
+        bad |= (unsigned)(end > L.n_coeffs) | (unsigned)(t.rsvd > n * n);
+    } else {
+        bad |= (unsigned)((size_t)t.coeff_off * 16 + (size_t)(n * n) > L.n_coeffs);
+    }
+    return bad;
+}
+
+// the first offending descriptor, in words (only reached when the fast pass found one)
+static int diagnose_tu(const p265_tu_desc &t, long long k, int log2n, bool have_table, bool packed, const TuLimits &L) {
+    const int n = 1 << log2n;
+    const unsigned c = t.c_idx < 3 ? t.c_idx : 0;
+    if (t.log2n != log2n)
+        return set_error(P265_EINVAL, "descriptor %lld: log2n %d where bin expects %d (list must be sorted 32,16,8,4)", k,
+                         t.log2n, log2n);
+    if (t.c_idx > 2) return set_error(P265_EINVAL, "descriptor %lld: c_idx %d", k, t.c_idx);
+    if (t.x % n || t.y % n || t.x + n > L.wmax[c] || t.y + n > L.hmax[c])
+        return set_error(P265_EINVAL, "descriptor %lld: %dx%d block at (%d,%d) outside the %dx%d plane or unaligned", k, n, n,
+                         t.x, t.y, L.wmax[c], L.hmax[c]);
+    if (t.pic >= L.n_pics) return set_error(P265_EINVAL, "descriptor %lld: picture %d", k, t.pic);
+    if (packed && t.rsvd > n * n)
+        return set_error(P265_EINVAL, "descriptor %lld: %d levels in a %dx%d block", k, t.rsvd, n, n);
+    if (tu_bad<true>(t, log2n, 0, L) && packed)
+        return set_error(P265_EINVAL, "descriptor %lld: coefficients beyond the packed stream", k);
+    if (!packed && (size_t)t.coeff_off * 16 + (size_t)(n * n) > L.n_coeffs)
+        return set_error(P265_EINVAL, "descriptor %lld: coefficients beyond the arena", k);
+    if (t.flags & (packed ? 0xc0u : (0xc0u | P265_TU_LEVELS8)))
+        return set_error(P265_EINVAL, "descriptor %lld: flags 0x%02x not defined for this entry point", k, t.flags);
+    if ((t.flags & P265_TU_SKIP) && log2n != 2)
+        return set_error(P265_EINVAL, "descriptor %lld: transform_skip on a %dx%d block", k, n, n);
+    if ((t.flags & P265_TU_DST) && (log2n != 2 || t.c_idx != 0))
+        return set_error(P265_EINVAL, "descriptor %lld: DST on a non-4x4-luma block", k);
+    if (have_table && (t.flags & P265_TU_PRESCALED))
+        return set_error(P265_EINVAL, "descriptor %lld: PRESCALED needs scaling_factor == NULL", k);
+    return set_error(P265_EINVAL, "descriptor %lld: qP %d out of range", k, t.qp);
+}
+
 static int check_tus(const p265_tu_desc *tus, const int32_t bin_counts[4], size_t n_coeffs, const p265_pic_geom *g,
-                     bool have_table, bool *dense_small, const uint8_t *stream = nullptr) {
-    // one pass over caller data, on the latency path of every host call: plane limits and the qP
-    // bound are hoisted per component, the rare diagnostics are formatted only on failure
-    const int wmax[3] = {g->width, g->width / 2, g->width / 2}, hmax[3] = {g->height, g->height / 2, g->height / 2};
-    const int qmax[3] = {51 + 6 * (g->bit_depth_y - 8), 51 + 6 * (g->bit_depth_c - 8), 51 + 6 * (g->bit_depth_c - 8)};
+                     bool have_table, bool *dense_small, bool packed = false) {
+    // one branch-free pass over caller data, on the latency path of every host call (119 k descriptors per
+    // 4K picture); the diagnostics are formatted by a second look only when something is wrong
+    TuLimits L;
+    for (int c = 0; c < 3; c++) {
+        L.wmax[c] = c ? g->width / 2 : g->width;
+        L.hmax[c] = c ? g->height / 2 : g->height;
+        L.qmax[c] = 51 + 6 * ((c ? g->bit_depth_c : g->bit_depth_y) - 8);
+    }
+    L.n_pics = g->n_pics;
+    L.n_coeffs = n_coeffs;
     int64_t k = 0;
     uint32_t not_dense = 0;
     for (int b = 0; b < 4; b++) {
@@ -82,60 +142,18 @@ static int check_tus(const p265_tu_desc *tus, const int32_t bin_counts[4], size_
         const int log2n = 5 - b, n = 1 << log2n;
         const uint32_t units = (uint32_t)(n * n) / 16, z0 = bin_counts[b] ? tus[k].coeff_off : 0u;
         const unsigned bad_flags = (log2n != 2 ? (P265_TU_SKIP | P265_TU_DST) : 0u) | (have_table ? P265_TU_PRESCALED : 0u) |
-                                   (stream ? 0u : P265_TU_LEVELS8) | 0xc0u;
-        const size_t bm_bytes = (size_t)(n * n) / 8;
-        for (int32_t i = 0; i < bin_counts[b]; i++, k++) {
-            const p265_tu_desc &t = tus[k];
-            const unsigned c = t.c_idx < 3 ? t.c_idx : 0;
-            bool in_range;
-            if (stream) {  // record = bitmap + one level per set bit, inside the stream
-                const size_t off = (size_t)t.coeff_off * 4;
-                in_range = off + bm_bytes <= n_coeffs;
-                if (in_range) {
-                    size_t nnz = 0;
-                    if (bm_bytes >= 8) {
-                        for (size_t w = 0; w < bm_bytes; w += 8) {
-                            uint64_t v;
-                            memcpy(&v, stream + off + w, 8);
-                            nnz += (size_t)__builtin_popcountll(v);
-                        }
-                    } else {
-                        uint16_t v;
-                        memcpy(&v, stream + off, 2);
-                        nnz = (size_t)__builtin_popcount(v);
-                    }
-                    in_range = off + bm_bytes + nnz * ((t.flags & P265_TU_LEVELS8) ? 1 : 2) <= n_coeffs;
-                }
-            } else {
-                in_range = (size_t)t.coeff_off * 16 + (size_t)n * n <= n_coeffs;
-            }
-            const bool ok = t.log2n == log2n && t.c_idx <= 2 && ((t.x | t.y) & (n - 1)) == 0 && t.x + n <= wmax[c] &&
-                            t.y + n <= hmax[c] && t.pic < g->n_pics && in_range && !(t.flags & bad_flags) &&
-                            !((t.flags & P265_TU_DST) && t.c_idx != 0) && t.qp <= qmax[c];
-            if (b >= 2) not_dense |= t.coeff_off ^ (z0 + (uint32_t)i * units);
-            if (ok) continue;
-            if (t.log2n != log2n)
-                return set_error(P265_EINVAL, "descriptor %lld: log2n %d where bin expects %d (list must be sorted "
-                                 "32,16,8,4)", (long long)k, t.log2n, log2n);
-            if (t.c_idx > 2) return set_error(P265_EINVAL, "descriptor %lld: c_idx %d", (long long)k, t.c_idx);
-            if (t.x % n || t.y % n || t.x + n > wmax[c] || t.y + n > hmax[c])
-                return set_error(P265_EINVAL, "descriptor %lld: %dx%d block at (%d,%d) outside the %dx%d plane or "
-                                 "unaligned", (long long)k, n, n, t.x, t.y, wmax[c], hmax[c]);
-            if (t.pic >= g->n_pics) return set_error(P265_EINVAL, "descriptor %lld: picture %d", (long long)k, t.pic);
-            if (!in_range)
-                return set_error(P265_EINVAL, "descriptor %lld: coefficients beyond the %s", (long long)k,
-                                 stream ? "packed stream" : "arena");
-            if (t.flags & (stream ? 0xc0u : (0xc0u | P265_TU_LEVELS8)))
-                return set_error(P265_EINVAL, "descriptor %lld: flags 0x%02x not defined for this entry point", (long long)k,
-                                 t.flags);
-            if ((t.flags & P265_TU_SKIP) && log2n != 2)
-                return set_error(P265_EINVAL, "descriptor %lld: transform_skip on a %dx%d block", (long long)k, n, n);
-            if ((t.flags & P265_TU_DST) && (log2n != 2 || t.c_idx != 0))
-                return set_error(P265_EINVAL, "descriptor %lld: DST on a non-4x4-luma block", (long long)k);
-            if (have_table && (t.flags & P265_TU_PRESCALED))
-                return set_error(P265_EINVAL, "descriptor %lld: PRESCALED needs scaling_factor == NULL", (long long)k);
-            return set_error(P265_EINVAL, "descriptor %lld: qP %d out of range", (long long)k, t.qp);
-        }
+                                   (packed ? 0u : P265_TU_LEVELS8) | 0xc0u;
+        const p265_tu_desc *t = tus + k;
+        const int32_t cnt = bin_counts[b];
+        unsigned bad = 0;
+        if (packed) for (int32_t i = 0; i < cnt; i++) bad |= tu_bad<true>(t[i], log2n, bad_flags, L);
+        else for (int32_t i = 0; i < cnt; i++) bad |= tu_bad<false>(t[i], log2n, bad_flags, L);
+        if (b >= 2) for (int32_t i = 0; i < cnt; i++) not_dense |= t[i].coeff_off ^ (z0 + (uint32_t)i * units);
+        if (bad)
+            for (int32_t i = 0; i < cnt; i++)
+                if (packed ? tu_bad<true>(t[i], log2n, bad_flags, L) : tu_bad<false>(t[i], log2n, bad_flags, L))
+                    return diagnose_tu(t[i], (long long)(k + i), log2n, have_table, packed, L);
+        k += cnt;
     }
     *dense_small = not_dense == 0;
     return P265_OK;
@@ -318,7 +336,7 @@ int p265_residual_batch_packed(p265_ctx *ctx, const p265_tu_desc *tus, const int
     for (int b = 0; b < 4; b++) n += bin_counts[b] > 0 ? bin_counts[b] : 0;
     if (n && (!tus || !stream)) return set_error(P265_EINVAL, "descriptor / stream pointer is NULL");
     bool dense_small = false;
-    if ((rc = check_tus(tus, bin_counts, stream_bytes, geom, scaling_factor != nullptr, &dense_small, stream ? stream : (const uint8_t *)""))) return rc;
+    if ((rc = check_tus(tus, bin_counts, stream_bytes, geom, scaling_factor != nullptr, &dense_small, true))) return rc;
     flags |= P265_RES_ZERO_FILL;  // see p265_residual_batch
     P265_CUDA(cudaSetDevice(ctx->device));
     void *d_tus, *d_st, *d_sf = nullptr, *d_out, *d_arena, *d_tus2;

@@ -47,13 +47,16 @@ __device__ __forceinline__ void unpack_item(const UnpackArgs &a, int item, int l
         if (wi >= o) incl += v;
     }
     int idx = incl - __popc(word);
+    const int n_levels = (int)(d.w >> 16);  // descriptor field rsvd: the record holds exactly this many levels --
+                                            // never read past them, whatever the bitmap claims (the host entry
+                                            // point bounds records by this field, not by counting bits)
     const bool narrow = ((d.y >> 24) & P265_TU_LEVELS8) != 0;
     const uint8_t *lv = rec + NN / 8;
     uint32_t out[BITS / 2];
 #pragma unroll
     for (int b = 0; b < BITS; b++) {
         uint32_t v = 0;
-        if ((word >> b) & 1u) {
+        if (((word >> b) & 1u) && idx < n_levels) {
             v = narrow ? (uint32_t)(int)reinterpret_cast<const int8_t *>(lv)[idx]
                        : (uint32_t)reinterpret_cast<const uint16_t *>(lv)[idx];
             idx++;
@@ -68,6 +71,7 @@ __device__ __forceinline__ void unpack_item(const UnpackArgs &a, int item, int l
     for (int q = 0; q < BITS / 8; q++) dst[q] = make_uint4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
     if (wi == 0) {
         d.z = unit;
+        d.w &= 0xffffu;  // rsvd is a packed-stream field
         d.y &= ~((uint32_t)P265_TU_LEVELS8 << 24);
         *reinterpret_cast<uint4 *>(&a.tus_out[a.first_tb[bin] + tb]) = d;
     }

@@ -371,6 +371,103 @@ __device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride
     cp_async_wait<0>();
 }
 
+// ---- small TBs, streaming form: one warp = ONE item, no software pipeline ---------------
+// The persistent pipelines above hide the two global latencies of an item behind the previous
+// item's arithmetic -- but a warp of a small bin only ever sees a handful of items (the 4x4 bin of
+// 16 4K pictures is 8 items per warp), so its lifetime is mostly pipeline fill: the ncu source view
+// of the round-1 4x4 bin shows 18 % of all stall samples on the cp.async wait at the head of the
+// item loop and an achieved occupancy of 34 %.  Here the hardware does the hiding instead, as in the
+// SAO kernel: a grid of one-item warps, every load of an item issued up front (descriptor, both
+// halves of the tile; with a dense arena the tile address does not depend on the descriptor), 32
+// warps per SM in flight, the block scheduler balancing the tail.  Measured on 16 4K pictures (B200,
+// profiles/r2_small_bins.txt): 8x8 bin 46.2 -> 42.5 us, 4x4 bin 40.7 -> 42.3 us (its items are too
+// short: the per-CTA set-up is not amortised) -- so the 8x8 bin streams and the 4x4 bin keeps its
+// pipeline.  P265_STREAM_BIN8 / P265_STREAM_BIN4 (compile time, 0 / 1) select the form per bin.
+#ifndef P265_STREAM_BIN8
+#define P265_STREAM_BIN8 1
+#endif
+#ifndef P265_STREAM_BIN4
+#define P265_STREAM_BIN4 0
+#endif
+template <int BIN>
+struct SmallStream {
+    static constexpr bool on = BIN == 2 ? (P265_STREAM_BIN8 != 0) : (BIN == 3 ? (P265_STREAM_BIN4 != 0) : false);
+};
+
+template <int SF>
+__device__ __forceinline__ void stream_bin4(const KernelArgs &a, int item, int lane, const uint8_t *sfs) {
+    const int n_tb = a.n_tb[3], first = a.first_tb[3];
+    const int i = item * 32 + lane;
+    const bool valid = i < n_tb;
+    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+    uint4 d;
+    if (a.dense_arena) {  // tile address from the TB's index: all three loads of the lane are independent
+        const uint32_t z0 = __ldg(&a.tus[first].coeff_off);
+        d = SmallDesc<SF, 2>::load(a, first + i, valid);
+        if (valid) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.coeffs + (size_t)(z0 + (uint32_t)i) * 16);
+            v0 = __ldg(src);
+            v1 = __ldg(src + 1);
+        }
+    } else {
+        d = SmallDesc<SF, 2>::load(a, first + i, valid);
+        if (valid) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.coeffs + (size_t)d.z * 16);
+            v0 = __ldg(src);
+            v1 = __ldg(src + 1);
+        }
+    }
+    const TbParams t = SmallDesc<SF, 2>::params(a, d, valid);
+    const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    const bool slow = __any_sync(0xffffffffu, t.lsh != 0);
+    const uint8_t *sfm = small_sf_ptr<SF, 2>(sfs, d);
+    if (slow) tb4_lane<SF, true>(t, w, sfm);
+    else tb4_lane<SF, false>(t, w, sfm);
+}
+
+template <int SF>
+__device__ __forceinline__ void stream_bin8(const KernelArgs &a, int item, int lane, unsigned char *wbase,
+                                            const uint8_t *sfs) {
+    const int n_tb = a.n_tb[2], first = a.first_tb[2];
+    const int n_here = n_tb - item * 32;
+    const bool valid = lane < n_here;
+    const uint32_t wbase_s = smem_addr(wbase), sfs_s = smem_addr(sfs);
+    uint4 d;
+    // cooperative tile copy (see run_bin8): copy instruction i = the 8 chunks of TBs 4i .. 4i+3
+    if (a.dense_arena) {
+        const uint32_t z0 = __ldg(&a.tus[first].coeff_off);
+        d = SmallDesc<SF, 3>::load(a, first + item * 32 + lane, valid);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int t = (lane >> 3) + 4 * i;
+            if (t < n_here)
+                copy16_async(wbase + tb8_chunk_off(t, lane & 7),
+                             a.coeffs + (size_t)(z0 + (uint32_t)(item * 32 + t) * 4u) * 16 + (lane & 7) * 8);
+        }
+    } else {
+        d = SmallDesc<SF, 3>::load(a, first + item * 32 + lane, valid);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int t = (lane >> 3) + 4 * i;
+            const uint32_t z = __shfl_sync(0xffffffffu, d.z, t);
+            if (t < n_here) copy16_async(wbase + tb8_chunk_off(t, lane & 7), a.coeffs + (size_t)z * 16 + (lane & 7) * 8);
+        }
+    }
+    cp_async_commit();
+    bool slow_lane;
+    if (SmallDesc<SF, 3>::X) {
+        slow_lane = (d.w >> 24) != 0;
+    } else {
+        const int qp = (int)((d.y >> 16) & 0xff), c_idx = (int)((d.y >> 8) & 0xff);
+        slow_lane = ((qp * 43) >> 8) >= (c_idx ? a.bit_depth_c : a.bit_depth_y) - 2;
+    }
+    const bool slow = __any_sync(0xffffffffu, valid && slow_lane);
+    cp_async_wait<0>();
+    __syncwarp();
+    if (slow) tb8_call<SF, true>(a, d, valid, wbase_s, lane, sfs_s);
+    else tb8_call<SF, false>(a, d, valid, wbase_s, lane, sfs_s);
+}
+
 // CTAs per SM per bin: 32x32 is shared-memory limited (9.25 KB per warp); 16x16 needs only
 // 5.25 KB per warp and fits 64 registers; 8x8 keeps 64 packed words live per lane; 4x4 is
 // register-only.
@@ -386,10 +483,10 @@ struct BinCfg {
     static constexpr int ctas = BIN == 0 ? P265_CTAS_BIN0 : (BIN == 1 ? P265_CTAS_BIN1 : (BIN == 3 ? P265_CTAS_BIN3 : kCtasPerSm));
     // per warp: tile + g buffers + descriptor ring (2 slots x TBs per item x 16 B for the big sizes)
     static constexpr int smem =
-        BIN == 3 ? kSfcBytes + kWarpsPerCta * kBin4WarpBytes
+        BIN == 3 ? kSfcBytes + (SmallStream<3>::on ? 0 : kWarpsPerCta * kBin4WarpBytes)
         : BIN == 0 ? kSfcBytes + kWarpsPerCta * (2 * Layout<5>::WARP_BYTES + 3 * Layout<5>::TBS * 16 + 32)
         : BIN == 1 ? kSfcBytes + kWarpsPerCta * (2 * Layout<4>::WARP_BYTES + 3 * Layout<4>::TBS * 16)
-                   : kSfcBytes + kCtaSmemBytes;
+                   : kSfcBytes + (SmallStream<2>::on ? kWarpsPerCta * kWarpSmemBytes : kCtaSmemBytes);
 };
 
 template <int BIN, int SF>
@@ -421,7 +518,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, BinCfg<BIN>::ctas) residual
     }
     if (BIN == 0) run_bin<5, SF>(a, gw, stride, lane, wbase, smem);
     else if (BIN == 1) run_bin<4, SF>(a, gw, stride, lane, wbase, smem);
-    else if (BIN == 2) run_bin8<SF>(a, gw, stride, lane, wbase, smem);
+    else if (SmallStream<BIN>::on) {  // one item per warp; the grid covers the bin
+        if (gw < a.first_item[BIN + 1] - a.first_item[BIN]) {
+            if (BIN == 2) stream_bin8<SF>(a, gw, lane, wbase, smem);
+            else stream_bin4<SF>(a, gw, lane, smem);
+        }
+    } else if (BIN == 2) run_bin8<SF>(a, gw, stride, lane, wbase, smem);
     else run_bin4<SF>(a, gw, stride, lane, wbase, smem);
     // Make the chain transitive: a bin launched with programmatic stream serialization may start
     // (and finish) before its predecessor has finished, so "the last bin is complete" would not
@@ -590,7 +692,7 @@ static int launch_bin(p265_ctx *ctx, KernelArgs a, bool first) {
     if (occ_use < 1) occ_use = 1;
     const int max_warps = ctx->sm_count * occ_use * kWarpsPerCta;
     const int rounds = (items + max_warps - 1) / max_warps;
-    const int warps = (items + rounds - 1) / rounds;
+    const int warps = SmallStream<BIN>::on ? items : (items + rounds - 1) / rounds;  // streaming bins: one warp per item
     const int grid = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);

@@ -54,7 +54,7 @@ class PictureSink:
         self.stream += vals.astype(np.int8 if narrow else "<i2").tobytes()
         self.stream += b"\0" * (-len(self.stream) & 3)
         self.recs.append((x, y, log2n, c_idx, qp, (flags & ~TU_LEVELS8) | (TU_LEVELS8 if narrow else 0),
-                          off >> 2, self.pic, 0))
+                          off >> 2, self.pic, int(vals.size)))
         self.area += n * n
 
     def add_cu(self, cu, sps) -> None:

@@ -282,6 +282,7 @@ def pack_coefficients(tus: np.ndarray, coeffs: np.ndarray):
     if stream.size >> 2 > 0xFFFFFFFF:
         raise ValueError("packed stream too large for 32-bit record offsets")
     tus["coeff_off"] = (rec_off >> 2).astype(np.uint32)
+    tus["rsvd"] = nnz.astype(np.uint16)                     # number of levels in the record
     tus["flags"] = (tus["flags"] & ~np.uint8(TU_LEVELS8)) | np.where(wide, 0, TU_LEVELS8).astype(np.uint8)
     return tus, stream
 
@@ -317,6 +318,7 @@ def unpack_coefficients(tus: np.ndarray, stream: np.ndarray):
         blocks[mask] = vals
         arena[(off[idx][:, None] + np.arange(nn, dtype=np.int64)[None, :]).ravel()] = blocks.ravel()
     tus["coeff_off"] = (off >> 4).astype(np.uint32)
+    tus["rsvd"] = 0
     tus["flags"] = tus["flags"] & np.uint8(0xFF ^ TU_LEVELS8)
     return tus, arena
 

@@ -115,12 +115,24 @@ def test_packed_stream_rejects_malformed_input(engine):
     bad.tus["flags"][0] |= TU_LEVELS8
     with pytest.raises(ValueError):
         engine.residual(bad)
-    # every bitmap bit set + a record at the very end: the level list would run past the stream
-    evil = pb.stream.copy()
-    last = int(pb.tus["coeff_off"].max()) * 4
-    evil[last:last + 2] = 0xFF
+    # a descriptor that announces more levels than the stream holds behind its record
+    k = int(np.argmax(pb.tus["coeff_off"]))
+    liar = pb.tus.copy()
+    liar["rsvd"][k] = 1 << (2 * int(liar["log2n"][k]))
     with pytest.raises(ValueError):
-        engine.residual(PackedResidualBatch(pb.geom, pb.tus, evil, pb.scaling_factor, bins=pb.bins))
+        engine.residual(PackedResidualBatch(pb.geom, liar, pb.stream, pb.scaling_factor, bins=pb.bins))
+    liar["rsvd"][k] = 2000
+    with pytest.raises(ValueError):
+        engine.residual(PackedResidualBatch(pb.geom, liar, pb.stream, pb.scaling_factor, bins=pb.bins))
+    # a bitmap with more bits than announced levels is memory-safe: the device reads `rsvd` levels, the
+    # surplus positions stay zero (record at the very end of the stream, every bit set)
+    evil = pb.stream.copy()
+    last = int(pb.tus["coeff_off"][k]) * 4
+    nn8 = (1 << (2 * int(pb.tus["log2n"][k]))) // 8
+    evil[last:last + nn8] = 0xFF
+    a = engine.residual(PackedResidualBatch(pb.geom, pb.tus, evil, pb.scaling_factor, bins=pb.bins))
+    b = engine.residual(PackedResidualBatch(pb.geom, pb.tus, evil, pb.scaling_factor, bins=pb.bins))
+    assert np.array_equal(a, b)
 
 
 # ------------------------------------------------------------------ PDL chain of the bins

@@ -19,6 +19,7 @@ def test_known_answer_record():
     assert not (t["flags"][0] & TU_LEVELS8)
     # bitmap bits 0, 1 and 2*4+3 = 11 -> bytes 0x03, 0x08; then 3, -2, 300 as little-endian int16; padded to 4
     assert s.tolist() == [0x03, 0x08, 3, 0, 0xFE, 0xFF, 0x2C, 0x01]
+    assert t["rsvd"][0] == 3                                  # number of levels travels in the descriptor
     # the same block without the 300: int8 levels
     blk[2, 3] = -128
     t, s = pack_coefficients(tus, blk.reshape(-1))
