@@ -380,11 +380,14 @@ __device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride
 // SAO kernel: a grid of one-item warps, every load of an item issued up front (descriptor, both
 // halves of the tile; with a dense arena the tile address does not depend on the descriptor), 32
 // warps per SM in flight, the block scheduler balancing the tail.  Measured on 16 4K pictures (B200,
-// profiles/r2_small_bins.txt): 8x8 bin 46.2 -> 42.5 us, 4x4 bin 40.7 -> 42.3 us (its items are too
-// short: the per-CTA set-up is not amortised) -- so the 8x8 bin streams and the 4x4 bin keeps its
-// pipeline.  P265_STREAM_BIN8 / P265_STREAM_BIN4 (compile time, 0 / 1) select the form per bin.
+// profiles/r2_small_bins.txt): alone, the 8x8 bin gains (46.2 -> 42.5 us) and the 4x4 bin does not
+// (40.7 -> 42.3 us: its items are too short to amortise the per-CTA set-up); in the mix BOTH lose
+// (0.2246 -> 0.2330 ms): a multi-wave grid releases its successor (griddepcontrol.launch_dependents)
+// only when its last CTA has started, so 10 us of the tail overlap between the bins is gone.  The
+// pipelined form therefore stays the default; P265_STREAM_BIN8 / P265_STREAM_BIN4 (compile time)
+// select the streaming form per bin for A/B runs.
 #ifndef P265_STREAM_BIN8
-#define P265_STREAM_BIN8 1
+#define P265_STREAM_BIN8 0
 #endif
 #ifndef P265_STREAM_BIN4
 #define P265_STREAM_BIN4 0
