@@ -499,6 +499,7 @@ def run_gpu(args):
     if pool is not None:
         e2e_launches = sum(pool.launch_counts().values()) // (e2e_steps + 2)
     # secondary: every step synchronised on its own (pipeline drained between steps), median step time
+    barrier()
     step_s = []
     for _ in range(max(3, e2e_steps // 3)):
         t0 = time.perf_counter()

@@ -12,6 +12,7 @@ Transform, nothing else is touched:
   3. dec.py: `import decoder.X as X` -> `import X` (so `log` is one module)
   4. stub `matplotlib`, `matplotlib.pyplot`, `matplotlib.patches` (imported at
      image.py:1-2, tree.py:2-3, slice.py:1; never used while decoding)
+  5. pps.py:64-65: the misspelt `num_tile_colums_minus1` (tile branch only; see transform_source)
 
 Only tests/, bench.py's cpu_baseline / --impl reference leg and
 __graft_entry__ may import this module; the product package never does.
@@ -59,17 +60,48 @@ def _fix_division(src: str) -> str:
     return "".join(lines)
 
 
+#: bump when the transform changes: build() regenerates a shim directory with another stamp
+SHIM_VERSION = "5"
+
+
 def transform_source(src: str, name: str) -> str:
     src = src.replace("\t", "        ")
     src = "".join(_fix_print(l) for l in src.splitlines(keepends=True))
     src = _fix_division(src)
     if name == "dec.py":
         src = re.sub(r"^import decoder\.(\w+) as \1$", r"import \1", src, flags=re.M)
+    if name == "pps.py":
+        # 5. harness patch for the tile fuzz stream (tests/golden/make_fuzz_streams.py): the PPS tile
+        #    branch cannot run as written -- pps.py:64-65 read the misspelt attribute
+        #    `num_tile_colums_minus1` (AttributeError) and derive the ROW count from the COLUMN syntax
+        #    element.  Only reached when tiles_enabled_flag = 1 (sanity.bin: 0; the 95 golden logs are
+        #    unaffected).
+        src = src.replace("self.num_tile_rows = self.num_tile_colums_minus1 + 1", "self.num_tile_rows = self.num_tile_rows_minus1 + 1")
+        src = src.replace("self.num_tile_columns = self.num_tile_colums_minus1 + 1",
+                          "self.num_tile_columns = self.num_tile_columns_minus1 + 1")
+        #    ... and pps.py:178 reads `self.pic_width_in_ctbs_y` (an Sps attribute) for every tile row but the first
+        src = src.replace("+= self.pic_width_in_ctbs_y * self.row_height[j]",
+                          "+= self.sps.pic_width_in_ctbs_y * self.row_height[j]")
+    if name == "cu.py":
+        #    ... and cu.py:518 (tile branch of decode_qp) reads the misspelt `sps.ctb_log2size_y`
+        src = src.replace("self.ctx.sps.ctb_log2size_y", "self.ctx.sps.ctb_log2_size_y")
+    if name == "slice.py":
+        #    ... and slice.py:182 calls `self.ue(...)` (no such method) for num_entry_point_offsets, a syntax
+        #    element that only exists when tiles or wavefronts are enabled
+        src = src.replace('self.ue("num_entry_point_offsets")', 'bs.ue("num_entry_point_offsets")')
     return src
 
 
 def reference_available() -> bool:
     return os.path.isfile(os.path.join(REF_ROOT, "decoder", "transform.py"))
+
+
+def _stamp() -> str:
+    try:
+        with open(os.path.join(SHIM_DIR, ".shim_version")) as fh:
+            return fh.read().strip()
+    except OSError:
+        return ""
 
 
 def shim_available() -> bool:
@@ -78,7 +110,7 @@ def shim_available() -> bool:
 
 def build(force: bool = False) -> str:
     """Generate baseline/_ref/p265ref/ from REF_ROOT.  Returns the shim dir."""
-    if shim_available() and not force:
+    if shim_available() and not force and (_stamp() == SHIM_VERSION or not reference_available()):
         return SHIM_DIR
     if not reference_available():
         raise FileNotFoundError("reference tree not found at %s" % REF_ROOT)
@@ -98,6 +130,8 @@ def build(force: bool = False) -> str:
     with open(os.path.join(REF_ROOT, "sanity.bin"), "rb") as fi, \
             open(os.path.join(SHIM_DIR, "sanity.bin"), "wb") as fo:
         fo.write(fi.read())
+    with open(os.path.join(SHIM_DIR, ".shim_version"), "w") as fh:
+        fh.write(SHIM_VERSION)
     return SHIM_DIR
 
 
@@ -117,7 +151,7 @@ def load(workdir: str | None = None):
     (log.py:33-83), so the first call chdir()s into `workdir` (a scratch dir with a
     logs/ sub-directory) for the import.
     """
-    if not shim_available():
+    if not shim_available() or (_stamp() != SHIM_VERSION and reference_available()):
         build()
     _stub_matplotlib()
     if SHIM_DIR not in sys.path:

@@ -63,12 +63,18 @@ def parse(name, cfg):
     return gen.run_parser(_ns, os.path.join(FUZZ_DIR, name + ".bin"))
 
 
-def lav_sao_avail(img, sps):
-    """Per-CTB neighbour masks under libavcodec's rule (current CTB's flag for every direction)."""
+def lav_sao_avail(img, sps, pps=None):
+    """Per-CTB neighbour masks under libavcodec's rule (current CTB's flag for every direction).
+    Tile boundaries with loop_filter_across_tiles_enabled_flag = 0 follow the standard there (a
+    neighbouring CTB of another tile is unusable, diagonals included)."""
     wc, hc = int(sps.pic_width_in_ctbs_y), int(sps.pic_height_in_ctbs_y)
     sl = np.zeros((hc, wc), np.int64)
     for a, ctu in img.ctus.items():
         sl[a // wc, a % wc] = int(ctu.slice_addr)
+    tile = None
+    if pps is not None and getattr(pps, "tiles_enabled_flag", 0) and \
+            not getattr(pps, "loop_filter_across_tiles_enabled_flag", 1):
+        tile = np.asarray(pps.tile_id_rs).reshape(hc, wc)
     flag = {int(h.slice_segment_address): int(getattr(h, "slice_loop_filter_across_slices_enabled_flag", 1))
             for h in img.slice_hdrs}
     out = np.zeros((hc, wc), np.uint16)
@@ -78,7 +84,8 @@ def lav_sao_avail(img, sps):
             for dy in (-1, 0, 1):
                 for dx in (-1, 0, 1):
                     ny, nx = ry + dy, rx + dx
-                    if 0 <= ny < hc and 0 <= nx < wc and (sl[ny, nx] == sl[ry, rx] or flag[int(sl[ry, rx])]):
+                    if 0 <= ny < hc and 0 <= nx < wc and (sl[ny, nx] == sl[ry, rx] or flag[int(sl[ry, rx])]) \
+                            and (tile is None or tile[ny, nx] == tile[ry, rx]):
                         m |= 1 << ((dy + 1) * 3 + (dx + 1))
             out[ry, rx] = m
     return out
@@ -121,9 +128,9 @@ def decode_picture(img, sps, pps, backend):
         return [geom.plane_view(o, 0, c).copy() for c in range(3)]
 
     out_spec = sao(sao_api.availability_from_picture(img, sps, pps), nf)
-    out_lav = sao(lav_sao_avail(img, sps), nf)
+    out_lav = sao(lav_sao_avail(img, sps, pps), nf)
     if nf is not None:
-        unfiltered = sao(lav_sao_avail(img, sps), None)
+        unfiltered = sao(lav_sao_avail(img, sps, pps), None)
         bypass, restored = lav_chroma_restored(nf, w, h, ctb_log2)
         for c in (1, 2):
             out_lav[c] = np.where(bypass & ~restored, unfiltered[c], out_lav[c])

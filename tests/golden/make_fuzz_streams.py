@@ -171,7 +171,12 @@ def pps_rbsp(cfg, sl=None) -> bytes:
     w.u(1, 0)                                                  # slice chroma qp offsets present
     w.u(1, 0); w.u(1, 0)                                       # weighted pred / bipred
     w.u(1, cfg["bypass"])                                      # transquant_bypass_enabled_flag
-    w.u(1, 0); w.u(1, 0)                                       # tiles, wavefront
+    tiles = cfg.get("tiles")
+    w.u(1, 1 if tiles else 0); w.u(1, 0)                       # tiles_enabled_flag, wavefront
+    if tiles:
+        w.ue(tiles[0] - 1); w.ue(tiles[1] - 1)                 # num_tile_columns_minus1, num_tile_rows_minus1
+        w.u(1, 1)                                              # uniform_spacing_flag
+        w.u(1, cfg["lf_across_tiles"])                         # loop_filter_across_tiles_enabled_flag
     w.u(1, 1)                                                  # pps_loop_filter_across_slices_enabled_flag
     ctl = cfg["dbk_disable"] or cfg["beta_offset_div2"] or cfg["tc_offset_div2"]
     w.u(1, 1 if ctl else 0)                                    # deblocking_filter_control_present_flag
@@ -202,6 +207,8 @@ def slice_header_bits(cfg, first: bool, address: int, qp: int, across: int) -> B
     w.u(1, 1); w.u(1, cfg["sao_chroma"])                       # slice_sao_luma_flag, slice_sao_chroma_flag
     w.se(qp - 26)                                              # slice_qp_delta (init_qp_minus26 = 0)
     w.u(1, across)                                             # slice_loop_filter_across_slices_enabled_flag
+    if cfg.get("tiles"):
+        w.ue(0)                                                # num_entry_point_offsets: one tile per slice
     w.align_one()                                              # byte_alignment()
     return w
 
@@ -343,7 +350,21 @@ def make_stream(ns, cfg):
     # slices of every picture: list of (first CTB address, qp, across flag)
     rng = np.random.default_rng(cfg["seed"] + 1)
     pictures = []
+    tile_ends = None
+    if cfg.get("tiles"):
+        # one slice per tile, in tile-scan order (6.5.1): slice_segment_address = raster address of the
+        # tile's first CTB.  Every slice has slice_loop_filter_across_slices_enabled_flag = 1, so the only
+        # thing that stops the in-loop filters at these boundaries is loop_filter_across_tiles_enabled_flag
+        # (uniform spacing with CTB counts divisible by the tile counts, see pps.py:87-91)
+        tc, tr = cfg["tiles"]
+        assert cfg["ctbs_w"] % tc == 0 and cfg["ctbs_h"] % tr == 0 and cfg["slices"] == tc * tr
+        cw, rh = cfg["ctbs_w"] // tc, cfg["ctbs_h"] // tr
+        starts = [j * rh * cfg["ctbs_w"] + i * cw for j in range(tr) for i in range(tc)]
+        tile_ends = [((j + 1) * rh - 1) * cfg["ctbs_w"] + (i + 1) * cw - 1 for j in range(tr) for i in range(tc)]
     for _ in range(cfg["pictures"]):
+        if tile_ends is not None:
+            pictures.append([(a, int(rng.choice(cfg["qps"])), 1) for a in starts])
+            continue
         starts = [0] + sorted(rng.choice(np.arange(1, n_ctb), size=min(cfg["slices"] - 1, n_ctb - 1),
                                          replace=False).tolist()) if cfg["slices"] > 1 else [0]
         # slice_loop_filter_across_slices_enabled_flag: 1, 0, 1, ... (the first slice has no left / upper slice)
@@ -357,6 +378,8 @@ def make_stream(ns, cfg):
     policy = Policy(cfg["seed"], cfg["dense"], cfg["big"])
     payloads = []
     ends = [[(pic[i + 1][0] if i + 1 < len(pic) else n_ctb) - 1 for i in range(len(pic))] for pic in pictures]
+    if tile_ends is not None:
+        ends = [list(tile_ends) for _ in pictures]             # a tile's last CTB in raster addressing
     state = {"pic": 0, "slice": 0}
 
     def hook(d):
@@ -474,11 +497,17 @@ STREAMS = [
                                 beta_offset_div2=-2, tc_offset_div2=3)),
     ("main8_big_levels_slices", dict(dense=True, big=True, slices=2, seed=16, qps=(8, 51), width=192, height=128,
                                      tu_depth=3, cb_qp_offset=-5, cr_qp_offset=6, tc_offset_div2=4)),
+    # 2x2 tiles (one slice each), loop_filter_across_tiles_enabled_flag = 0: tile-scan CTU order, intra
+    # availability, deblocking filterEdgeFlag and SAO neighbour availability at tile boundaries
+    ("main8_tiles_2x2_no_lf_across", dict(tiles=(2, 2), lf_across_tiles=0, slices=4, ctb_log2=5, width=128, height=128,
+                                          dense=True, seed=18, qps=(26, 34, 41), tc_offset_div2=2)),
+    ("main10_tiles_3x2_lf_across", dict(tiles=(3, 2), lf_across_tiles=1, slices=6, ctb_log2=4, width=96, height=64,
+                                        bit_depth=10, profile=2, dense=False, seed=19, qps=(24, 36), pictures=1)),
 ]
 BASE = dict(width=128, height=96, bit_depth=8, profile=1, ctb_log2=6, tu_depth=2, scaling_lists="off",
             strong_smoothing=1, sdh=1, transform_skip=1, bypass=0, cb_qp_offset=0, cr_qp_offset=0,
             dbk_disable=0, beta_offset_div2=0, tc_offset_div2=0, sao_chroma=1, pictures=2, slices=1,
-            qps=(24, 32), dense=True, big=False, seed=10)
+            qps=(24, 32), dense=True, big=False, seed=10, tiles=None, lf_across_tiles=1)
 
 
 def prepare(ns, cfg):
@@ -497,7 +526,14 @@ def main():
     ns = refshim.load(tempfile.mkdtemp(prefix="p265ref_"))
     os.makedirs(OUT_DIR, exist_ok=True)
     answers, manifest = {}, {}
+    only = set(sys.argv[1:])          # stream names: (re)generate just these, keep every other answer
+    if only:
+        answers = dict(np.load(os.path.join(HERE, "fuzz_ffmpeg.npz")))
+        with open(os.path.join(OUT_DIR, "manifest.json")) as fh:
+            manifest = json.load(fh)
     for name, over in STREAMS:
+        if only and name not in only:
+            continue
         cfg = dict(BASE, **over)
         stream, (imgs, sps, pps) = make_stream(ns, cfg)
         path = os.path.join(OUT_DIR, name + ".bin")

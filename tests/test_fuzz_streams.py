@@ -18,6 +18,8 @@ def test_oracle_chain_equals_libavcodec(name, cfg, c_oracle):
         assert total == [0, 0, 0]            # no rule on which the standard and libavcodec differ is in play
     if cfg["bypass"]:
         assert total[0] == 0                 # libavcodec's restore deviation is chroma-only
+    if cfg.get("tiles"):
+        assert total == [0, 0, 0]            # tiles: one slice each, every slice flag 1 -> only the tile rule acts
 
 
 def test_the_streams_cover_what_sanity_bin_does_not():
@@ -28,3 +30,5 @@ def test_the_streams_cover_what_sanity_bin_does_not():
     assert any(c["bypass"] for c in m.values()) and any(c["slices"] > 1 for c in m.values())
     assert any(c["dbk_disable"] for c in m.values()) and any(c["tc_offset_div2"] for c in m.values())
     assert any(c["cb_qp_offset"] for c in m.values()) and sum(c["tbs"] for c in m.values()) > 3000
+    tiles = [c for c in m.values() if c.get("tiles")]
+    assert any(not c["lf_across_tiles"] for c in tiles) and any(c["lf_across_tiles"] for c in tiles)
