@@ -442,8 +442,12 @@ def run_gpu(args):
                 futs.append(pool.residual(hb, h_ro, picture=p))
                 futs.append(pool.sao(h_rec, g1, 6, h_par, out=h_so, inplace=h_so is None, picture=p))
                 continue
-            e = engs[p % n_ctx]
+            # the two calls of a picture are independent of each other (a decoder filters picture n while
+            # it computes the residual of picture n+1): they go to DIFFERENT contexts, so the H2D copy of the
+            # reconstructed planes is not ordered behind the D2H copy of the residual planes
+            e = engs[(2 * p) % n_ctx] if args.e2e_split else engs[p % n_ctx]
             e.residual(hb, h_ro)
+            e = engs[(2 * p + 1) % n_ctx] if args.e2e_split else e
             if h_so is None:
                 e.sao(h_rec, g1, 6, h_par, inplace=True)
             else:
@@ -801,6 +805,8 @@ def main():
     ap.add_argument("--no-verify", dest="verify", action="store_false",
                     help="skip the oracle comparison of the timed buffers")
     ap.add_argument("--e2e-dense", action="store_true", help="e2e leg with the round-1 transport (A/B)")
+    ap.add_argument("--no-e2e-split", dest="e2e_split", action="store_false",
+                    help="queue a picture's residual and SAO call on the same context (round-1 behaviour)")
     ap.add_argument("--e2e-pool", action="store_true",
                     help="e2e leg through EnginePool over every visible GPU in this one process")
     args = ap.parse_args()

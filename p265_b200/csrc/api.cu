@@ -221,6 +221,12 @@ int p265_ctx_destroy(p265_ctx *ctx) {
     for (int i = 0; i < p265_ctx::kScratchSlots; i++)
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->xtus) cudaFree(ctx->xtus);
+    if (ctx->aux_stream) {
+        cudaStreamSynchronize(ctx->aux_stream);
+        cudaStreamDestroy(ctx->aux_stream);
+        cudaEventDestroy(ctx->ev_fork);
+        cudaEventDestroy(ctx->ev_join);
+    }
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return P265_OK;

@@ -20,6 +20,8 @@ struct p265_ctx {
     enum { kScratchSlots = 12 };
     void *scratch[kScratchSlots] = {nullptr};
     size_t scratch_bytes[kScratchSlots] = {0};
+    cudaStream_t aux_stream = nullptr;  // second chain of residual bins (tuning knob P265_SPLIT), created on demand
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     void *xtus = nullptr;  // expanded TU descriptors of the current residual launch (grow-only)
     size_t xtus_bytes = 0;
 };

@@ -8,6 +8,7 @@
 // -> stage 2 transpose) is warp-private shared memory fenced by __syncwarp(), so there
 // is no __syncthreads() in the kernel and CTAs are only a scheduling container.
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -663,12 +664,16 @@ static int fill_args(KernelArgs &a, const p265_tu_desc *d_tus, const int32_t bin
     return P265_OK;
 }
 
+// plain = first kernel of a chain on the auxiliary stream: ordered behind expand_kernel by an event, no
+// programmatic launch, nothing to wait for inside the kernel.  pct_limit (1..100, 0 = the P265_GRID_PCT
+// knob): share of the occupancy-maximal persistent grid to launch (two chains sharing the SMs).
 template <int BIN, int SF>
-static int launch_bin(p265_ctx *ctx, KernelArgs a, bool first) {
+static int launch_bin(p265_ctx *ctx, KernelArgs a, bool first, cudaStream_t stream = nullptr, bool plain = false,
+                      int pct_limit = 0) {
     // behind expand_kernel (first big-size bin: wait for it) or overlapping the previous bin
     const bool expanded = a.n_tb[0] + a.n_tb[1] + (a.sf ? a.n_tb[2] + a.n_tb[3] : 0) > 0;
-    const bool overlap_previous = !first || expanded;
-    a.wait_prev = (first && expanded) ? 1 : 0;
+    const bool overlap_previous = !plain && (!first || expanded);
+    a.wait_prev = (!plain && first && expanded) ? 1 : 0;
     const int items = a.first_item[BIN + 1] - a.first_item[BIN];
     if (items == 0) return P265_OK;
     constexpr int smem = BinCfg<BIN>::smem;
@@ -691,9 +696,11 @@ static int launch_bin(p265_ctx *ctx, KernelArgs a, bool first) {
         pct = e ? atoi(e) : 100;
         if (pct < 1 || pct > 100) pct = 100;
     }
-    int occ_use = (occ * pct + 99) / 100;
-    if (occ_use < 1) occ_use = 1;
-    const int max_warps = ctx->sm_count * occ_use * kWarpsPerCta;
+    const int pct_use = pct_limit > 0 ? pct_limit : pct;
+    // CTAs over the whole device (not per SM): a 70 % grid of a 4-CTA kernel is 2.8 CTAs per SM on average
+    int max_ctas = (int)((int64_t)ctx->sm_count * occ * pct_use / 100);
+    if (max_ctas < 1) max_ctas = 1;
+    const int max_warps = max_ctas * kWarpsPerCta;
     const int rounds = (items + max_warps - 1) / max_warps;
     const int warps = SmallStream<BIN>::on ? items : (items + rounds - 1) / rounds;  // streaming bins: one warp per item
     const int grid = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -701,7 +708,7 @@ static int launch_bin(p265_ctx *ctx, KernelArgs a, bool first) {
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kWarpsPerCta * 32);
     cfg.dynamicSmemBytes = smem;
-    cfg.stream = ctx->stream;
+    cfg.stream = stream ? stream : ctx->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -729,20 +736,65 @@ static int launch_residual_sf(p265_ctx *ctx, const KernelArgs &a) {
         order[1] = o[1]; order[2] = o[2]; order[3] = o[3]; order[0] = o[0];
     }
     int rc = P265_OK;
-    bool first = true;
-    for (int i = 0; i < 4; i++) {
-        const int b = order[i];
-        if (!a.n_tb[b]) continue;
-        switch (b) {
-            case 0: rc = launch_bin<0, SF>(ctx, a, first); break;
-            case 1: rc = launch_bin<1, SF>(ctx, a, first); break;
-            case 2: rc = launch_bin<2, SF>(ctx, a, first); break;
-            default: rc = launch_bin<3, SF>(ctx, a, first); break;
+    // Two chains sharing the SMs (tuning knob P265_SPLIT, e.g. "03|12": bins 32x32 + 4x4 on the context's
+    // stream, 16x16 + 8x8 on an auxiliary stream, forked and joined by events; P265_SPLIT_PCT "a,b" = share
+    // of each chain's persistent grids).  The issue-bound big bins and the latency-bound small ones then
+    // run side by side instead of one after the other.
+    static int split_a = -1, split_b = 0, pct_a = 70, pct_b = 70;
+    if (split_a < 0) {
+        split_a = 0;
+        const char *e = getenv("P265_SPLIT");
+        if (e && strlen(e) == 5 && e[2] == '|') {
+            int seen = 0, ma = 0, mb = 0;
+            for (int i = 0; i < 5; i++) {
+                if (i == 2) continue;
+                const int b = e[i] - '0';
+                if (b < 0 || b > 3) { seen = 0; break; }
+                seen |= 1 << b;
+                (i < 2 ? ma : mb) |= 1 << b;
+            }
+            if (seen == 15) { split_a = ma; split_b = mb; }
         }
-        if (rc) return rc;
-        first = false;
+        const char *p = getenv("P265_SPLIT_PCT");
+        if (p) {
+            int x = 0, y = 0;
+            if (sscanf(p, "%d,%d", &x, &y) == 2 && x >= 10 && x <= 100 && y >= 10 && y <= 100) { pct_a = x; pct_b = y; }
+        }
     }
-    return P265_OK;
+    auto chain = [&](int mask, cudaStream_t st, bool aux, int pct_limit) -> int {
+        bool first = true;
+        for (int i = 0; i < 4; i++) {
+            const int b = order[i];
+            if (!a.n_tb[b] || !(mask & (1 << b))) continue;
+            const bool plain = aux && first;
+            int r;
+            switch (b) {
+                case 0: r = launch_bin<0, SF>(ctx, a, first, st, plain, pct_limit); break;
+                case 1: r = launch_bin<1, SF>(ctx, a, first, st, plain, pct_limit); break;
+                case 2: r = launch_bin<2, SF>(ctx, a, first, st, plain, pct_limit); break;
+                default: r = launch_bin<3, SF>(ctx, a, first, st, plain, pct_limit); break;
+            }
+            if (r) return r;
+            first = false;
+        }
+        return P265_OK;
+    };
+    auto has = [&](int mask) { for (int b = 0; b < 4; b++) if ((mask & (1 << b)) && a.n_tb[b]) return true; return false; };
+    if (split_a && has(split_a) && has(split_b)) {
+        if (!ctx->aux_stream) {
+            P265_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+            P265_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            P265_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        }
+        P265_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));            // expand_kernel (and everything before) is done
+        P265_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+        if ((rc = chain(split_b, ctx->aux_stream, true, pct_b))) return rc;
+        if ((rc = chain(split_a, ctx->stream, false, pct_a))) return rc;
+        P265_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+        P265_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        return P265_OK;
+    }
+    return chain(15, ctx->stream, false, 0);
 }
 
 int launch_residual(p265_ctx *ctx, const p265_tu_desc *d_tus, const int32_t bin_counts[4], const int16_t *d_coeffs,

@@ -156,6 +156,8 @@ def bench_residual(args, time_residual):
     if not os.environ.get("P265_KB_NO_DENSE"):
         full = full.densified()   # arena in descriptor order: P265_RES_DENSE_ARENA applies
     time_residual(full, "4k10 mix, SF replicated")
+    if os.environ.get("P265_KB_MIX_ONLY"):
+        return
     if not args.quick:
         time_residual(full, "4k10 mix, SF general", force_general=True)
         flat = ResidualBatch(full.geom, full.tus, full.coeffs, None, covers_all=True)
