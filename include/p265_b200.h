@@ -164,6 +164,14 @@ int p265_sync(p265_ctx *ctx);
  *   - overlap between pictures comes from SEVERAL contexts (one per in-flight picture): the
  *     H2D copy of one picture then overlaps the kernels and the D2H copy of another.        */
 int p265_ctx_set_async(p265_ctx *ctx, int enable);
+/* Timeline of the host entry points (p265_residual_batch_packed, p265_sao_batch): with tracing on, every
+ * call leaves four marks on the context's stream (0 call start, 1 inputs copied, 2 kernels done, 3 outputs
+ * back).  p265_trace_read synchronises the context, writes up to max_marks triples (kind: 1 residual,
+ * 2 SAO; phase; milliseconds since the process enabled tracing on this device) into out[3 * max_marks],
+ * forgets them and returns how many it wrote.  The reference has no tracing of this path (its log.py
+ * writes syntax-element logs); this is what tools/e2e_trace.py draws the copy-engine occupancy from.  */
+int p265_ctx_set_trace(p265_ctx *ctx, int enable);
+int p265_trace_read(p265_ctx *ctx, double *out, int max_marks);
 int p265_sm_count(p265_ctx *ctx);
 /* kernels launched through this context so far (bench.py reports it as gpu_launches) */
 uint64_t p265_launch_count(p265_ctx *ctx);

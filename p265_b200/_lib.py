@@ -29,7 +29,7 @@ SYMBOLS = (
     "p265_reconstruct_batch", "p265_reconstruct_batch_dev", "p265_deblock_batch",
     "p265_deblock_batch_dev", "p265_int_peak",
     "p265_residual_batch_packed", "p265_residual_batch_packed_dev", "p265_loop_filter_batch",
-    "p265_pcie_probe",
+    "p265_pcie_probe", "p265_ctx_set_trace", "p265_trace_read",
 )
 ABI_VERSION = 2
 
@@ -86,6 +86,8 @@ def load():
     lib.p265_residual_batch_packed.argtypes = [vp, vp, i64p, vp, C.c_size_t, vp, C.POINTER(Geom), vp, C.c_int]
     lib.p265_residual_batch_packed_dev.argtypes = [vp, vp, i64p, vp, vp, C.POINTER(Geom), vp, vp, vp, C.c_int]
     lib.p265_loop_filter_batch.argtypes = [vp, vp, C.POINTER(Geom), C.c_int, vp, vp, vp, vp]
+    lib.p265_ctx_set_trace.argtypes = [vp, C.c_int]
+    lib.p265_trace_read.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
     lib.p265_pcie_probe.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = lib
     return lib

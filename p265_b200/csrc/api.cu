@@ -29,6 +29,17 @@ int cuda_error(cudaError_t e, const char *what, const char *file, int line) {
     return e == cudaErrorMemoryAllocation ? P265_ENOMEM : P265_ECUDA;
 }
 
+// process-wide time origin of the traces (one per device would do; events of one device share a clock)
+static cudaEvent_t g_trace_origin[64] = {nullptr};
+
+void trace_mark(p265_ctx *ctx, int kind, int phase) {
+    if (!ctx->trace) return;
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, ctx->stream);
+    ctx->marks.push_back({kind, phase, ev});
+}
+
 static int ensure(p265_ctx *ctx, int slot, size_t bytes, void **out) {
     if (bytes == 0) bytes = 16;
     if (ctx->scratch_bytes[slot] < bytes) {
@@ -221,6 +232,7 @@ int p265_ctx_destroy(p265_ctx *ctx) {
     for (int i = 0; i < p265_ctx::kScratchSlots; i++)
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->xtus) cudaFree(ctx->xtus);
+    for (const auto &m : ctx->marks) cudaEventDestroy(m.ev);
     if (ctx->aux_stream) {
         cudaStreamSynchronize(ctx->aux_stream);
         cudaStreamDestroy(ctx->aux_stream);
@@ -249,6 +261,39 @@ static int finish(p265_ctx *ctx) {
     if (ctx->async_mode) return P265_OK;
     P265_CUDA(cudaStreamSynchronize(ctx->stream));
     return P265_OK;
+}
+
+int p265_ctx_set_trace(p265_ctx *ctx, int enable) {
+    if (!ctx) return set_error(P265_EINVAL, "ctx is NULL");
+    P265_CUDA(cudaSetDevice(ctx->device));
+    cudaEvent_t &origin = g_trace_origin[ctx->device & 63];
+    if (enable && !origin) {
+        P265_CUDA(cudaEventCreate(&origin));
+        P265_CUDA(cudaEventRecord(origin, ctx->stream));
+        P265_CUDA(cudaEventSynchronize(origin));
+    }
+    ctx->trace = enable != 0;
+    return P265_OK;
+}
+
+int p265_trace_read(p265_ctx *ctx, double *out, int max_marks) {
+    if (!ctx || (max_marks > 0 && !out)) return set_error(P265_EINVAL, "p265_trace_read: NULL argument");
+    P265_CUDA(cudaSetDevice(ctx->device));
+    P265_CUDA(cudaStreamSynchronize(ctx->stream));
+    int n = 0;
+    for (const auto &m : ctx->marks) {
+        float ms = 0;
+        if (n < max_marks && cudaEventElapsedTime(&ms, g_trace_origin[ctx->device & 63], m.ev) == cudaSuccess) {
+            out[3 * n] = m.kind;
+            out[3 * n + 1] = m.phase;
+            out[3 * n + 2] = ms;
+            n++;
+        }
+        cudaEventDestroy(m.ev);
+    }
+    cudaGetLastError();
+    ctx->marks.clear();
+    return n;
 }
 
 int p265_sm_count(p265_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
@@ -356,9 +401,11 @@ int p265_residual_batch_packed(p265_ctx *ctx, const p265_tu_desc *tus, const int
         if ((rc = ensure(ctx, 3, P265_SF_BYTES, &d_sf))) return rc;
         P265_CUDA(cudaMemcpyAsync(d_sf, scaling_factor, P265_SF_BYTES, cudaMemcpyHostToDevice, ctx->stream));
     }
+    trace_mark(ctx, 1, 0);
     if (n) {
         P265_CUDA(cudaMemcpyAsync(d_tus, tus, sizeof(p265_tu_desc) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
         P265_CUDA(cudaMemcpyAsync(d_st, stream, stream_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        trace_mark(ctx, 1, 1);
         if ((rc = launch_unpack(ctx, (const p265_tu_desc *)d_tus, bin_counts, (const uint8_t *)d_st, (int16_t *)d_arena,
                                 (p265_tu_desc *)d_tus2)))
             return rc;
@@ -366,7 +413,9 @@ int p265_residual_batch_packed(p265_ctx *ctx, const p265_tu_desc *tus, const int
     rc = launch_residual(ctx, (const p265_tu_desc *)d_tus2, bin_counts, (const int16_t *)d_arena, (const uint8_t *)d_sf,
                          geom, (int16_t *)d_out, flags | P265_RES_DENSE_ARENA);
     if (rc) return rc;
+    trace_mark(ctx, 1, 2);
     P265_CUDA(cudaMemcpyAsync(residual, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    trace_mark(ctx, 1, 3);
     return finish(ctx);
 }
 
@@ -541,14 +590,17 @@ int p265_sao_batch(p265_ctx *ctx, const void *rec, void *out, const p265_pic_geo
     if ((rc = ensure(ctx, 2, plane_bytes, &d_rec))) return rc;
     if ((rc = ensure(ctx, 6, plane_bytes, &d_out))) return rc;
     if ((rc = ensure(ctx, 0, sizeof(p265_sao_ctb) * ctbs, &d_par))) return rc;
+    trace_mark(ctx, 2, 0);
     P265_CUDA(cudaMemcpyAsync(d_rec, rec, plane_bytes, cudaMemcpyHostToDevice, ctx->stream));
     P265_CUDA(cudaMemcpyAsync(d_par, params, sizeof(p265_sao_ctb) * ctbs, cudaMemcpyHostToDevice, ctx->stream));
     if (no_filter) {
         if ((rc = ensure(ctx, 7, nf_bytes, &d_nf))) return rc;
         P265_CUDA(cudaMemcpyAsync(d_nf, no_filter, nf_bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
+    trace_mark(ctx, 2, 1);
     if ((rc = launch_sao(ctx, d_rec, d_out, geom, ctb_log2, (const p265_sao_ctb *)d_par, (const uint8_t *)d_nf)))
         return rc;
+    trace_mark(ctx, 2, 2);
     // In place on a page-locked host buffer: the host already holds every sample SAO leaves alone, so only
     // the CTB components with sao type != 0 cross the bus again, stored by a kernel straight into the
     // caller's buffer.  Otherwise: the plane rows by the copy engine.
@@ -556,6 +608,7 @@ int p265_sao_batch(p265_ctx *ctx, const void *rec, void *out, const p265_pic_geo
     if (h_dev) rc = launch_sao_writeback(ctx, d_out, h_dev, geom, ctb_log2, (const p265_sao_ctb *)d_par);
     else rc = copy_planes_to_host(ctx, out, d_out, geom, bytes);
     if (rc) return rc;
+    trace_mark(ctx, 2, 3);
     return finish(ctx);
 }
 

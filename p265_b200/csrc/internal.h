@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "p265_b200.h"
 
@@ -20,6 +21,12 @@ struct p265_ctx {
     enum { kScratchSlots = 12 };
     void *scratch[kScratchSlots] = {nullptr};
     size_t scratch_bytes[kScratchSlots] = {0};
+    // optional timeline of the host entry points (p265_ctx_set_trace): events on the context's stream
+    // around the phases of a call (kind: 1 residual, 2 SAO, 3 loop filter; phase: 0 start, 1 inputs
+    // copied, 2 kernels done, 3 outputs back)
+    bool trace = false;
+    struct TraceMark { int kind, phase; cudaEvent_t ev; };
+    std::vector<TraceMark> marks;
     cudaStream_t aux_stream = nullptr;  // second chain of residual bins (tuning knob P265_SPLIT), created on demand
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     void *xtus = nullptr;  // expanded TU descriptors of the current residual launch (grow-only)
@@ -29,6 +36,7 @@ struct p265_ctx {
 namespace p265 {
 
 int set_error(int code, const char *fmt, ...);
+void trace_mark(p265_ctx *ctx, int kind, int phase);
 int cuda_error(cudaError_t e, const char *what, const char *file, int line);
 
 #define P265_CUDA(expr)                                                        \

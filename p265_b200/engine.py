@@ -54,6 +54,19 @@ class Engine:
         _lib.check(self._lib.p265_ctx_set_async(self._ctx, 1 if enable else 0))
         self._async = bool(enable)
 
+    def set_trace(self, enable: bool = True):
+        """Record a timeline of the host calls on this context (see trace())."""
+        _lib.check(self._lib.p265_ctx_set_trace(self._ctx, 1 if enable else 0))
+
+    def trace(self, max_marks: int = 4096):
+        """[(kind, phase, ms)] since the last read: kind 1 residual / 2 SAO; phase 0 call start, 1 inputs
+        copied, 2 kernels done, 3 outputs back; ms on the device clock since tracing was first enabled."""
+        buf = (C.c_double * (3 * max_marks))()
+        n = self._lib.p265_trace_read(self._ctx, buf, max_marks)
+        if n < 0:
+            _lib.check(n)
+        return [(int(buf[3 * i]), int(buf[3 * i + 1]), float(buf[3 * i + 2])) for i in range(n)]
+
     @property
     def sm_count(self) -> int:
         return int(self._lib.p265_sm_count(self._ctx))

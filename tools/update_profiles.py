@@ -1,13 +1,18 @@
 #!/usr/bin/env python
 """Copy the evidence of a tools/gpu_profile_final.sh run from gpurun_out/ into profiles/ (tracked).
 
-    python tools/update_profiles.py <tag> [deblock-report-tag]
+    python tools/update_profiles.py <tag> [deblock-report-tag] [--round r2]
 """
 import json, os, re, shutil, subprocess, sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT, PROF = os.path.join(REPO, "gpurun_out"), os.path.join(REPO, "profiles")
-tag = sys.argv[1]
-dbk = sys.argv[2] if len(sys.argv) > 2 else None
+argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+RND = "r1"
+if "--round" in sys.argv:
+    RND = sys.argv[sys.argv.index("--round") + 1]
+    argv = [a for a in argv if a != RND]
+tag = argv[0]
+dbk = argv[1] if len(argv) > 1 else None
 
 
 def summary(rep):
@@ -23,21 +28,23 @@ def first_json_line(path):
 
 
 line = first_json_line(os.path.join(OUT, "bench_%s.json" % tag))
-json.dump(line, open(os.path.join(PROF, "r1_bench_line.json"), "w"), indent=1)
-ref = first_json_line(os.path.join(OUT, "bench_%s_reference.json" % tag))
-json.dump(ref, open(os.path.join(PROF, "r1_bench_reference_line.json"), "w"), indent=1)
-shutil.copy(os.path.join(OUT, "launches_%s.csv" % tag), os.path.join(PROF, "r1_launches.csv"))
+json.dump(line, open(os.path.join(PROF, RND + "_bench_line.json"), "w"), indent=1)
+if os.path.exists(os.path.join(OUT, "bench_%s_reference.json" % tag)):
+    ref = first_json_line(os.path.join(OUT, "bench_%s_reference.json" % tag))
+    json.dump(ref, open(os.path.join(PROF, RND + "_bench_reference_line.json"), "w"), indent=1)
+shutil.copy(os.path.join(OUT, "launches_%s.csv" % tag), os.path.join(PROF, RND + "_launches.csv"))
 main = summary(os.path.join(OUT, "prof_%s.ncu-rep" % tag))
-open(os.path.join(PROF, "r1_ncu_summary.txt"), "w").write(main)
-other = summary(os.path.join(OUT, "prof_other_%s.ncu-rep" % tag))
-if dbk:
-    other += summary(os.path.join(OUT, "prof_%s.ncu-rep" % dbk))
-open(os.path.join(PROF, "r1_other_kernels_summary.txt"), "w").write(other)
+open(os.path.join(PROF, RND + "_ncu_summary.txt"), "w").write(main)
+if os.path.exists(os.path.join(OUT, "prof_other_%s.ncu-rep" % tag)):
+    other = summary(os.path.join(OUT, "prof_other_%s.ncu-rep" % tag))
+    if dbk:
+        other += summary(os.path.join(OUT, "prof_%s.ncu-rep" % dbk))
+    open(os.path.join(PROF, RND + "_other_kernels_summary.txt"), "w").write(other)
 
 # DRAM traffic per picture of the capture (pictures per launch = bench default of the capture command)
 pics = line["config"]["pics_per_step_per_gpu"]
 blocks = re.split(r"^===== ", main, flags=re.M)[1:]
-tr = {"source": "profiles/r1_ncu_summary.txt (ncu --set full, %d pictures per launch)" % pics}
+tr = {"source": "profiles/%s_ncu_summary.txt (ncu --set full, %d pictures per launch)" % (RND, pics)}
 res_bytes, n_res = 0.0, 0
 for b in blocks:
     name = b.splitlines()[0]
