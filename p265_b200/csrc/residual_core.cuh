@@ -897,14 +897,47 @@ template <int SF, bool SLOW>
 P265_HD void tb4_lane(const TbParams &t, const uint32_t (&w)[8], const uint8_t *sf) {
     if (!t.valid) return;
     const uint8_t *sfm = (SF != SF_NONE) ? sf : nullptr;
-    if (t.flags & (P265_TU_SKIP | P265_TU_BYPASS)) {
-        lane_special<4>(t, w, sfm);
-        return;
-    }
     uint32_t mrow[4] = {0, 0, 0, 0};  // ScalingFactor bytes, one word per row
     if (SF != SF_NONE && sfm) {
         const uint4 mv = *reinterpret_cast<const uint4 *>(sfm);
         mrow[0] = mv.x; mrow[1] = mv.y; mrow[2] = mv.z; mrow[3] = mv.w;
+    }
+    if (t.flags & (P265_TU_SKIP | P265_TU_BYPASS)) {
+        // transform-skip / bypass, element-wise (8.6.2, 8.6.4.2).  Same packed level * factor products as
+        // the transform path below: the byte-by-byte form of lane_special (16 dependent shared-memory
+        // byte loads per TB) made the 10 % transform-skip TBs of the 4K mix 20 % of this bin's stall samples
+        if (SF != SF_NONE && !sfm) mrow[0] = mrow[1] = mrow[2] = mrow[3] = 0x01010101u;  // host only
+        P265_UNROLL
+        for (int y = 0; y < 4; y++) {
+            uint32_t o[2];
+            P265_UNROLL
+            for (int pr = 0; pr < 2; pr++) {
+                const uint32_t ww = w[y * 2 + pr];
+                int r0, r1;
+                if (t.flags & P265_TU_BYPASS) {
+                    r0 = sx_lo(ww);
+                    r1 = sx_hi(ww);
+                } else {
+                    int v0, v1;
+                    if (SF != SF_NONE) {
+                        const uint32_t f = sf_pair(mrow[y], pr);
+                        v0 = dp2a_lo_su((int)ww, f, 0);
+                        v1 = dp2a_hi_su((int)ww, f, 0);
+                    } else {
+                        v0 = sx_lo(ww);
+                        v1 = sx_hi(ww);
+                    }
+                    int d0 = dequant(v0, t.w, t), d1 = dequant(v1, t.w, t);
+                    d0 = d0 < -32768 ? -32768 : (d0 > 32767 ? 32767 : d0);
+                    d1 = d1 < -32768 ? -32768 : (d1 > 32767 ? 32767 : d1);
+                    r0 = (d0 * 128 + t.rnd2) >> t.sh2;
+                    r1 = (d1 * 128 + t.rnd2) >> t.sh2;
+                }
+                o[pr] = (uint32_t)pack_sat(r0, r1);
+            }
+            *reinterpret_cast<uint2 *>(t.dst + (size_t)y * t.stride) = make_uint2(o[0], o[1]);
+        }
+        return;
     }
     int d[4][4];  // [y][x]
     if (SF != SF_NONE) {

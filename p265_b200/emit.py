@@ -65,7 +65,7 @@ class PictureSink:
         tus = np.array(self.recs, dtype=TU_DESC) if self.recs else np.zeros(0, dtype=TU_DESC)
         stream = np.frombuffer(bytes(self.stream), dtype=np.uint8)
         covers = self.area == geom.width * geom.height + 2 * geom.width_c * geom.height_c and geom.n_pics == 1
-        return PackedResidualBatch(geom, sort_by_size(tus), stream, scaling_factor, covers_all=covers)
+        return PackedResidualBatch(geom, sort_by_size(tus, geom), stream, scaling_factor, covers_all=covers)
 
 
 _ATTR = "_p265_b200_sink"

@@ -95,7 +95,7 @@ def pack_pictures(imgs, sps, scaling_factor=None) -> ResidualBatch:
             off += n * n
     tus = np.array(recs, dtype=TU_DESC) if recs else np.zeros(0, dtype=TU_DESC)
     coeffs = np.concatenate(blocks) if blocks else np.zeros(0, dtype=np.int16)
-    return ResidualBatch(geom=geom, tus=sort_by_size(tus), coeffs=coeffs,
+    return ResidualBatch(geom=geom, tus=sort_by_size(tus, geom), coeffs=coeffs,
                          scaling_factor=scaling_factor, covers_all=tbs_cover_planes(tus, geom))
 
 

@@ -166,17 +166,27 @@ class ResidualBatch:
         return self._dense
 
 
-def size_kind_order(tus: np.ndarray) -> np.ndarray:
+def size_kind_order(tus: np.ndarray, geom=None) -> np.ndarray:
     """Permutation that sorts descriptors largest TBs first -- the order `p265_residual_*`
-    requires -- and, inside a size, clusters the kinds (normal, DST, transform-skip, bypass) so
-    that a warp's lanes take the same path; stable otherwise (picture / decoding order kept).
-    The one ordering rule of the packed format: the packer and the synthetic workloads share it."""
-    key = (-(tus["log2n"].astype(np.int32)) * 16 + (tus["flags"] & (TU_DST | TU_SKIP | TU_BYPASS)))
+    requires -- and, inside a size, clusters TBs that take the same path through the kernels so
+    that a warp's 32 lanes (32 small TBs) agree: the kinds (normal, DST, transform-skip, bypass)
+    and, when the bit depths are known (`geom`), whether the TB's dequantisation is the
+    left-shift form of 8.6.3 (qP / 6 >= bdShift: `clip16(level * m) << n` instead of
+    `(level * m + round) >> n`) -- the kernels pick that slower form per warp, and unsorted almost
+    every warp of the 8x8 / 4x4 bins holds one such TB.  Stable otherwise (picture / decoding order
+    kept).  The one ordering rule of the packed format: the packer, the parser-side emitter and the
+    synthetic workloads share it; any order inside a size is CORRECT, this one is fast."""
+    key = (-(tus["log2n"].astype(np.int32)) * 32 + (tus["flags"] & (TU_DST | TU_SKIP | TU_BYPASS)).astype(np.int32) * 2)
+    if geom is not None:
+        bd = np.where(tus["c_idx"] == 0, geom.bit_depth_y, geom.bit_depth_c).astype(np.int32)
+        left_shift = (tus["qp"].astype(np.int32) // 6 >= bd + tus["log2n"].astype(np.int32) - 5) & \
+            ((tus["flags"] & (TU_PRESCALED | TU_BYPASS)) == 0)
+        key = key + left_shift.astype(np.int32)
     return np.argsort(key, kind="stable")
 
 
-def sort_by_size(tus: np.ndarray) -> np.ndarray:
-    return np.ascontiguousarray(tus[size_kind_order(tus)])
+def sort_by_size(tus: np.ndarray, geom=None) -> np.ndarray:
+    return np.ascontiguousarray(tus[size_kind_order(tus, geom)])
 
 
 def sf_offset(size_id: int, matrix_id: int) -> int:

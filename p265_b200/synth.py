@@ -146,7 +146,7 @@ def residual_batch(name: str, n_pics: int = 1, seed: int | None = None, stress: 
     geom = PicGeom(cfg["width"], cfg["height"], n_pics, cfg["bit_depth"], cfg["bit_depth"])
     sf = pack_scaling_factor(default_scaling_factor()) if cfg["scaling_lists"] else None
     # same ordering rule as the product packer (picture.sort_by_size: size, then kind)
-    return ResidualBatch(geom=geom, tus=sort_by_size(np.concatenate(tus)),
+    return ResidualBatch(geom=geom, tus=sort_by_size(np.concatenate(tus), geom),
                          coeffs=np.concatenate(arenas), scaling_factor=sf, covers_all=True)
 
 
