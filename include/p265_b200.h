@@ -265,11 +265,13 @@ int p265_loop_filter_batch(p265_ctx *ctx, void *planes /* host in/out */, const 
 /* Register-resident integer-pipe microbenchmark; kind: 0 IMAD, 1 IADD3, 2 IMAD+IADD3
  * interleaved, 3 DP2A, 4 SHF, 5 DP2A+IADD3.  Returns lane-ops per second.           */
 int p265_int_peak(p265_ctx *ctx, int kind, double *ops_per_s, double *ms);
-/* Plain page-locked host <-> device copies on two streams at once (what the host entry points
- * are made of): `bytes` per direction and repetition, both directions concurrently.  Returns
- * the two rates in bytes per second -- the ceiling bench.py compares its end-to-end number
- * with (e2e.pcie_frac).  One direction alone: pass NULL for the other rate.                   */
-int p265_pcie_probe(p265_ctx *ctx, size_t bytes, int reps, double *h2d_bytes_per_s,
+/* Plain page-locked host <-> device copies on two streams at once (what the host entry points are made
+ * of): copies of `bytes`, `reps` per direction, both directions concurrently, cycling through `n_buffers`
+ * distinct host buffers per direction (1 = the same buffer over and over, which stays in the host's
+ * last-level cache and is what copy benchmarks usually report; a decoder moves pictures between many
+ * buffers).  Returns the two rates in bytes per second -- the ceiling bench.py compares its end-to-end
+ * number with (e2e.pcie_frac).  One direction alone: pass NULL for the other rate.                    */
+int p265_pcie_probe(p265_ctx *ctx, size_t bytes, int n_buffers, int reps, double *h2d_bytes_per_s,
                     double *d2h_bytes_per_s);
 
 #ifdef __cplusplus

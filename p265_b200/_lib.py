@@ -88,7 +88,7 @@ def load():
     lib.p265_loop_filter_batch.argtypes = [vp, vp, C.POINTER(Geom), C.c_int, vp, vp, vp, vp]
     lib.p265_ctx_set_trace.argtypes = [vp, C.c_int]
     lib.p265_trace_read.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
-    lib.p265_pcie_probe.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.p265_pcie_probe.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = lib
     return lib
 

@@ -40,12 +40,29 @@ void trace_mark(p265_ctx *ctx, int kind, int phase) {
     ctx->marks.push_back({kind, phase, ev});
 }
 
+static int ensure(p265_ctx *ctx, int slot, size_t bytes, void **out);
+
+// ScalingFactor table -> scratch slot 3, copied only when its content changed since the last upload of this
+// context (one 4 KB copy less per picture on the H2D engine; the stream orders a new upload behind the kernels
+// that still read the old table)
+static int upload_sf(p265_ctx *ctx, const uint8_t *scaling_factor, void **d_sf) {
+    int rc = ensure(ctx, 3, P265_SF_BYTES, d_sf);
+    if (rc) return rc;
+    if (ctx->sf_shadow_valid && memcmp(ctx->sf_shadow, scaling_factor, P265_SF_BYTES) == 0) return P265_OK;
+    memcpy(ctx->sf_shadow, scaling_factor, P265_SF_BYTES);   // the copy below reads OUR copy: the caller's may be gone by then
+    ctx->sf_shadow_valid = false;
+    P265_CUDA(cudaMemcpyAsync(*d_sf, ctx->sf_shadow, P265_SF_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->sf_shadow_valid = true;
+    return P265_OK;
+}
+
 static int ensure(p265_ctx *ctx, int slot, size_t bytes, void **out) {
     if (bytes == 0) bytes = 16;
     if (ctx->scratch_bytes[slot] < bytes) {
         if (ctx->scratch[slot]) P265_CUDA(cudaFree(ctx->scratch[slot]));
         ctx->scratch[slot] = nullptr;
         ctx->scratch_bytes[slot] = 0;
+        if (slot == 3) ctx->sf_shadow_valid = false;
         size_t cap = bytes + bytes / 4;  // grow-only with head-room
         P265_CUDA(cudaMalloc(&ctx->scratch[slot], cap));
         ctx->scratch_bytes[slot] = cap;
@@ -338,8 +355,7 @@ int p265_residual_batch(p265_ctx *ctx, const p265_tu_desc *tus, const int32_t bi
     if ((rc = ensure(ctx, 1, sizeof(int16_t) * n_coeffs + 64, &d_co))) return rc;
     if ((rc = ensure(ctx, 2, out_bytes, &d_out))) return rc;
     if (scaling_factor) {
-        if ((rc = ensure(ctx, 3, P265_SF_BYTES, &d_sf))) return rc;
-        P265_CUDA(cudaMemcpyAsync(d_sf, scaling_factor, P265_SF_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = upload_sf(ctx, scaling_factor, &d_sf))) return rc;
     }
     if (n) {
         P265_CUDA(cudaMemcpyAsync(d_tus, tus, sizeof(p265_tu_desc) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
@@ -398,8 +414,7 @@ int p265_residual_batch_packed(p265_ctx *ctx, const p265_tu_desc *tus, const int
     if ((rc = ensure(ctx, 8, sizeof(int16_t) * (size_t)dense_elems(bin_counts) + 64, &d_arena))) return rc;
     if ((rc = ensure(ctx, 9, sizeof(p265_tu_desc) * (size_t)n, &d_tus2))) return rc;
     if (scaling_factor) {
-        if ((rc = ensure(ctx, 3, P265_SF_BYTES, &d_sf))) return rc;
-        P265_CUDA(cudaMemcpyAsync(d_sf, scaling_factor, P265_SF_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = upload_sf(ctx, scaling_factor, &d_sf))) return rc;
     }
     trace_mark(ctx, 1, 0);
     if (n) {
@@ -442,8 +457,7 @@ int p265_dequant_batch(p265_ctx *ctx, const p265_tu_desc *tus, int32_t n_tus, co
     if ((rc = ensure(ctx, 1, sizeof(int16_t) * n_coeffs + 64, &d_co))) return rc;
     if ((rc = ensure(ctx, 4, sizeof(int16_t) * n_coeffs, &d_out))) return rc;
     if (scaling_factor) {
-        if ((rc = ensure(ctx, 3, P265_SF_BYTES, &d_sf))) return rc;
-        P265_CUDA(cudaMemcpyAsync(d_sf, scaling_factor, P265_SF_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = upload_sf(ctx, scaling_factor, &d_sf))) return rc;
     }
     P265_CUDA(cudaMemcpyAsync(d_tus, tus, sizeof(p265_tu_desc) * (size_t)n_tus, cudaMemcpyHostToDevice, ctx->stream));
     P265_CUDA(cudaMemcpyAsync(d_co, coeffs, sizeof(int16_t) * n_coeffs, cudaMemcpyHostToDevice, ctx->stream));
@@ -752,10 +766,11 @@ int p265_loop_filter_batch(p265_ctx *ctx, void *planes, const p265_pic_geom *geo
     return finish(ctx);
 }
 
-int p265_pcie_probe(p265_ctx *ctx, size_t bytes, int reps, double *h2d_bytes_per_s, double *d2h_bytes_per_s) {
+int p265_pcie_probe(p265_ctx *ctx, size_t bytes, int n_buffers, int reps, double *h2d_bytes_per_s,
+                    double *d2h_bytes_per_s) {
     if (!ctx || (!h2d_bytes_per_s && !d2h_bytes_per_s)) return set_error(P265_EINVAL, "p265_pcie_probe: NULL argument");
     P265_CUDA(cudaSetDevice(ctx->device));
-    return run_pcie_probe(ctx, bytes, reps, h2d_bytes_per_s, d2h_bytes_per_s);
+    return run_pcie_probe(ctx, bytes, n_buffers, reps, h2d_bytes_per_s, d2h_bytes_per_s);
 }
 
 int p265_int_peak(p265_ctx *ctx, int kind, double *ops_per_s, double *ms) {

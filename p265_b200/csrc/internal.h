@@ -29,6 +29,10 @@ struct p265_ctx {
     std::vector<TraceMark> marks;
     cudaStream_t aux_stream = nullptr;  // second chain of residual bins (tuning knob P265_SPLIT), created on demand
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // host copy of the ScalingFactor table that scratch slot 3 currently holds on the device: the table of a
+    // stream changes with its parameter sets, not with its pictures, so it is uploaded when it differs
+    uint8_t sf_shadow[P265_SF_BYTES] = {0};
+    bool sf_shadow_valid = false;
     void *xtus = nullptr;  // expanded TU descriptors of the current residual launch (grow-only)
     size_t xtus_bytes = 0;
 };
@@ -53,7 +57,7 @@ int launch_unpack(p265_ctx *ctx, const p265_tu_desc *d_tus, const int32_t bin_co
 // device-visible address of the caller's buffer, which already holds the unfiltered samples)
 int launch_sao_writeback(p265_ctx *ctx, const void *d_out, void *h_out, const p265_pic_geom *g, int ctb_log2,
                          const p265_sao_ctb *d_params);
-int run_pcie_probe(p265_ctx *ctx, size_t bytes, int reps, double *h2d, double *d2h);
+int run_pcie_probe(p265_ctx *ctx, size_t bytes, int n_buffers, int reps, double *h2d, double *d2h);
 int launch_dequant(p265_ctx *ctx, const p265_tu_desc *d_tus, int n_tus, const int16_t *d_coeffs, const uint8_t *d_sf,
                    int bit_depth_y, int bit_depth_c, int16_t *d_scaled);
 int launch_ref_literal(p265_ctx *ctx, const p265_tu_desc *d_tus, int n_tus, const int16_t *d_scaled, int32_t *d_out);

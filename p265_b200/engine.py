@@ -304,12 +304,14 @@ class Engine:
         return planes
 
     # ---------------------------------------------------------------- measurement
-    def pcie_probe(self, n_bytes: int = 256 << 20, reps: int = 8, h2d: bool = True, d2h: bool = True):
-        """(H2D, D2H) bytes per second of plain page-locked copies, both directions at once when both
-        are requested (None for a direction that was not)."""
+    def pcie_probe(self, n_bytes: int = 256 << 20, reps: int = 8, h2d: bool = True, d2h: bool = True,
+                   n_buffers: int = 1):
+        """(H2D, D2H) bytes per second of plain page-locked copies of `n_bytes`, both directions at once
+        when both are requested (None for a direction that was not), cycling through `n_buffers` distinct
+        host buffers per direction (1 = one cache-resident buffer, the usual copy benchmark)."""
         a, b = C.c_double(), C.c_double()
-        _lib.check(self._lib.p265_pcie_probe(self._ctx, int(n_bytes), int(reps), C.byref(a) if h2d else None,
-                                             C.byref(b) if d2h else None))
+        _lib.check(self._lib.p265_pcie_probe(self._ctx, int(n_bytes), int(n_buffers), int(reps),
+                                             C.byref(a) if h2d else None, C.byref(b) if d2h else None))
         return (a.value if h2d else None), (b.value if d2h else None)
 
     def int_peak(self, kind: int):

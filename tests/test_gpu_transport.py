@@ -289,3 +289,7 @@ def test_pcie_probe_reports_both_directions(engine):
     assert h2d > 1e9 and d2h > 1e9
     only, none = engine.pcie_probe(32 << 20, reps=2, d2h=False)
     assert only > 1e9 and none is None
+    h2d, d2h = engine.pcie_probe(8 << 20, reps=8, n_buffers=4)
+    assert h2d > 1e9 and d2h > 1e9
+    with pytest.raises(ValueError):
+        engine.pcie_probe(8 << 20, reps=1, n_buffers=0)
