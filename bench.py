@@ -368,6 +368,33 @@ def run_gpu(args):
             "frac_hbm": round(b / (ms * 1e-3) / 1e9 / measured_peaks()[0]["hbm_gbs"], 4),
             "alg_int_ops": alg_int_ops(c2)}
         del c_tus, c_co, c_out
+        # Zero-aware passes (include/p265_b200.h: zero-extent codes): config 3's TB mix with the coefficients of
+        # every 16x16 / 32x32 TB confined as in the reference's only real stream (synth.SANITY_EXTENT_MIX) --
+        # the same launch once without codes in the descriptors and once with them.  Outside the metric: the
+        # SURVEY 8(d) coefficient model of config 3 itself leaves nothing to skip.
+        zb = synth.residual_batch("4k10_lowfreq", n_pics=n_o, n_unique=2, extents=True).densified()
+        z_co, z_sf = to_dev(zb.coeffs), to_dev(zb.scaling_factor)
+        z_out = torch.empty(zb.geom.total_elems() * 2, dtype=torch.uint8, device=dev)
+        z_bins = zb.bin_counts()
+        z_plain = zb.tus.copy()
+        z_plain["rsvd"] = 0
+        zo = {"pics": n_o, "tbs": int(len(zb.tus)), "alg_bytes": int(4 * zb.samples() + 16 * len(zb.tus))}
+        for key, tus in (("ms_without_codes", z_plain), ("ms_with_codes", zb.tus)):
+            z_tus = to_dev(tus)
+
+            def residual_z():
+                eng.residual_dev(z_tus.data_ptr(), z_bins, z_co.data_ptr(), z_sf.data_ptr(), zb.geom, z_out.data_ptr(),
+                                 zero_fill=False, sf_replicated=bool(zb.sf_replicated), dense_arena=zb.dense_small_bins())
+            for _ in range(3):
+                residual_z()
+            zo[key] = round(timed(residual_z, args.steps) / args.steps, 4)
+            del z_tus
+        zo["speedup"] = round(zo["ms_without_codes"] / zo["ms_with_codes"], 3)
+        zo["frac_hbm_with_codes"] = round(zo["alg_bytes"] / (zo["ms_with_codes"] * 1e-3) / 1e9 / measured_peaks()[0]["hbm_gbs"], 4)
+        zo["what"] = ("config-3 TB mix, coefficients of the 16x16 / 32x32 TBs confined to the (rows, columns) extents "
+                      "measured on sanity.bin's 16x16 TBs: 41 % full, 29 % first quarter both ways, rest mixed")
+        other["zero_aware_residual_4k10_lowfreq"] = zo
+        del z_co, z_sf, z_out
 
     ms_total_max = partition.max_over_ranks(ms_total)
     pixels_step = PIC_W * PIC_H * args.pics * world

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define P265_ABI_VERSION 2
+#define P265_ABI_VERSION 3
 
 typedef enum p265_status {
     P265_OK = 0,
@@ -53,9 +53,24 @@ typedef struct p265_tu_desc {
     uint8_t flags;       /* P265_TU_*                                               */
     uint32_t coeff_off;  /* offset into the coefficient arena, units of 16 coeffs   */
     uint16_t pic;        /* picture index inside the batch                          */
-    uint16_t rsvd;       /* dense arena: ignored.  Packed stream: number of non-zero
-                            levels in the TB's record (= set bits of its bitmap)     */
+    uint16_t rsvd;       /* bits 0-10  packed stream: number of non-zero levels in the
+                                       TB's record (= set bits of its bitmap); dense
+                                       arena: ignored
+                            bits 11-12 zr, bits 13-14 zc: zero-extent codes, below     */
 } p265_tu_desc;
+
+/* Zero-extent codes (16x16 and 32x32 TBs; ignored for smaller ones).  The parser knows the last
+ * significant position of every TB (last_sig_coeff_x / y, tu.py:145-148).  Code z in the row field
+ * promises that every coefficient in rows >= N >> z is zero, in the column field the same for
+ * columns: 0 = nothing known, 1 = upper / left half only, 2 = first quarter only; 3 is rejected.
+ * The residual kernels then skip the products of the empty rows / columns (zero contributes zero:
+ * results are identical).  Dense arena (p265_residual_batch[_dev]): the codes are the caller's
+ * promise; a TB that breaks it gets a wrong residual, nothing else is affected.  Packed stream
+ * (p265_residual_batch_packed[_dev]): the codes are ignored -- the device derives them from the
+ * record's significance bitmap while it expands the stream.                                     */
+#define P265_TU_ZR_SHIFT 11
+#define P265_TU_ZC_SHIFT 13
+#define P265_TU_LEVELS_MASK 0x07ffu
 
 #define P265_TU_DST 1u    /* trType 1: 4x4 luma of an intra CU (transform.py:97)     */
 #define P265_TU_SKIP 2u   /* transform_skip_flag (tu.py:142-143)                     */

@@ -591,8 +591,8 @@ def unpack_stream(tus, stream):
         rec = int(t["coeff_off"]) * 4
         bits = np.unpackbits(stream[rec:rec + nn // 8], bitorder="little")[:nn].astype(bool)
         k = int(bits.sum())
-        if k != int(t["rsvd"]):
-            raise ValueError("TB %d: descriptor announces %d levels, bitmap has %d bits set" % (i, int(t["rsvd"]), k))
+        if k != int(t["rsvd"]) & 0x7FF:    # bits 0-10: level count; bits 11-14: zero-extent codes (include/p265_b200.h)
+            raise ValueError("TB %d: descriptor announces %d levels, bitmap has %d bits set" % (i, int(t["rsvd"]) & 0x7FF, k))
         lv0 = rec + nn // 8
         if int(t["flags"]) & _TU_LEVELS8:
             lv = stream[lv0:lv0 + k].view(np.int8).astype(np.int16)

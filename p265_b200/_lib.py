@@ -31,7 +31,7 @@ SYMBOLS = (
     "p265_residual_batch_packed", "p265_residual_batch_packed_dev", "p265_loop_filter_batch",
     "p265_pcie_probe", "p265_ctx_set_trace", "p265_trace_read",
 )
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Geom(C.Structure):

@@ -114,10 +114,13 @@ static inline unsigned tu_bad(const p265_tu_desc &t, int log2n, unsigned bad_fla
                    (unsigned)((t.flags & bad_flags) != 0) | (unsigned)(((t.flags & P265_TU_DST) != 0) & (t.c_idx != 0)) |
                    (unsigned)(t.qp > L.qmax[c]);
     if (PACKED) {
-        const size_t end = (size_t)t.coeff_off * 4 + (size_t)(n * n) / 8 + (size_t)t.rsvd * ((t.flags & P265_TU_LEVELS8) ? 1 : 2);
-        bad |= (unsigned)(end > L.n_coeffs) | (unsigned)(t.rsvd > n * n);
+        const unsigned lv = t.rsvd & P265_TU_LEVELS_MASK;
+        const size_t end = (size_t)t.coeff_off * 4 + (size_t)(n * n) / 8 + (size_t)lv * ((t.flags & P265_TU_LEVELS8) ? 1 : 2);
+        bad |= (unsigned)(end > L.n_coeffs) | (unsigned)(lv > (unsigned)(n * n));
     } else {
         bad |= (unsigned)((size_t)t.coeff_off * 16 + (size_t)(n * n) > L.n_coeffs);
+        // zero-extent codes (a promise about the dense arena; the packed path derives its own): 3 is undefined
+        bad |= (unsigned)(((t.rsvd >> P265_TU_ZR_SHIFT) & 3) == 3) | (unsigned)(((t.rsvd >> P265_TU_ZC_SHIFT) & 3) == 3);
     }
     return bad;
 }
@@ -134,8 +137,10 @@ static int diagnose_tu(const p265_tu_desc &t, long long k, int log2n, bool have_
         return set_error(P265_EINVAL, "descriptor %lld: %dx%d block at (%d,%d) outside the %dx%d plane or unaligned", k, n, n,
                          t.x, t.y, L.wmax[c], L.hmax[c]);
     if (t.pic >= L.n_pics) return set_error(P265_EINVAL, "descriptor %lld: picture %d", k, t.pic);
-    if (packed && t.rsvd > n * n)
-        return set_error(P265_EINVAL, "descriptor %lld: %d levels in a %dx%d block", k, t.rsvd, n, n);
+    if (packed && (t.rsvd & P265_TU_LEVELS_MASK) > n * n)
+        return set_error(P265_EINVAL, "descriptor %lld: %d levels in a %dx%d block", k, t.rsvd & P265_TU_LEVELS_MASK, n, n);
+    if (!packed && (((t.rsvd >> P265_TU_ZR_SHIFT) & 3) == 3 || ((t.rsvd >> P265_TU_ZC_SHIFT) & 3) == 3))
+        return set_error(P265_EINVAL, "descriptor %lld: zero-extent code 3 is not defined (rsvd 0x%04x)", k, t.rsvd);
     if (tu_bad<true>(t, log2n, 0, L) && packed)
         return set_error(P265_EINVAL, "descriptor %lld: coefficients beyond the packed stream", k);
     if (!packed && (size_t)t.coeff_off * 16 + (size_t)(n * n) > L.n_coeffs)

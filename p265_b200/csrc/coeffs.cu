@@ -47,7 +47,7 @@ __device__ __forceinline__ void unpack_item(const UnpackArgs &a, int item, int l
         if (wi >= o) incl += v;
     }
     int idx = incl - __popc(word);
-    const int n_levels = (int)(d.w >> 16);  // descriptor field rsvd: the record holds exactly this many levels --
+    const int n_levels = (int)((d.w >> 16) & P265_TU_LEVELS_MASK);  // descriptor field rsvd: the record holds exactly this many levels --
                                             // never read past them, whatever the bitmap claims (the host entry
                                             // point bounds records by this field, not by counting bits)
     const bool narrow = ((d.y >> 24) & P265_TU_LEVELS8) != 0;
@@ -64,6 +64,33 @@ __device__ __forceinline__ void unpack_item(const UnpackArgs &a, int item, int l
         if (b & 1) out[b >> 1] |= v << 16;
         else out[b >> 1] = v & 0xffffu;
     }
+    // Zero-extent codes of the 16x16 / 32x32 TBs, straight from the significance bitmap (a bit that is set
+    // beyond n_levels only makes the extent larger: conservative).  The residual kernels skip the products
+    // of rows >= N >> zr and columns >= N >> zc (residual.cu: "Zero-aware passes").
+    uint32_t zbits = 0;
+    if (LOG2N >= 4) {
+        constexpr int N = 1 << LOG2N;
+        int last_row, last_col;
+        if (LOG2N == 5) {  // one TB per warp, lane = row
+            const uint32_t rows = __ballot_sync(0xffffffffu, word != 0);
+            const uint32_t cols = __reduce_or_sync(0xffffffffu, word);
+            last_row = 31 - __clz((int)rows);
+            last_col = 31 - __clz((int)cols);
+        } else {           // 8 lanes per TB, lane = two rows of 16 columns
+            int r = word ? 2 * wi + ((word >> 16) ? 1 : 0) : -1;
+            uint32_t c = (word | (word >> 16)) & 0xffffu;
+#pragma unroll
+            for (int o = 1; o < WPT; o <<= 1) {
+                r = max(r, __shfl_xor_sync(0xffffffffu, r, o, WPT));
+                c |= __shfl_xor_sync(0xffffffffu, c, o, WPT);
+            }
+            last_row = r;
+            last_col = 31 - __clz((int)c);
+        }
+        const uint32_t zr = last_row < N / 4 ? 2u : (last_row < N / 2 ? 1u : 0u);
+        const uint32_t zc = last_col < N / 4 ? 2u : (last_col < N / 2 ? 1u : 0u);
+        zbits = (zr << (16 + P265_TU_ZR_SHIFT)) | (zc << (16 + P265_TU_ZC_SHIFT));
+    }
     if (!valid) return;
     const uint32_t unit = a.arena_base[bin] + (uint32_t)tb * (NN / 16);
     uint4 *dst = reinterpret_cast<uint4 *>(a.arena + (size_t)unit * 16 + (size_t)wi * BITS);
@@ -71,7 +98,7 @@ __device__ __forceinline__ void unpack_item(const UnpackArgs &a, int item, int l
     for (int q = 0; q < BITS / 8; q++) dst[q] = make_uint4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
     if (wi == 0) {
         d.z = unit;
-        d.w &= 0xffffu;  // rsvd is a packed-stream field
+        d.w = (d.w & 0xffffu) | zbits;  // the level count is a packed-stream field; the extent codes stay
         d.y &= ~((uint32_t)P265_TU_LEVELS8 << 24);
         *reinterpret_cast<uint4 *>(&a.tus_out[a.first_tb[bin] + tb]) = d;
     }

@@ -224,11 +224,26 @@ P265_HD int slot_index_rt(int n, int s, int h) {
 // C independent vectors in lock step (they share every uniform-register constant).
 // p[c][s]: packed operands in slot order; out[c][i]: natural order, int32, includes
 // `rnd` (the rounding offset of the shift that follows) exactly once per output.
-template <int N, int C>
+//
+// Z = zero-extent code (the parser knows the last significant position, tu.py:145-148): every input
+// with natural index >= N >> Z is zero.  An input that is zero contributes nothing, so its products are
+// simply not issued -- bit-exact by construction.  In slot order the non-zero inputs are the first
+// max(1, 2^L >> Z) slots of every level [2^L, 2^(L+1)) (extent_slot_needed), and the even part of an
+// N-point transform with extent N >> Z is an N/2-point transform with extent (N/2) >> Z: the same Z
+// all the way down.  32-point pass: 172 / 88 / 46 IDP.2A for Z = 0 / 1 / 2.
+P265_HD constexpr bool extent_slot_needed(int s, int z) {
+    if (s == 0) return true;
+    if (s == 1) return z < 2;  // rows (N/4, 3N/4)
+    const int l = s >= 8 ? 3 : (s >= 4 ? 2 : 1);
+    const int keep = (1 << l) >> z;
+    return (s - (1 << l)) < (keep < 1 ? 1 : keep);
+}
+
+template <int N, int C, int Z = 0>
 struct Idct;
 
-template <int C>
-struct Idct<4, C> {
+template <int C, int Z>
+struct Idct<4, C, Z> {
     static P265_HD void run(const int (&p)[C][2], int rnd, int (&out)[C][4]) {
         P265_UNROLL
         for (int c = 0; c < C; c++) {
@@ -237,7 +252,11 @@ struct Idct<4, C> {
             // pipe (IDP.2A / IMAD, one warp-instruction per 2 cycles) is the scarce one
             const int e0 = dp2a_lo(p[c][0], P265_K(e4), rnd);
             const int e1 = dp2a_hi(p[c][0], P265_K(e4), rnd);
-            if (C == 4) {
+            if (Z >= 2) {
+                // inputs 1 and 3 of the 4-point stage (natural rows N/4, 3N/4) lie beyond the extent
+                out[c][0] = e0; out[c][3] = e0;
+                out[c][1] = e1; out[c][2] = e1;
+            } else if (C == 4) {
                 // one-lane-per-4x4-TB path: latency-bound, keep the even and odd products independent
                 const int o0 = dp2a_lo(p[c][1], P265_K(o4), 0);
                 const int o1 = dp2a_hi(p[c][1], P265_K(o4), 0);
@@ -270,8 +289,10 @@ struct OddK<32> {
     static P265_HD int w(int k, int q) { return P265_K(o32)[k][q]; }
 };
 
-template <int N, int C>
+template <int N, int C, int Z>
 struct Idct {
+    // odd-part slots that can hold a non-zero input
+    static constexpr int SN = ((N / 4) >> Z) < 1 ? 1 : ((N / 4) >> Z);
     static P265_HD void run(const int (&p)[C][N / 2], int rnd, int (&out)[C][N]) {
         int pe[C][N / 4];
         int e[C][N / 2];
@@ -280,14 +301,14 @@ struct Idct {
             P265_UNROLL
             for (int s = 0; s < N / 4; s++) pe[c][s] = p[c][s];
         }
-        Idct<N / 2, C>::run(pe, rnd, e);
+        Idct<N / 2, C, Z>::run(pe, rnd, e);
         P265_UNROLL
         for (int k = 0; k < N / 2; k++) {
             int o[C];  // e + O[k]: the odd chain starts from the even value
             P265_UNROLL
             for (int c = 0; c < C; c++) o[c] = e[c][k];
             P265_UNROLL
-            for (int s = 0; s < N / 4; s++) {
+            for (int s = 0; s < SN; s++) {
                 const int w = OddK<N>::w(k, s >> 1);
                 P265_UNROLL
                 for (int c = 0; c < C; c++)
@@ -436,15 +457,24 @@ P265_HD int sf_matrix_id(int log2n, int c_idx, int flags) {
 //   .y  flags | matrixId << 8 (3 bits; 6 = prescaled, no table) | (20 - BitDepth) << 11 (4 bits)
 //       | (plane stride / 8) << 15
 //   .z  coefficient arena offset, units of 16 coefficients       (unchanged)
-//   .w  w (16 bits: 16 * levelScale, levelScale with a table, 1 when prescaled) | sh << 16 | lsh << 24
+//   .w  w (16 bits: 16 * levelScale, levelScale with a table, 1 when prescaled) | sh << 16 (5 bits)
+//       | zr << 21 (2 bits) | lsh << 24 (4 bits) | zc << 28 (2 bits)
+//       zr / zc = zero-extent codes of the TB (P265_TU_ZR / P265_TU_ZC of the public descriptor): rows >=
+//       N >> zr and columns >= N >> zc hold no coefficient (0 = nothing known)
 // (the TB size is the bin's; strides are multiples of 8 elements, checked by the launcher)
 P265_HD uint32_t xd_flags(const uint4 x) { return x.y & 0xff; }
 P265_HD uint32_t xd_mid(const uint4 x) { return (x.y >> 8) & 7; }
 P265_HD int xd_sh2(const uint4 x) { return (int)((x.y >> 11) & 15); }
 P265_HD int xd_stride(const uint4 x) { return (int)((x.y >> 15) << 3); }
 P265_HD int xd_w(const uint4 x) { return (int)(x.w & 0xffff); }
-P265_HD int xd_sh(const uint4 x) { return (int)((x.w >> 16) & 0xff); }
-P265_HD int xd_lsh(const uint4 x) { return (int)(x.w >> 24); }
+P265_HD int xd_sh(const uint4 x) { return (int)((x.w >> 16) & 0x1f); }
+P265_HD int xd_lsh(const uint4 x) { return (int)((x.w >> 24) & 0xf); }
+P265_HD int xd_zr(const uint4 x) { return (int)((x.w >> 21) & 3); }
+P265_HD int xd_zc(const uint4 x) { return (int)((x.w >> 28) & 3); }
+// zero-extent codes of a public descriptor (p265_tu_desc.rsvd, bits 11-12 and 13-14); code 3 is not defined
+// (the host entry points reject it) and reads as "nothing known"
+P265_HD int desc_zr(const uint4 d) { const int z = (int)((d.w >> (16 + P265_TU_ZR_SHIFT)) & 3); return z == 3 ? 0 : z; }
+P265_HD int desc_zc(const uint4 d) { const int z = (int)((d.w >> (16 + P265_TU_ZC_SHIFT)) & 3); return z == 3 ? 0 : z; }
 
 P265_HD uint4 expand_desc(const KernelArgs &a, const uint4 d) {
     const TbParams t = make_params(a, d, true);
@@ -454,8 +484,10 @@ P265_HD uint4 expand_desc(const KernelArgs &a, const uint4 d) {
     // matrixId 6, where the small-bin kernels keep an all-ones matrix
     const int mid = (t.flags & P265_TU_PRESCALED) ? 6 : sf_matrix_id(log2n, c_idx, t.flags);
     const uint32_t flags = (uint32_t)t.flags & 0xff;
+    // extents only matter where a transform runs on them: not for transform-skip / bypass TBs (4x4 only anyway)
+    const uint32_t zr = (uint32_t)desc_zr(d), zc = (uint32_t)desc_zc(d);
     return make_uint4(dst_off, flags | ((uint32_t)mid << 8) | ((uint32_t)t.sh2 << 11) | ((uint32_t)(t.stride >> 3) << 15),
-                      d.z, (uint32_t)t.w | ((uint32_t)t.sh << 16) | ((uint32_t)t.lsh << 24));
+                      d.z, (uint32_t)t.w | ((uint32_t)t.sh << 16) | (zr << 21) | ((uint32_t)t.lsh << 24) | (zc << 28));
 }
 
 P265_HD TbParams params_from_x(const KernelArgs &a, const uint4 x, bool valid, int log2n) {
@@ -704,7 +736,9 @@ P265_HD void stage1_column(const unsigned char *in, unsigned char *g, int x, int
 // the two columns share every basis constant and their results leave as one packed 32-bit
 // store per row (half the I2IP / STS of the one-column form).  Needs twice the registers of
 // the transform state, so it is used where that fits the occupancy target (16x16).
-template <int LOG2N, int SF, bool SLOW>
+// Z (zero-extent code, see Idct): the TB's rows >= N >> Z hold no coefficient -- they are neither read
+// nor dequantised, and the column transform skips their products.
+template <int LOG2N, int SF, bool SLOW, int Z = 0>
 P265_HD void stage1_pair(const unsigned char *in, unsigned char *g, int x0, int x1, int tl, const uint8_t *sf, int w,
                          int rnd, int sh, int lsh) {
     using L = Layout<LOG2N>;
@@ -729,23 +763,29 @@ P265_HD void stage1_pair(const unsigned char *in, unsigned char *g, int x0, int 
         }
         P265_UNROLL
         for (int s = 0; s < N / 2; s++) {
+            if (!extent_slot_needed(s, Z)) {  // both rows of the slot lie beyond the extent
+                p[c][s] = 0;
+                continue;
+            }
             const int y0 = slot_index(N, s, 0), y1 = slot_index(N, s, 1);
             const int e0 = y0 * N + x, e1 = y1 * N + x;
-            const int l0 = lds_s16(in, e0 * 2), l1 = lds_s16(in, e1 * 2);
+            const bool has1 = y1 < (N >> Z);  // the slot's second row may already be outside
+            const int l0 = lds_s16(in, e0 * 2), l1 = has1 ? lds_s16(in, e1 * 2) : 0;
             int m0 = w, m1 = w;
             if (SF == SF_GENERAL) {
                 m0 *= (int)sf[e0];
-                m1 *= (int)sf[e1];
+                if (has1) m1 *= (int)sf[e1];
             } else if (SF == SF_REPLICATED) {
                 m0 = y0 == 0 ? dc : mw[y0 / REP];
                 m1 = mw[y1 / REP];
             }
-            if (!SLOW) p[c][s] = pack_sat(dequant_fast(l0, m0, t), dequant_fast(l1, m1, t));
+            if (!has1) p[c][s] = pack_sat(SLOW ? dequant(l0, m0, t) : dequant_fast(l0, m0, t), 0);
+            else if (!SLOW) p[c][s] = pack_sat(dequant_fast(l0, m0, t), dequant_fast(l1, m1, t));
             else p[c][s] = pack_sat(dequant(l0, m0, t), dequant(l1, m1, t));
         }
     }
     int e[2][N];
-    Idct<N, 2>::run(p, 64, e);
+    Idct<N, 2, Z>::run(p, 64, e);
     // g[y][slot tl] = (clip16((e0[y] + 64) >> 7), clip16((e1[y] + 64) >> 7)); chunk index XOR-swizzled per row
     unsigned char *base[4];
     P265_UNROLL
@@ -758,7 +798,9 @@ P265_HD void stage1_pair(const unsigned char *in, unsigned char *g, int x0, int 
 // ------------------------------------------------- stage 2: ONE row of one TB
 // Horizontal pass (8.6.4.2) over row `row` of g, final bdShift rounding (8.6.2), int16
 // saturation: the row leaves as N/2 packed words.
-template <int LOG2N>
+// Z: the TB's columns >= N >> Z hold no coefficient, so those columns of g are zero (dequantisation and
+// the column transform map 0 to 0) and the row transform skips their products.
+template <int LOG2N, int Z = 0>
 P265_HD void stage2_compute(const unsigned char *g, int row, int rnd2, int sh2, int dst_flag,
                             uint32_t (&w)[(1 << LOG2N) / 2]) {
     using L = Layout<LOG2N>;
@@ -788,7 +830,7 @@ P265_HD void stage2_compute(const unsigned char *g, int row, int rnd2, int sh2, 
         P265_UNROLL
         for (int i = 0; i < 4; i++) r[0][i] = r4[0][i];
     } else {
-        Idct<N, 1>::run(p, rnd2, r);
+        Idct<N, 1, Z>::run(p, rnd2, r);
     }
     P265_UNROLL
     for (int i = 0; i < N / 2; i++) w[i] = (uint32_t)pack_sat(r[0][2 * i] >> sh2, r[0][2 * i + 1] >> sh2);
@@ -813,13 +855,13 @@ P265_HD void stage2_row(const unsigned char *g, int row, int16_t *dst, int rnd2,
 // ... or back into the lane's own row of g (consumed by the loads above; same chunk swizzle), for
 // the coalesced copy-out below: the scattered form costs 32 LSU wavefronts per store instruction
 // (32 rows), measured as 16-20 % of the big-size bins.
-template <int LOG2N>
+template <int LOG2N, int Z = 0>
 P265_HD void stage2_row_g(unsigned char *g, int row, int rnd2, int sh2) {
     using L = Layout<LOG2N>;
     constexpr int N = L::N;
     static_assert(N >= 16, "shared-memory sizes only");
     uint32_t w[N / 2];
-    stage2_compute<LOG2N>(g, row, rnd2, sh2, 0, w);
+    stage2_compute<LOG2N, Z>(g, row, rnd2, sh2, 0, w);
     unsigned char *grow = g + row * L::ROW_BYTES;
     const int sw = L::swz(row);
     P265_UNROLL

@@ -22,7 +22,8 @@ from __future__ import annotations
 import numpy as np
 
 from . import packer
-from .picture import TU_DESC, TU_LEVELS8, PackedResidualBatch, PicGeom, sort_by_size
+from .picture import (TU_DESC, TU_LEVELS8, TU_ZC_SHIFT, TU_ZR_SHIFT, PackedResidualBatch, PicGeom, extent_code,
+                      sort_by_size)
 
 
 class PictureSink:
@@ -53,8 +54,18 @@ class PictureSink:
         self.stream += np.packbits(nz, bitorder="little").tobytes()
         self.stream += vals.astype(np.int8 if narrow else "<i2").tobytes()
         self.stream += b"\0" * (-len(self.stream) & 3)
+        # rsvd: level count + the zero-extent codes of a 16x16 / 32x32 TB (the parser knows the last
+        # significant position, tu.py:145-148; here: of the stored levels).  They are the ordering key of
+        # the end-of-picture sort; the device derives the same codes from the bitmap.
+        rsvd = int(vals.size)
+        if log2n >= 4:
+            pos = np.flatnonzero(nz)
+            last_row = int(pos[-1]) >> log2n if pos.size else -1
+            last_col = int((pos & (n - 1)).max()) if pos.size else -1
+            rsvd |= int(extent_code(np.int64(last_row), n)) << TU_ZR_SHIFT
+            rsvd |= int(extent_code(np.int64(last_col), n)) << TU_ZC_SHIFT
         self.recs.append((x, y, log2n, c_idx, qp, (flags & ~TU_LEVELS8) | (TU_LEVELS8 if narrow else 0),
-                          off >> 2, self.pic, int(vals.size)))
+                          off >> 2, self.pic, rsvd))
         self.area += n * n
 
     def add_cu(self, cu, sps) -> None:

@@ -14,7 +14,7 @@ from __future__ import annotations
 import numpy as np
 
 from .picture import (AVAIL_ALL, SAO_CTB, TU_BYPASS, TU_DESC, TU_DST, TU_INTRA, TU_SKIP,
-                      PicGeom, ResidualBatch, sort_by_size)
+                      PicGeom, ResidualBatch, extent_codes, set_extents, sort_by_size)
 
 MODE_INTRA = 1   # cu.py:29
 
@@ -95,6 +95,7 @@ def pack_pictures(imgs, sps, scaling_factor=None) -> ResidualBatch:
             off += n * n
     tus = np.array(recs, dtype=TU_DESC) if recs else np.zeros(0, dtype=TU_DESC)
     coeffs = np.concatenate(blocks) if blocks else np.zeros(0, dtype=np.int16)
+    set_extents(tus, *extent_codes(tus, coeffs))     # zero-extent codes of the 16x16 / 32x32 TBs (picture.py)
     return ResidualBatch(geom=geom, tus=sort_by_size(tus, geom), coeffs=coeffs,
                          scaling_factor=scaling_factor, covers_all=tbs_cover_planes(tus, geom))
 

@@ -29,6 +29,13 @@ TU_INTRA = 8      # CuPredMode == MODE_INTRA -> matrixId (scaling.py:33-42)
 TU_PRESCALED = 16  # arena holds d[] already (pu.scaled_samples)
 TU_LEVELS8 = 32   # packed coefficient stream: this TB's levels are int8
 
+# `rsvd` of a descriptor: bits 0-10 number of levels (packed stream), bits 11-12 / 13-14 zero-extent
+# codes of the rows / columns (16x16 and 32x32 TBs): code z = every coefficient in rows (columns)
+# >= N >> z is zero; 0 = nothing known.  The parser knows the last significant position of a TB
+# (tu.py:145-148); the kernels skip the products of the empty rows / columns.
+TU_LEVELS_MASK = 0x07FF
+TU_ZR_SHIFT, TU_ZC_SHIFT = 11, 13
+
 #: mirrors `p265_sao_ctb` (24 bytes)
 SAO_CTB = np.dtype([("type", "u1", 3), ("band_pos", "u1", 3), ("eo_class", "u1", 3),
                     ("offset_val", "i1", (3, 4)), ("pad", "u1"), ("avail", "<u2")])
@@ -150,6 +157,14 @@ class ResidualBatch:
         tus["coeff_off"] = new_off.astype(np.uint32)
         return ResidualBatch(self.geom, tus, arena, self.scaling_factor, self.covers_all, self.sf_replicated, self.bins)
 
+    def with_extents(self) -> "ResidualBatch":
+        """The same batch with the zero-extent codes of its 16x16 / 32x32 TBs in the descriptors
+        (`extent_codes`) and the list re-sorted by the ordering rule, which clusters equal codes."""
+        tus = self.tus.copy()
+        set_extents(tus, *extent_codes(tus, self.coeffs))
+        return ResidualBatch(self.geom, sort_by_size(tus, self.geom), self.coeffs, self.scaling_factor,
+                             self.covers_all, self.sf_replicated, self.bins)
+
     def dense_small_bins(self) -> bool:
         """True when, inside the 8x8 bin and inside the 4x4 bin, every TB's coefficients directly
         follow the previous TB's in the arena (what P265_RES_DENSE_ARENA asserts for the device
@@ -164,6 +179,36 @@ class ResidualBatch:
                 k += n_tb
             self._dense = ok
         return self._dense
+
+
+def extent_code(last: np.ndarray, n: int) -> np.ndarray:
+    """Zero-extent code of a TB side from the index of its last non-zero row / column (-1: none)."""
+    return np.where(last < n // 4, 2, np.where(last < n // 2, 1, 0)).astype(np.uint16)
+
+
+def extent_codes(tus: np.ndarray, coeffs: np.ndarray):
+    """(zr, zc) per descriptor of a dense arena: the zero-extent codes of the 16x16 / 32x32 TBs
+    (0 for the smaller sizes, which do not use them).  A parser has them for free (emit.py); this is
+    the vectorised form for synthetic / already packed data."""
+    zr = np.zeros(len(tus), np.uint16)
+    zc = np.zeros(len(tus), np.uint16)
+    l2 = tus["log2n"]
+    for k in (5, 4):
+        idx = np.nonzero(l2 == k)[0]
+        if not idx.size:
+            continue
+        n = 1 << k
+        nz = coeffs[(tus["coeff_off"][idx].astype(np.int64) * 16)[:, None] +
+                    np.arange(n * n, dtype=np.int64)[None, :]].reshape(-1, n, n) != 0
+        ar = np.arange(1, n + 1)
+        zr[idx] = extent_code((nz.any(axis=2) * ar).max(axis=1) - 1, n)
+        zc[idx] = extent_code((nz.any(axis=1) * ar).max(axis=1) - 1, n)
+    return zr, zc
+
+
+def set_extents(tus: np.ndarray, zr: np.ndarray, zc: np.ndarray) -> None:
+    keep = np.uint16(0xFFFF ^ (3 << TU_ZR_SHIFT) ^ (3 << TU_ZC_SHIFT))
+    tus["rsvd"] = (tus["rsvd"] & keep) | (zr.astype(np.uint16) << TU_ZR_SHIFT) | (zc.astype(np.uint16) << TU_ZC_SHIFT)
 
 
 def size_kind_order(tus: np.ndarray, geom=None) -> np.ndarray:
@@ -182,6 +227,10 @@ def size_kind_order(tus: np.ndarray, geom=None) -> np.ndarray:
         left_shift = (tus["qp"].astype(np.int32) // 6 >= bd + tus["log2n"].astype(np.int32) - 5) & \
             ((tus["flags"] & (TU_PRESCALED | TU_BYPASS)) == 0)
         key = key + left_shift.astype(np.int32)
+    # ... and the zero-extent codes of the big TBs: a work item (2 TBs of 32x32, 4 of 16x16) runs the passes
+    # of the weakest promise among its TBs, so equal codes should sit next to each other
+    z = ((tus["rsvd"] >> TU_ZR_SHIFT) & 3).astype(np.int32) * 4 + ((tus["rsvd"] >> TU_ZC_SHIFT) & 3).astype(np.int32)
+    key = key * 16 + np.where(tus["log2n"] >= 4, z, 0)
     return np.argsort(key, kind="stable")
 
 
@@ -292,7 +341,9 @@ def pack_coefficients(tus: np.ndarray, coeffs: np.ndarray):
     if stream.size >> 2 > 0xFFFFFFFF:
         raise ValueError("packed stream too large for 32-bit record offsets")
     tus["coeff_off"] = (rec_off >> 2).astype(np.uint32)
-    tus["rsvd"] = nnz.astype(np.uint16)                     # number of levels in the record
+    # number of levels in the record; the zero-extent codes (the host's ordering key) travel along,
+    # the device derives its own from the bitmap
+    tus["rsvd"] = (tus["rsvd"] & np.uint16(0xFFFF ^ TU_LEVELS_MASK)) | nnz.astype(np.uint16)
     tus["flags"] = (tus["flags"] & ~np.uint8(TU_LEVELS8)) | np.where(wide, 0, TU_LEVELS8).astype(np.uint8)
     return tus, stream
 
@@ -328,7 +379,7 @@ def unpack_coefficients(tus: np.ndarray, stream: np.ndarray):
         blocks[mask] = vals
         arena[(off[idx][:, None] + np.arange(nn, dtype=np.int64)[None, :]).ravel()] = blocks.ravel()
     tus["coeff_off"] = (off >> 4).astype(np.uint32)
-    tus["rsvd"] = 0
+    tus["rsvd"] = tus["rsvd"] & np.uint16(0xFFFF ^ TU_LEVELS_MASK)
     tus["flags"] = tus["flags"] & np.uint8(0xFF ^ TU_LEVELS8)
     return tus, arena
 

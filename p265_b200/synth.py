@@ -32,18 +32,38 @@ CONFIGS = {
 }
 
 
+# "4k10_lowfreq": config 3 with the coefficients of every 16x16 / 32x32 TB confined to its first N >> zr
+# rows and N >> zc columns, (zr, zc) drawn from the distribution measured on the 16x16 TBs of the
+# reference's only real stream (sanity.bin, 368 TBs: tests/test_extents.py prints it).  The SURVEY 8(d)
+# coefficient model itself leaves nothing to skip (a level in the last quarter of the rows of 99.85 % of its
+# 32x32 TBs); real streams do, and this variant is what the zero-aware passes are measured on.
+SANITY_EXTENT_MIX = (((0, 0), 0.41), ((2, 2), 0.29), ((1, 0), 0.07), ((2, 1), 0.055), ((0, 2), 0.05),
+                     ((1, 1), 0.045), ((1, 2), 0.03), ((0, 1), 0.03), ((2, 0), 0.02))
+CONFIGS["4k10_lowfreq"] = dict(CONFIGS["4k10"], extent_mix=SANITY_EXTENT_MIX)
+
+
 def _nz_prob(n: int, density: float) -> np.ndarray:
     yy, xx = np.mgrid[0:n, 0:n]
     p = np.exp(-(xx + yy) / (n / 4.0))
     return np.minimum(1.0, p * (density * n * n / p.sum()))
 
 
-def _coeff_blocks(rng, count: int, n: int, stress: bool) -> np.ndarray:
+def _coeff_blocks(rng, count: int, n: int, stress: bool, extent_mix=None) -> np.ndarray:
     if count == 0:
         return np.zeros((0, n, n), np.int16)
+    box = None
+    if extent_mix is not None and n >= 16:   # per TB: coefficients only in rows < n >> zr, columns < n >> zc
+        codes = np.array([c for c, _ in extent_mix])
+        pick = codes[rng.choice(len(codes), size=count, p=np.array([p for _, p in extent_mix]) /
+                                sum(p for _, p in extent_mix))]
+        ar = np.arange(n)
+        box = (ar[None, :, None] < (n >> pick[:, 0])[:, None, None]) & (ar[None, None, :] < (n >> pick[:, 1])[:, None, None])
     if stress:
-        return rng.integers(-32768, 32768, (count, n, n), dtype=np.int64).astype(np.int16)
+        lv = rng.integers(-32768, 32768, (count, n, n), dtype=np.int64).astype(np.int16)
+        return lv if box is None else np.where(box, lv, 0).astype(np.int16)
     mask = rng.random((count, n, n), dtype=np.float32) < _nz_prob(n, 0.20).astype(np.float32)
+    if box is not None:
+        mask &= box
     mag = rng.laplace(0.0, 6.0, (count, n, n)).astype(np.float32)
     mag[:, 0, 0] = rng.laplace(0.0, 40.0, count)
     lv = np.where(mask, np.rint(mag), 0.0)
@@ -85,7 +105,7 @@ def residual_picture(cfg: dict, rng, pic: int = 0, stress: bool = False):
         r["x"], r["y"], r["log2n"], r["c_idx"] = x, y, log2n, c_idx
         r["qp"], r["flags"], r["pic"] = qp, flags, pic
         r["coeff_off"] = (off + np.arange(cnt, dtype=np.int64) * n * n) >> 4
-        blocks = _coeff_blocks(rng, cnt, n, stress)
+        blocks = _coeff_blocks(rng, cnt, n, stress, cfg.get("extent_mix"))
         byp = (flags & TU_BYPASS) != 0
         if byp.any():      # bypass "coefficients" are residual samples: keep them small
             blocks[byp] = np.clip(blocks[byp], -(1 << bd), (1 << bd) - 1)
@@ -126,10 +146,12 @@ def residual_picture(cfg: dict, rng, pic: int = 0, stress: bool = False):
 
 
 def residual_batch(name: str, n_pics: int = 1, seed: int | None = None, stress: bool = False,
-                   n_unique: int | None = None) -> ResidualBatch:
+                   n_unique: int | None = None, extents: bool = False) -> ResidualBatch:
     """A batch of `n_pics` synthetic pictures of config `name`.  `n_unique` < n_pics
     generates that many distinct pictures and repeats them (distinct memory, same
-    values) to keep host generation time down for large benchmark batches."""
+    values) to keep host generation time down for large benchmark batches.  `extents`: descriptors
+    carry the zero-extent codes of their coefficients and are ordered by them (what the parser-side
+    emitter hands over, picture.ResidualBatch.with_extents)."""
     cfg = CONFIGS[name]
     rng = np.random.default_rng(cfg["seed"] if seed is None else seed)
     n_unique = n_pics if n_unique is None else min(n_unique, n_pics)
@@ -146,8 +168,9 @@ def residual_batch(name: str, n_pics: int = 1, seed: int | None = None, stress: 
     geom = PicGeom(cfg["width"], cfg["height"], n_pics, cfg["bit_depth"], cfg["bit_depth"])
     sf = pack_scaling_factor(default_scaling_factor()) if cfg["scaling_lists"] else None
     # same ordering rule as the product packer (picture.sort_by_size: size, then kind)
-    return ResidualBatch(geom=geom, tus=sort_by_size(np.concatenate(tus), geom),
-                         coeffs=np.concatenate(arenas), scaling_factor=sf, covers_all=True)
+    batch = ResidualBatch(geom=geom, tus=sort_by_size(np.concatenate(tus), geom),
+                          coeffs=np.concatenate(arenas), scaling_factor=sf, covers_all=True)
+    return batch.with_extents() if extents else batch
 
 
 # ------------------------------------------------------------------------------ SAO

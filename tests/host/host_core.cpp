@@ -20,12 +20,18 @@ static void run_item_sf(const KernelArgs &a, int item) {
     TbParams t[32];
     int lane_tb_index[32];
     bool slow = false;
+    int zr = 2, zc = 2;  // the item's zero-extent codes: the weakest promise among its TBs (run_bin)
     for (int lane = 0; lane < 32; lane++) {
         bool valid;
         int tb = lane_tb<LOG2N>(a, item, lane, valid);
         lane_tb_index[lane] = valid ? tb : 0;
-        t[lane] = params_from_x(a, valid ? expand_desc(a, load_desc(a, tb, true)) : make_uint4(0, 0, 0, 0), valid, LOG2N);
+        const uint4 x = valid ? expand_desc(a, load_desc(a, tb, true)) : make_uint4(0, 0, 0, 0);
+        t[lane] = params_from_x(a, x, valid, LOG2N);
         slow |= t[lane].lsh != 0;
+        if (valid) {
+            zr = xd_zr(x) < zr ? xd_zr(x) : zr;
+            zc = xd_zc(x) < zc ? xd_zc(x) : zc;
+        }
         tile_issue<LOG2N>(lane, t[lane].src, valid, in_buf);
     }
     for (int lane = 0; lane < 32; lane++) phase_special<LOG2N>(lane, t[lane], in_buf);
@@ -44,8 +50,10 @@ static void run_item_sf(const KernelArgs &a, int item) {
         }
         if constexpr (LOG2N >= 4) {  // the kernel runs both columns of a lane in lock step
             const int xa = slot_index_rt(N, tl, 0), xb = slot_index_rt(N, tl, 1);
-            if (slow) stage1_pair<LOG2N, SF, true>(in, g, xa, xb, tl, sf1, q.w, q.rnd, q.sh, q.lsh);
-            else stage1_pair<LOG2N, SF, false>(in, g, xa, xb, tl, sf1, q.w, q.rnd, q.sh, 0);
+            if (slow) stage1_pair<LOG2N, SF, true, 0>(in, g, xa, xb, tl, sf1, q.w, q.rnd, q.sh, q.lsh);
+            else if (zr == 0) stage1_pair<LOG2N, SF, false, 0>(in, g, xa, xb, tl, sf1, q.w, q.rnd, q.sh, 0);
+            else if (zr == 1) stage1_pair<LOG2N, SF, false, 1>(in, g, xa, xb, tl, sf1, q.w, q.rnd, q.sh, 0);
+            else stage1_pair<LOG2N, SF, false, 2>(in, g, xa, xb, tl, sf1, q.w, q.rnd, q.sh, 0);
             continue;
         }
         for (int half = 0; half < 2; half++) {
@@ -62,7 +70,11 @@ static void run_item_sf(const KernelArgs &a, int item) {
         if (!q.valid || (q.flags & (P265_TU_SKIP | P265_TU_BYPASS))) continue;
         for (int c = 0; c < 2; c++) {
             const int row = tl + c * L::TPB;
-            if constexpr (LOG2N >= 4) stage2_row_g<LOG2N>(g, row, q.rnd2, q.sh2);  // the kernel's path
+            if constexpr (LOG2N >= 4) {  // the kernel's path
+                if (zc == 0) stage2_row_g<LOG2N, 0>(g, row, q.rnd2, q.sh2);
+                else if (zc == 1) stage2_row_g<LOG2N, 1>(g, row, q.rnd2, q.sh2);
+                else stage2_row_g<LOG2N, 2>(g, row, q.rnd2, q.sh2);
+            }
             else stage2_row<LOG2N>(g, row, q.dst + (size_t)row * q.stride, q.rnd2, q.sh2, q.flags & P265_TU_DST);
         }
     }

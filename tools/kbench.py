@@ -64,6 +64,8 @@ def main():
 
     if want("residual"):
         bench_residual(args, time_residual)
+    if want("lowfreq"):
+        bench_lowfreq(args, time_residual)
     if want("sao") or want("recon"):
         bench_sao_recon(args, eng, dev, stream, to_dev, want)
     if want("deblock"):
@@ -170,6 +172,26 @@ def bench_residual(args, time_residual):
             b = ResidualBatch(full.geom, np.ascontiguousarray(sel), full.coeffs, sf, covers_all=True)
             time_residual(b, "only %2dx%-2d (%7d TBs) %s" % (1 << l2, 1 << l2, len(sel), name))
 
+
+
+def bench_lowfreq(args, time_residual):
+    """Zero-aware passes: config 3's mix with confined coefficients (synth.SANITY_EXTENT_MIX), the big bins
+    with and without zero-extent codes in the descriptors, and one uniform code pair at a time."""
+    full = synth.residual_batch("4k10_lowfreq", n_pics=args.pics, n_unique=min(2, args.pics), extents=True).densified()
+    plain = ResidualBatch(full.geom, full.tus.copy(), full.coeffs, full.scaling_factor, covers_all=True)
+    plain.tus["rsvd"] = 0
+    time_residual(plain, "lowfreq mix, no codes")
+    time_residual(full, "lowfreq mix, codes")
+    for l2 in (5, 4):
+        for b, name in ((plain, "no codes"), (full, "codes")):
+            sel = b.tus[b.tus["log2n"] == l2]
+            time_residual(ResidualBatch(full.geom, np.ascontiguousarray(sel), full.coeffs, full.scaling_factor,
+                                        covers_all=True), "only %2dx%-2d lowfreq, %s" % (1 << l2, 1 << l2, name))
+        sel = full.tus[full.tus["log2n"] == l2].copy()
+        for z in (1, 2):   # timing only: every TB PROMISED the same extent (results are wrong for fuller TBs)
+            sel["rsvd"] = (z << 11) | (z << 13)
+            time_residual(ResidualBatch(full.geom, np.ascontiguousarray(sel), full.coeffs, full.scaling_factor,
+                                        covers_all=True), "only %2dx%-2d all codes (%d,%d) [timing]" % (1 << l2, 1 << l2, z, z))
 
 
 def bench_sao_recon(args, eng, dev, stream, to_dev, want):
