@@ -384,7 +384,8 @@ def run_gpu(args):
 
             def residual_z():
                 eng.residual_dev(z_tus.data_ptr(), z_bins, z_co.data_ptr(), z_sf.data_ptr(), zb.geom, z_out.data_ptr(),
-                                 zero_fill=False, sf_replicated=bool(zb.sf_replicated), dense_arena=zb.dense_small_bins())
+                                 zero_fill=False, sf_replicated=bool(zb.sf_replicated), dense_arena=zb.dense_small_bins(),
+                                 zero_extents=key == "ms_with_codes")
             for _ in range(3):
                 residual_z()
             zo[key] = round(timed(residual_z, args.steps) / args.steps, 4)

@@ -64,8 +64,11 @@ typedef struct p265_tu_desc {
  * promises that every coefficient in rows >= N >> z is zero, in the column field the same for
  * columns: 0 = nothing known, 1 = upper / left half only, 2 = first quarter only; 3 is rejected.
  * The residual kernels then skip the products of the empty rows / columns (zero contributes zero:
- * results are identical).  Dense arena (p265_residual_batch[_dev]): the codes are the caller's
- * promise; a TB that breaks it gets a wrong residual, nothing else is affected.  Packed stream
+ * results are identical).  The choice is made per work item of the kernels (2 consecutive 32x32 TBs,
+ * 4 consecutive 16x16 TBs of the list: the weakest promise among them), so TBs with similar extents
+ * should be neighbours in the list -- in decoding order they are.  Dense arena (p265_residual_batch,
+ * p265_residual_batch_dev with P265_RES_ZERO_EXTENTS): the codes are the caller's promise; a TB that
+ * breaks it gets a wrong residual, nothing else is affected.  Packed stream
  * (p265_residual_batch_packed[_dev]): the codes are ignored -- the device derives them from the
  * record's significance bitmap while it expands the stream.                                     */
 #define P265_TU_ZR_SHIFT 11
@@ -147,6 +150,10 @@ typedef struct p265_dbk_ctb {
                                     7.4.5 up-sampling of an 8x8 list (+ DC at [0][0]), as
                                     every conformant stream has them: enables the fast
                                     per-column factor path.  Unset: any table works.   */
+#define P265_RES_ZERO_EXTENTS 8 /* device entry point only (the host entry point finds out by itself, the
+                                   packed entry points always use the codes their unpack pass derives): the
+                                   descriptors of the 16x16 / 32x32 TBs carry zero-extent codes in rsvd.
+                                   Unset: the codes are ignored (full passes for every TB)                */
 #define P265_RES_DENSE_ARENA 4 /* device entry point only (the host entry point finds out by
                                   itself): inside the 8x8 bin and inside the 4x4 bin the
                                   coefficients of descriptor i directly follow those of

@@ -19,6 +19,7 @@ P265_OK, P265_EINVAL, P265_ECUDA, P265_ENOMEM = 0, -1, -2, -3
 RES_ZERO_FILL = 1
 RES_SF_REPLICATED = 2
 RES_DENSE_ARENA = 4
+RES_ZERO_EXTENTS = 8
 
 #: every symbol include/p265_b200.h declares (tests check the .so exports them all)
 SYMBOLS = (

@@ -156,8 +156,9 @@ static int diagnose_tu(const p265_tu_desc &t, long long k, int log2n, bool have_
     return set_error(P265_EINVAL, "descriptor %lld: qP %d out of range", k, t.qp);
 }
 
+// *any_codes = some 16x16 / 32x32 descriptor of a dense arena carries a zero-extent code (P265_RES_ZERO_EXTENTS)
 static int check_tus(const p265_tu_desc *tus, const int32_t bin_counts[4], size_t n_coeffs, const p265_pic_geom *g,
-                     bool have_table, bool *dense_small, bool packed = false) {
+                     bool have_table, bool *dense_small, bool packed = false, bool *any_codes = nullptr) {
     // one branch-free pass over caller data, on the latency path of every host call (119 k descriptors per
     // 4K picture); the diagnostics are formatted by a second look only when something is wrong
     TuLimits L;
@@ -169,7 +170,7 @@ static int check_tus(const p265_tu_desc *tus, const int32_t bin_counts[4], size_
     L.n_pics = g->n_pics;
     L.n_coeffs = n_coeffs;
     int64_t k = 0;
-    uint32_t not_dense = 0;
+    uint32_t not_dense = 0, codes = 0;
     for (int b = 0; b < 4; b++) {
         if (bin_counts[b] < 0) return set_error(P265_EINVAL, "negative bin count");
         const int log2n = 5 - b, n = 1 << log2n;
@@ -182,6 +183,7 @@ static int check_tus(const p265_tu_desc *tus, const int32_t bin_counts[4], size_
         if (packed) for (int32_t i = 0; i < cnt; i++) bad |= tu_bad<true>(t[i], log2n, bad_flags, L);
         else for (int32_t i = 0; i < cnt; i++) bad |= tu_bad<false>(t[i], log2n, bad_flags, L);
         if (b >= 2) for (int32_t i = 0; i < cnt; i++) not_dense |= t[i].coeff_off ^ (z0 + (uint32_t)i * units);
+        else for (int32_t i = 0; i < cnt; i++) codes |= t[i].rsvd;
         if (bad)
             for (int32_t i = 0; i < cnt; i++)
                 if (packed ? tu_bad<true>(t[i], log2n, bad_flags, L) : tu_bad<false>(t[i], log2n, bad_flags, L))
@@ -189,6 +191,7 @@ static int check_tus(const p265_tu_desc *tus, const int32_t bin_counts[4], size_
         k += cnt;
     }
     *dense_small = not_dense == 0;
+    if (any_codes) *any_codes = (codes >> P265_TU_ZR_SHIFT) != 0;
     return P265_OK;
 }
 
@@ -347,9 +350,10 @@ int p265_residual_batch(p265_ctx *ctx, const p265_tu_desc *tus, const int32_t bi
     int64_t n = 0;
     for (int b = 0; b < 4; b++) n += bin_counts[b] > 0 ? bin_counts[b] : 0;
     if (n && (!tus || !coeffs)) return set_error(P265_EINVAL, "descriptor / coefficient pointer is NULL");
-    bool dense_small = false;
-    if ((rc = check_tus(tus, bin_counts, n_coeffs, geom, scaling_factor != nullptr, &dense_small))) return rc;
+    bool dense_small = false, any_codes = false;
+    if ((rc = check_tus(tus, bin_counts, n_coeffs, geom, scaling_factor != nullptr, &dense_small, false, &any_codes))) return rc;
     flags = dense_small ? (flags | P265_RES_DENSE_ARENA) : (flags & ~P265_RES_DENSE_ARENA);  // found out here, not asserted
+    flags = any_codes ? (flags | P265_RES_ZERO_EXTENTS) : (flags & ~P265_RES_ZERO_EXTENTS);  // likewise
     // the whole buffer travels back to the host (row padding and inter-plane gaps included) and the
     // scratch slot is shared with other entry points: never return stale bytes of an earlier call
     flags |= P265_RES_ZERO_FILL;
@@ -395,7 +399,8 @@ int p265_residual_batch_packed_dev(p265_ctx *ctx, const p265_tu_desc *d_tus, con
     P265_CUDA(cudaSetDevice(ctx->device));
     if ((rc = launch_unpack(ctx, d_tus, bin_counts, d_stream, d_arena, d_tus_out))) return rc;
     // the arena comes out in descriptor order: the small bins are dense by construction
-    return launch_residual(ctx, d_tus_out, bin_counts, d_arena, d_sf, geom, d_residual, flags | P265_RES_DENSE_ARENA);
+    return launch_residual(ctx, d_tus_out, bin_counts, d_arena, d_sf, geom, d_residual,
+                           flags | P265_RES_DENSE_ARENA | P265_RES_ZERO_EXTENTS);
 }
 
 int p265_residual_batch_packed(p265_ctx *ctx, const p265_tu_desc *tus, const int32_t bin_counts[4], const uint8_t *stream,
@@ -431,7 +436,7 @@ int p265_residual_batch_packed(p265_ctx *ctx, const p265_tu_desc *tus, const int
             return rc;
     }
     rc = launch_residual(ctx, (const p265_tu_desc *)d_tus2, bin_counts, (const int16_t *)d_arena, (const uint8_t *)d_sf,
-                         geom, (int16_t *)d_out, flags | P265_RES_DENSE_ARENA);
+                         geom, (int16_t *)d_out, flags | P265_RES_DENSE_ARENA | P265_RES_ZERO_EXTENTS);
     if (rc) return rc;
     trace_mark(ctx, 1, 2);
     P265_CUDA(cudaMemcpyAsync(residual, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));

@@ -91,6 +91,12 @@ __device__ __noinline__ void stage2_call(uint32_t g_s, int row, int rnd2, int sh
 #endif
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// Small bins with a dense arena: software prefetch of a later item's tile into L2, P265_SMALL_PREFETCH items
+// ahead of the cp.async that fetches it (0 = off; the top stall of both small bins is the cp.async wait at the
+// head of the item loop, profiles/r2s3 source view).
+#ifndef P265_SMALL_PREFETCH
+#define P265_SMALL_PREFETCH 0
+#endif
 
 // One size bin, one warp: items w, w + W, w + 2W, ... of the bin.  Software pipeline,
 // everything asynchronous (cp.async / LDGSTS, no register staging):
@@ -101,7 +107,9 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 //     copy-out of item k      ->  whole rows per store instruction (OutMap)
 // so both dependent global-memory latencies of an item hide behind arithmetic.  The per-item
 // set-up reads the expanded record's fields as they are (no parameter derivation in the loop).
-template <int LOG2N, int SF>
+// ZEXT: honour the zero-extent codes of the records (KernelArgs.zext; a second copy of this loop, so that
+// batches without codes -- the benchmark's coefficient model -- run exactly the code they ran before)
+template <int LOG2N, int SF, bool ZEXT>
 __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride, int lane, unsigned char *wbase,
                                         const uint8_t *sfc) {
     using L = Layout<LOG2N>;
@@ -160,7 +168,7 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
             if (__any_sync(0xffffffffu, is_special)) phase_special<LOG2N>(lane, params_from_x(a, d, valid, LOG2N), in_base);
         }
         int zr = 0, zc = 0;
-        if (P265_ZERO_EXTENT) {  // lanes without a TB promise everything
+        if (ZEXT) {  // lanes without a TB promise everything
             zr = __reduce_min_sync(0xffffffffu, valid ? xd_zr(d) : 2);
             zc = __reduce_min_sync(0xffffffffu, valid ? xd_zc(d) : 2);
         }
@@ -282,6 +290,10 @@ __device__ __forceinline__ void run_bin8(const KernelArgs &a, int gw, int stride
     }
     int k = 0;
     for (int it = gw; it < n_items; it += stride, k ^= 1) {
+        if (P265_SMALL_PREFETCH > 0 && dense) {  // a later item's tile -> L2 (one 128-byte line = one TB per lane)
+            const int pit = it + P265_SMALL_PREFETCH * stride;
+            if (pit * 32 + lane < n_tb) prefetch_l2(a.coeffs + (size_t)(z0 + (uint32_t)(pit * 32 + lane) * 4u) * 16);
+        }
         cp_async_wait<0>();  // tile k and descriptor k+1 ...
         __syncwarp();        // ... of every lane; all lanes are done with the other tile buffer
         valid = it * 32 + lane < n_tb;
@@ -371,6 +383,10 @@ __device__ __forceinline__ void run_bin4(const KernelArgs &a, int gw, int stride
     int k = 0;  // item counter: tile stage k % 3, descriptor slot k % 4
 #pragma unroll 1
     for (int it = gw; it < n_items; it += stride, k++) {
+        if (P265_SMALL_PREFETCH > 0 && dense && lane < 8) {  // a later item's tile -> L2 (8 lines of 4 TBs)
+            const int pit = it + (P265_SMALL_PREFETCH + 2) * stride;
+            if (pit * 32 + lane * 4 < n_tb) prefetch_l2(a.coeffs + (size_t)(z0 + (uint32_t)(pit * 32 + lane * 4)) * 16);
+        }
         cp_async_wait<1>();
         const bool valid = it * 32 + lane < n_tb;
         const int st = k % kBin4Stages;
@@ -542,8 +558,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, BinCfg<BIN>::ctas) residual
         else build_sf_small<2>(a.sf, smem, threadIdx.x, blockDim.x);
         __syncthreads();
     }
-    if (BIN == 0) run_bin<5, SF>(a, gw, stride, lane, wbase, smem);
-    else if (BIN == 1) run_bin<4, SF>(a, gw, stride, lane, wbase, smem);
+    if (BIN == 0) {
+        if (P265_ZERO_EXTENT && a.zext) run_bin<5, SF, true>(a, gw, stride, lane, wbase, smem);
+        else run_bin<5, SF, false>(a, gw, stride, lane, wbase, smem);
+    } else if (BIN == 1) {
+        if (P265_ZERO_EXTENT && a.zext) run_bin<4, SF, true>(a, gw, stride, lane, wbase, smem);
+        else run_bin<4, SF, false>(a, gw, stride, lane, wbase, smem);
+    }
     else if (SmallStream<BIN>::on) {  // one item per warp; the grid covers the bin
         if (gw < a.first_item[BIN + 1] - a.first_item[BIN]) {
             if (BIN == 2) stream_bin8<SF>(a, gw, lane, wbase, smem);
@@ -665,6 +686,7 @@ static int fill_args(KernelArgs &a, const p265_tu_desc *d_tus, const int32_t bin
     a.sf = d_sf;
     a.sf_replicated = 0;
     a.dense_arena = 0;
+    a.zext = 0;
     a.out = d_out;
     for (int c = 0; c < 3; c++) a.plane_off[c] = g->plane_off[c];
     a.pic_stride = g->pic_stride;
@@ -828,6 +850,7 @@ int launch_residual(p265_ctx *ctx, const p265_tu_desc *d_tus, const int32_t bin_
     if (rc) return rc;
     a.sf_replicated = (flags & P265_RES_SF_REPLICATED) != 0;
     a.dense_arena = (flags & P265_RES_DENSE_ARENA) != 0;
+    a.zext = (flags & P265_RES_ZERO_EXTENTS) != 0;
     if (flags & P265_RES_ZERO_FILL)
         P265_CUDA(cudaMemsetAsync(d_out, 0, sizeof(int16_t) * (size_t)g->pic_stride * g->n_pics, ctx->stream));
     if (a.first_item[4] == 0) return P265_OK;

@@ -362,6 +362,7 @@ struct KernelArgs {
     int32_t n_tb[4];
     int32_t first_item[5];  // warp-item prefix sums per bin
     int32_t wait_prev;      // this launch directly follows expand_kernel: wait for it (griddepcontrol.wait)
+    int32_t zext;           // P265_RES_ZERO_EXTENTS: the big bins honour the zero-extent codes of their records
 };
 
 P265_HD int sf_matrix_offset(int log2n, int c_idx, int intra) {

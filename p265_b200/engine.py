@@ -131,13 +131,15 @@ class Engine:
             C.c_void_p(d_out), flags))
 
     def residual_dev(self, d_tus: int, bin_counts, d_coeffs: int, d_sf: int | None, geom: PicGeom,
-                     d_out: int, zero_fill: bool = False, sf_replicated: bool = False, dense_arena: bool = False):
+                     d_out: int, zero_fill: bool = False, sf_replicated: bool = False, dense_arena: bool = False,
+                     zero_extents: bool = False):
         """Device-resident batch.  `dense_arena` = ResidualBatch.dense_small_bins() of the batch the
-        device buffers were filled from (P265_RES_DENSE_ARENA: asserted by the caller here)."""
+        device buffers were filled from (P265_RES_DENSE_ARENA: asserted by the caller here);
+        `zero_extents` = its descriptors carry zero-extent codes (P265_RES_ZERO_EXTENTS)."""
         gs = _lib.geom_struct(geom)
         flags = (_lib.RES_ZERO_FILL if zero_fill else 0) | \
             (_lib.RES_SF_REPLICATED if (d_sf and sf_replicated) else 0) | \
-            (_lib.RES_DENSE_ARENA if dense_arena else 0)
+            (_lib.RES_DENSE_ARENA if dense_arena else 0) | (_lib.RES_ZERO_EXTENTS if zero_extents else 0)
         _lib.check(self._lib.p265_residual_batch_dev(
             self._ctx, C.c_void_p(d_tus), _lib.bins(bin_counts), C.c_void_p(d_coeffs),
             C.c_void_p(d_sf) if d_sf else None, C.byref(gs), C.c_void_p(d_out), flags))

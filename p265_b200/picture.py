@@ -159,11 +159,14 @@ class ResidualBatch:
 
     def with_extents(self) -> "ResidualBatch":
         """The same batch with the zero-extent codes of its 16x16 / 32x32 TBs in the descriptors
-        (`extent_codes`) and the list re-sorted by the ordering rule, which clusters equal codes."""
+        (`extent_codes`); the order of the list stays (see size_kind_order)."""
         tus = self.tus.copy()
         set_extents(tus, *extent_codes(tus, self.coeffs))
-        return ResidualBatch(self.geom, sort_by_size(tus, self.geom), self.coeffs, self.scaling_factor,
+        return ResidualBatch(self.geom, tus, self.coeffs, self.scaling_factor,
                              self.covers_all, self.sf_replicated, self.bins)
+
+    def has_extents(self) -> bool:
+        return bool((self.tus["rsvd"] >> TU_ZR_SHIFT).any())
 
     def dense_small_bins(self) -> bool:
         """True when, inside the 8x8 bin and inside the 4x4 bin, every TB's coefficients directly
@@ -227,10 +230,10 @@ def size_kind_order(tus: np.ndarray, geom=None) -> np.ndarray:
         left_shift = (tus["qp"].astype(np.int32) // 6 >= bd + tus["log2n"].astype(np.int32) - 5) & \
             ((tus["flags"] & (TU_PRESCALED | TU_BYPASS)) == 0)
         key = key + left_shift.astype(np.int32)
-    # ... and the zero-extent codes of the big TBs: a work item (2 TBs of 32x32, 4 of 16x16) runs the passes
-    # of the weakest promise among its TBs, so equal codes should sit next to each other
-    z = ((tus["rsvd"] >> TU_ZR_SHIFT) & 3).astype(np.int32) * 4 + ((tus["rsvd"] >> TU_ZC_SHIFT) & 3).astype(np.int32)
-    key = key * 16 + np.where(tus["log2n"] >= 4, z, 0)
+    # The zero-extent codes of the big TBs are deliberately NOT part of the key: a work item (2 TBs of 32x32, 4
+    # of 16x16) stores the rows of its TBs together, and in decoding order those TBs are spatial neighbours
+    # (64 / 128 contiguous bytes per row); sorted by codes they are not, and the 16x16 bin ran 57 % slower
+    # (B200, round 2) -- far more than the shortened passes of uniform items win.
     return np.argsort(key, kind="stable")
 
 

@@ -33,7 +33,7 @@ CONFIGS = {
 
 
 # "4k10_lowfreq": config 3 with the coefficients of every 16x16 / 32x32 TB confined to its first N >> zr
-# rows and N >> zc columns, (zr, zc) drawn from the distribution measured on the 16x16 TBs of the
+# rows and N >> zc columns, (zr, zc) drawn per 32x32 quadrant from the distribution measured on the 16x16 TBs of the
 # reference's only real stream (sanity.bin, 368 TBs: tests/test_extents.py prints it).  The SURVEY 8(d)
 # coefficient model itself leaves nothing to skip (a level in the last quarter of the rows of 99.85 % of its
 # 32x32 TBs); real streams do, and this variant is what the zero-aware passes are measured on.
@@ -48,14 +48,12 @@ def _nz_prob(n: int, density: float) -> np.ndarray:
     return np.minimum(1.0, p * (density * n * n / p.sum()))
 
 
-def _coeff_blocks(rng, count: int, n: int, stress: bool, extent_mix=None) -> np.ndarray:
+def _coeff_blocks(rng, count: int, n: int, stress: bool, pick=None) -> np.ndarray:
+    """`pick`: (count, 2) zero-extent codes (zr, zc) per TB or None."""
     if count == 0:
         return np.zeros((0, n, n), np.int16)
     box = None
-    if extent_mix is not None and n >= 16:   # per TB: coefficients only in rows < n >> zr, columns < n >> zc
-        codes = np.array([c for c, _ in extent_mix])
-        pick = codes[rng.choice(len(codes), size=count, p=np.array([p for _, p in extent_mix]) /
-                                sum(p for _, p in extent_mix))]
+    if pick is not None and n >= 16:   # per TB: coefficients only in rows < n >> zr, columns < n >> zc
         ar = np.arange(n)
         box = (ar[None, :, None] < (n >> pick[:, 0])[:, None, None]) & (ar[None, None, :] < (n >> pick[:, 1])[:, None, None])
     if stress:
@@ -95,6 +93,14 @@ def residual_picture(cfg: dict, rng, pic: int = 0, stress: bool = False):
     qp_q = rng.choice(np.array(cfg["qps"]), size=nq)
     byp_q = rng.random(nq) < cfg["bypass_frac"]
     recs, arenas, off = [], [], 0
+    # extent_mix: one (zr, zc) pair per 32x32 quadrant -- how sparse a block is follows the local texture, so
+    # the TBs of a quadrant (the four 16x16 TBs of one work item of the kernels) share it
+    quad_codes = None
+    if cfg.get("extent_mix") is not None:
+        mix = cfg["extent_mix"]
+        codes = np.array([c for c, _ in mix])
+        quad_codes = codes[rng.choice(len(codes), size=nq, p=np.array([p for _, p in mix]) / sum(p for _, p in mix))]
+    quads_per_row = (w + 31) // 32
 
     def emit(x, y, log2n, c_idx, qp, flags):
         nonlocal off
@@ -105,7 +111,11 @@ def residual_picture(cfg: dict, rng, pic: int = 0, stress: bool = False):
         r["x"], r["y"], r["log2n"], r["c_idx"] = x, y, log2n, c_idx
         r["qp"], r["flags"], r["pic"] = qp, flags, pic
         r["coeff_off"] = (off + np.arange(cnt, dtype=np.int64) * n * n) >> 4
-        blocks = _coeff_blocks(rng, cnt, n, stress, cfg.get("extent_mix"))
+        pick = None
+        if quad_codes is not None and n >= 16:
+            sh = 1 if c_idx else 0
+            pick = quad_codes[((y << sh) >> 5) * quads_per_row + ((x << sh) >> 5)]
+        blocks = _coeff_blocks(rng, cnt, n, stress, pick)
         byp = (flags & TU_BYPASS) != 0
         if byp.any():      # bypass "coefficients" are residual samples: keep them small
             blocks[byp] = np.clip(blocks[byp], -(1 << bd), (1 << bd) - 1)

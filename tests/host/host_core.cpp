@@ -135,7 +135,7 @@ static void run_item(const KernelArgs &a, int item) {
 extern "C" int host_residual_batch(const p265_tu_desc *tus, const int32_t bin_counts[4], const int16_t *coeffs,
                                    const uint8_t *sf, int sf_replicated, const p265_pic_geom *g, int16_t *out) {
     KernelArgs a;
-    a.tus = tus; a.xtus = nullptr; a.wait_prev = 0; a.coeffs = coeffs; a.sf = sf; a.out = out; a.sf_replicated = sf_replicated;
+    a.tus = tus; a.xtus = nullptr; a.wait_prev = 0; a.zext = 1; a.coeffs = coeffs; a.sf = sf; a.out = out; a.sf_replicated = sf_replicated;
     for (int c = 0; c < 3; c++) a.plane_off[c] = g->plane_off[c];
     a.pic_stride = g->pic_stride;
     a.stride_y = g->stride_y; a.stride_c = g->stride_c;

@@ -101,7 +101,26 @@ def test_packed_stream_device_entry(engine, c_oracle):
     # the expanded arena is the dense arena in descriptor order
     dense = batch.densified()
     assert np.array_equal(d_arena.cpu().numpy()[:dense.coeffs.nbytes].view(np.int16), dense.coeffs)
-    assert np.array_equal(d_tus2.cpu().numpy().view(TU_DESC), dense.tus)
+    # ... and the rewritten descriptors carry the zero-extent codes unpack_kernel derives from the bitmaps:
+    # the same codes the host derives from the coefficients (picture.extent_codes)
+    from p265_b200.picture import extent_codes, set_extents
+    want = dense.tus.copy()
+    set_extents(want, *extent_codes(dense.tus, dense.coeffs))
+    assert np.array_equal(d_tus2.cpu().numpy().view(TU_DESC), want)
+    low = synth.residual_batch(small_cfg("4k10_lowfreq", 512, 256), n_pics=2).densified()   # every code pair occurs
+    pl = low.packed()
+    d_tus, d_st = to_dev(pl.tus), to_dev(pl.stream)
+    d_tus2 = torch.empty_like(d_tus)
+    engine.residual_packed_dev(d_tus.data_ptr(), pl.bin_counts(), d_st.data_ptr(), d_sf.data_ptr(), pl.geom,
+                               d_arena.data_ptr(), d_tus2.data_ptr(), d_out.data_ptr(), zero_fill=False,
+                               sf_replicated=bool(pl.sf_replicated))
+    engine.sync()
+    want = low.tus.copy()
+    zr, zc = extent_codes(low.tus, low.coeffs)
+    assert len(set(zip(zr[low.tus["log2n"] >= 4].tolist(), zc[low.tus["log2n"] >= 4].tolist()))) >= 8
+    set_extents(want, zr, zc)
+    assert np.array_equal(d_tus2.cpu().numpy().view(TU_DESC), want)
+    assert_planes_equal(low.geom, d_out.cpu().numpy().view(np.int16), c_oracle.residual_batch(low, zero_fill=False))
 
 
 def test_packed_stream_rejects_malformed_input(engine):

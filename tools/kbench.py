@@ -39,7 +39,8 @@ def main():
 
         def run():
             eng.residual_dev(d_tus.data_ptr(), bins, d_co.data_ptr(), d_sf.data_ptr() if d_sf is not None else None,
-                             batch.geom, d_out.data_ptr(), zero_fill=False, sf_replicated=rep, dense_arena=dense)
+                             batch.geom, d_out.data_ptr(), zero_fill=False, sf_replicated=rep, dense_arena=dense,
+                             zero_extents=bool((batch.tus["rsvd"] >> 11).any()))
         for _ in range(3):
             run()
         torch.cuda.synchronize()
@@ -60,12 +61,20 @@ def main():
     only = set(x for x in args.only.split(",") if x)
 
     def want(name):
-        return not only or name in only
+        return (not only and name != "lowfreq") or name in only
 
     if want("residual"):
         bench_residual(args, time_residual)
     if want("lowfreq"):
         bench_lowfreq(args, time_residual)
+    if "zprof" in only:   # ncu target: the 32x32 / 16x16 bins without codes and with every TB promising the first quarter
+        full = synth.residual_batch("4k10_lowfreq", n_pics=args.pics, n_unique=min(2, args.pics), extents=True).densified()
+        for l2 in (5, 4):
+            sel = full.tus[full.tus["log2n"] == l2].copy()
+            for z in (0, 2):
+                sel["rsvd"] = (z << 11) | (z << 13)
+                time_residual(ResidualBatch(full.geom, np.ascontiguousarray(sel.copy()), full.coeffs, full.scaling_factor,
+                                            covers_all=True), "zprof %2dx%-2d codes (%d,%d)" % (1 << l2, 1 << l2, z, z))
     if want("sao") or want("recon"):
         bench_sao_recon(args, eng, dev, stream, to_dev, want)
     if want("deblock"):
