@@ -65,8 +65,10 @@ typedef struct p265_tu_desc {
  * columns: 0 = nothing known, 1 = upper / left half only, 2 = first quarter only; 3 is rejected.
  * The residual kernels then skip the products of the empty rows / columns (zero contributes zero:
  * results are identical).  The choice is made per work item of the kernels (2 consecutive 32x32 TBs,
- * 4 consecutive 16x16 TBs of the list: the weakest promise among them), so TBs with similar extents
- * should be neighbours in the list -- in decoding order they are.  Dense arena (p265_residual_batch,
+ * 4 consecutive 16x16 TBs, counted from the first descriptor of the size: the weakest promise among
+ * them).  Any order is correct; fastest is a list in which the TBs of an item are spatial neighbours
+ * (decoding order) and items with the same code pair follow each other (p265_b200/picture.py:
+ * size_kind_order does both).  Dense arena (p265_residual_batch,
  * p265_residual_batch_dev with P265_RES_ZERO_EXTENTS): the codes are the caller's promise; a TB that
  * breaks it gets a wrong residual, nothing else is affected.  Packed stream
  * (p265_residual_batch_packed[_dev]): the codes are ignored -- the device derives them from the

@@ -107,9 +107,7 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 //     copy-out of item k      ->  whole rows per store instruction (OutMap)
 // so both dependent global-memory latencies of an item hide behind arithmetic.  The per-item
 // set-up reads the expanded record's fields as they are (no parameter derivation in the loop).
-// ZEXT: honour the zero-extent codes of the records (KernelArgs.zext; a second copy of this loop, so that
-// batches without codes -- the benchmark's coefficient model -- run exactly the code they ran before)
-template <int LOG2N, int SF, bool ZEXT>
+template <int LOG2N, int SF>
 __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride, int lane, unsigned char *wbase,
                                         const uint8_t *sfc) {
     using L = Layout<LOG2N>;
@@ -167,15 +165,8 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
             slow = __any_sync(0xffffffffu, lsh != 0);
             if (__any_sync(0xffffffffu, is_special)) phase_special<LOG2N>(lane, params_from_x(a, d, valid, LOG2N), in_base);
         }
-        int zr = 0, zc = 0;
-        if (ZEXT) {  // lanes without a TB promise everything
-            zr = __reduce_min_sync(0xffffffffu, valid ? xd_zr(d) : 2);
-            zc = __reduce_min_sync(0xffffffffu, valid ? xd_zc(d) : 2);
-        }
-        if (slow) stage1_pair_call<LOG2N, SF, true, 0>(in_s, g_s, x0, x1, tl, sf1, w, rnd, sh, lsh);  // rare
-        else if (zr == 0) stage1_pair_call<LOG2N, SF, false, 0>(in_s, g_s, x0, x1, tl, sf1, w, rnd, sh, 0);
-        else if (zr == 1) stage1_pair_call<LOG2N, SF, false, 1>(in_s, g_s, x0, x1, tl, sf1, w, rnd, sh, 0);
-        else stage1_pair_call<LOG2N, SF, false, 2>(in_s, g_s, x0, x1, tl, sf1, w, rnd, sh, 0);
+        if (!slow) stage1_pair_call<LOG2N, SF, false, 0>(in_s, g_s, x0, x1, tl, sf1, w, rnd, sh, 0);
+        else stage1_pair_call<LOG2N, SF, true, 0>(in_s, g_s, x0, x1, tl, sf1, w, rnd, sh, lsh);  // rare
         __syncwarp();  // `in` is consumed, g is complete
         if (more) {
             tile_issue<LOG2N>(lane, a.coeffs + (size_t)ring[RS * k1].z * 16, v1, in_base);
@@ -185,9 +176,7 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
         cp_async_commit();
         if (valid && !is_special) {
             const int sh2 = xd_sh2(d);
-            if (zc == 0) stage2_call<LOG2N, 0>(g_s, tl, 1 << (sh2 - 1), sh2);
-            else if (zc == 1) stage2_call<LOG2N, 1>(g_s, tl, 1 << (sh2 - 1), sh2);
-            else stage2_call<LOG2N, 2>(g_s, tl, 1 << (sh2 - 1), sh2);
+            stage2_call<LOG2N, 0>(g_s, tl, 1 << (sh2 - 1), sh2);
         }
         __syncwarp();  // every result row of the item sits in g
         // copy-out: store instruction i = rows 4i .. 4i+3 of every TB of the item; the lane stays
@@ -200,6 +189,113 @@ __device__ __forceinline__ void run_bin(const KernelArgs &a, int gw, int stride,
                 *reinterpret_cast<uint4 *>(a.out + (e0 + (uint32_t)(i * M::RPI) * row_step)) = out_chunk_load<LOG2N>(g, i, lane);
         }
         const int kk = k; k = k1; k1 = k2; k2 = kk;
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+}
+
+// The same bin with the zero-extent codes of the records honoured (KernelArgs.zext).  A separate copy of the
+// loop, so that batches without codes -- the benchmark's coefficient model -- run exactly the code above.
+// Differences:
+//   * the item's code pair = the weakest promise among its TBs (records of special / left-shift TBs carry 0),
+//     found one item ahead, when the next item's records have landed in the ring;
+//   * with the code known that early, the next tile is requested at the TOP of the current item, into a second
+//     `in` buffer (the launch reserves it), and only its first N >> zr rows are copied: a shortened item is
+//     too short to hide a tile request that is issued only after its own column pass (measured: the 32x32 bin
+//     with every TB at code (2,2) executed 44 % fewer instructions and ran 15 % faster, long-scoreboard
+//     stalls 0.2 -> 2.0 warps per issue);
+//   * column and row passes are chosen by code: 172 / 88 / 46 IDP.2A per 32-point pass.
+template <int LOG2N, int SF>
+__device__ __forceinline__ void run_bin_zext(const KernelArgs &a, int gw, int stride, int lane, unsigned char *wbase,
+                                             int in1_off, const uint8_t *sfc) {
+    using L = Layout<LOG2N>;
+    using M = OutMap<LOG2N>;
+    constexpr int N = L::N, bin = 5 - LOG2N;
+    const int n_items = a.first_item[bin + 1] - a.first_item[bin];
+    if (gw >= n_items) return;
+    const int n_tb = a.n_tb[bin];
+    const uint4 *xt = a.xtus + a.first_tb[bin];
+    auto inb = [&](int which) { return wbase + (which ? in1_off : 0); };  // the two tile buffers of the warp
+    unsigned char *g_base = wbase + L::WARP_BYTES;
+    const int tb_l = lane / L::TPB, tl = lane % L::TPB;
+    constexpr int RS = L::TBS;
+    uint4 *ring0 = reinterpret_cast<uint4 *>(wbase + 2 * L::WARP_BYTES);
+    uint4 *ring = ring0 + tb_l;
+    unsigned char *g = g_base + tb_l * L::TB_BYTES;
+    const uint32_t in_s0 = smem_addr(wbase + tb_l * L::TB_BYTES);
+    const uint32_t g_s = smem_addr(g), sfc_s = smem_addr(sfc);
+    const int x0 = slot_index_rt(N, tl, 0), x1 = slot_index_rt(N, tl, 1);
+    auto item_codes = [&](const uint4 d, bool v, int &zr, int &zc) {  // lanes without a TB promise everything
+        zr = __reduce_min_sync(0xffffffffu, v ? xd_zr(d) : 2);
+        zc = __reduce_min_sync(0xffffffffu, v ? xd_zc(d) : 2);
+    };
+    int zr, zc;
+    {
+        const int tb = gw * L::TBS + tb_l;
+        const bool valid = tb < n_tb;
+        const uint4 d0 = valid ? xt[tb] : make_uint4(0, 0, 0, 0);
+        ring[0] = d0;
+        item_codes(d0, valid, zr, zc);
+        tile_issue<LOG2N>(lane, a.coeffs + (size_t)d0.z * 16, valid, inb(0), N >> zr);
+        const int tb1 = (gw + stride) * L::TBS + tb_l;
+        if (gw + stride < n_items && tb1 < n_tb && tl == 0) copy16_async(&ring[RS], &xt[tb1]);
+        cp_async_commit();
+    }
+    const uint32_t out_row0 = (uint32_t)M::row0(lane), out_part8 = (uint32_t)M::part(lane) * 8;
+    int k = 0, k1 = 1, k2 = 2, par = 0;
+    for (int it = gw; it < n_items; it += stride) {
+        cp_async_wait<0>();  // tile k and descriptor k+1 have landed
+        __syncwarp();        // ... for every lane; all lanes are done with g and with the other `in` buffer
+        const bool valid = it * L::TBS + tb_l < n_tb;
+        const bool more = it + stride < n_items;
+        const bool v1 = more && (it + stride) * L::TBS + tb_l < n_tb;
+        const uint4 d = ring[RS * k];
+        int zr1 = 0, zc1 = 0;
+        if (more) {  // the next item: its codes, then its tile (the rows its row code leaves) and the record after it
+            const uint4 dn = ring[RS * k1];
+            item_codes(dn, v1, zr1, zc1);
+            tile_issue<LOG2N>(lane, a.coeffs + (size_t)dn.z * 16, v1, inb(par ^ 1), N >> zr1);
+            const int tb2 = (it + 2 * stride) * L::TBS + tb_l;
+            if (it + 2 * stride < n_items && tb2 < n_tb && tl == 0) copy16_async(&ring[RS * k2], &xt[tb2]);
+        }
+        cp_async_commit();
+        const int flags = valid ? (int)xd_flags(d) : 0;
+        const int w = valid ? xd_w(d) : 0, sh = xd_sh(d), lsh = valid ? xd_lsh(d) : 0;
+        const int rnd = (1 << sh) >> 1;
+        uint64_t sf1 = 0;
+        if (SF == SF_REPLICATED) sf1 = sfc_s + (valid ? xd_mid(d) : 0u) * kSfcStride;
+        else if (SF == SF_GENERAL && valid && !(flags & P265_TU_PRESCALED))
+            sf1 = reinterpret_cast<uintptr_t>(a.sf + sf_matrix_offset(LOG2N, 0, 1) + (xd_mid(d) << (2 * LOG2N)));
+        const bool is_special = (flags & (P265_TU_SKIP | P265_TU_BYPASS)) != 0;
+        bool slow = false;
+        if (__any_sync(0xffffffffu, is_special || lsh != 0)) {  // such an item has code (0, 0): the whole tile is there
+            slow = __any_sync(0xffffffffu, lsh != 0);
+            if (__any_sync(0xffffffffu, is_special)) phase_special<LOG2N>(lane, params_from_x(a, d, valid, LOG2N), inb(par));
+        }
+        const uint32_t in_cur = in_s0 + (par ? (uint32_t)in1_off : 0u);
+        if (slow) stage1_pair_call<LOG2N, SF, true, 0>(in_cur, g_s, x0, x1, tl, sf1, w, rnd, sh, lsh);  // rare
+        else if (zr == 0) stage1_pair_call<LOG2N, SF, false, 0>(in_cur, g_s, x0, x1, tl, sf1, w, rnd, sh, 0);
+        else if (zr == 1) stage1_pair_call<LOG2N, SF, false, 1>(in_cur, g_s, x0, x1, tl, sf1, w, rnd, sh, 0);
+        else stage1_pair_call<LOG2N, SF, false, 2>(in_cur, g_s, x0, x1, tl, sf1, w, rnd, sh, 0);
+        __syncwarp();  // g is complete
+        if (valid && !is_special) {
+            const int sh2 = xd_sh2(d);
+            if (zc == 0) stage2_call<LOG2N, 0>(g_s, tl, 1 << (sh2 - 1), sh2);
+            else if (zc == 1) stage2_call<LOG2N, 1>(g_s, tl, 1 << (sh2 - 1), sh2);
+            else stage2_call<LOG2N, 2>(g_s, tl, 1 << (sh2 - 1), sh2);
+        }
+        __syncwarp();  // every result row of the item sits in g
+        if (valid && !is_special) {
+            const uint32_t row_step = (uint32_t)xd_stride(d);
+            const uint32_t e0 = d.x + out_row0 * row_step + out_part8;
+#pragma unroll
+            for (int i = 0; i < M::ITERS; i++)
+                *reinterpret_cast<uint4 *>(a.out + (e0 + (uint32_t)(i * M::RPI) * row_step)) = out_chunk_load<LOG2N>(g, i, lane);
+        }
+        const int kk = k; k = k1; k1 = k2; k2 = kk;
+        par ^= 1;
+        zr = zr1;
+        zc = zc1;
     }
     cp_async_wait<0>();
     __syncwarp();
@@ -529,6 +625,8 @@ struct BinCfg {
         : BIN == 0 ? kSfcBytes + kWarpsPerCta * (2 * Layout<5>::WARP_BYTES + 3 * Layout<5>::TBS * 16 + 32)
         : BIN == 1 ? kSfcBytes + kWarpsPerCta * (2 * Layout<4>::WARP_BYTES + 3 * Layout<4>::TBS * 16)
                    : kSfcBytes + (SmallStream<2>::on ? kWarpsPerCta * kWarpSmemBytes : kCtaSmemBytes);
+    // with zero-extent codes (run_bin_zext): a second tile buffer per warp of the big bins, behind the ring
+    static constexpr int zext_extra = BIN == 0 ? Layout<5>::WARP_BYTES : (BIN == 1 ? Layout<4>::WARP_BYTES : 0);
 };
 
 template <int BIN, int SF>
@@ -545,7 +643,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, BinCfg<BIN>::ctas) residual
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stride = gridDim.x * kWarpsPerCta;
     const int gw = blockIdx.x * kWarpsPerCta + warp;
-    constexpr int warp_bytes = (BinCfg<BIN>::smem - kSfcBytes) / kWarpsPerCta;
+    constexpr int warp_bytes0 = (BinCfg<BIN>::smem - kSfcBytes) / kWarpsPerCta;
+    const bool zext = P265_ZERO_EXTENT && BIN <= 1 && a.zext;
+    const int warp_bytes = warp_bytes0 + (zext ? BinCfg<BIN>::zext_extra : 0);
     unsigned char *wbase = smem + kSfcBytes + warp * warp_bytes;
     if (SF == SF_REPLICATED && BIN <= 1) {
         if (BIN == 0) build_sf_compact<5>(a.sf, smem, threadIdx.x, blockDim.x);
@@ -559,11 +659,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, BinCfg<BIN>::ctas) residual
         __syncthreads();
     }
     if (BIN == 0) {
-        if (P265_ZERO_EXTENT && a.zext) run_bin<5, SF, true>(a, gw, stride, lane, wbase, smem);
-        else run_bin<5, SF, false>(a, gw, stride, lane, wbase, smem);
+        if (zext) run_bin_zext<5, SF>(a, gw, stride, lane, wbase, warp_bytes0, smem);
+        else run_bin<5, SF>(a, gw, stride, lane, wbase, smem);
     } else if (BIN == 1) {
-        if (P265_ZERO_EXTENT && a.zext) run_bin<4, SF, true>(a, gw, stride, lane, wbase, smem);
-        else run_bin<4, SF, false>(a, gw, stride, lane, wbase, smem);
+        if (zext) run_bin_zext<4, SF>(a, gw, stride, lane, wbase, warp_bytes0, smem);
+        else run_bin<4, SF>(a, gw, stride, lane, wbase, smem);
     }
     else if (SmallStream<BIN>::on) {  // one item per warp; the grid covers the bin
         if (gw < a.first_item[BIN + 1] - a.first_item[BIN]) {
@@ -720,15 +820,18 @@ static int launch_bin(p265_ctx *ctx, KernelArgs a, bool first, cudaStream_t stre
     a.wait_prev = (!plain && first && expanded) ? 1 : 0;
     const int items = a.first_item[BIN + 1] - a.first_item[BIN];
     if (items == 0) return P265_OK;
-    constexpr int smem = BinCfg<BIN>::smem;
+    const bool zext = P265_ZERO_EXTENT && BIN <= 1 && a.zext;
+    const int smem = BinCfg<BIN>::smem + (zext ? kWarpsPerCta * BinCfg<BIN>::zext_extra : 0);
     // CTAs per SM the kernel really gets; function attributes are per device, so the
     // carve-out hint is set once for every device this process uses
-    static int occ_dev[64] = {0};
-    int &occ = occ_dev[ctx->device & 63];
+    static int occ_dev[2][64] = {{0}};
+    int &occ = occ_dev[zext ? 1 : 0][ctx->device & 63];
     if (!occ) {
         int o = 0;
         P265_CUDA(cudaFuncSetAttribute(residual_kernel<BIN, SF>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        cudaSharedmemCarveoutMaxShared));
+        P265_CUDA(cudaFuncSetAttribute(residual_kernel<BIN, SF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       BinCfg<BIN>::smem + kWarpsPerCta * BinCfg<BIN>::zext_extra));
         P265_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, residual_kernel<BIN, SF>, kWarpsPerCta * 32,
                                                                 smem));
         occ = o < 1 ? 1 : o;

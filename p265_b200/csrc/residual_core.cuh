@@ -485,8 +485,11 @@ P265_HD uint4 expand_desc(const KernelArgs &a, const uint4 d) {
     // matrixId 6, where the small-bin kernels keep an all-ones matrix
     const int mid = (t.flags & P265_TU_PRESCALED) ? 6 : sf_matrix_id(log2n, c_idx, t.flags);
     const uint32_t flags = (uint32_t)t.flags & 0xff;
-    // extents only matter where a transform runs on them: not for transform-skip / bypass TBs (4x4 only anyway)
-    const uint32_t zr = (uint32_t)desc_zr(d), zc = (uint32_t)desc_zc(d);
+    // extents only mean something where a transform runs: a bypass TB's "coefficients" are residual samples and
+    // the element-wise path reads all of them -- such a TB promises nothing (and with it its work item)
+    // (likewise a TB with the rare left-shift dequantisation: its item runs the one full-extent copy of that pass)
+    const bool elementwise = (t.flags & (P265_TU_SKIP | P265_TU_BYPASS)) != 0 || t.lsh != 0;
+    const uint32_t zr = elementwise ? 0u : (uint32_t)desc_zr(d), zc = elementwise ? 0u : (uint32_t)desc_zc(d);
     return make_uint4(dst_off, flags | ((uint32_t)mid << 8) | ((uint32_t)t.sh2 << 11) | ((uint32_t)(t.stride >> 3) << 15),
                       d.z, (uint32_t)t.w | ((uint32_t)t.sh << 16) | (zr << 21) | ((uint32_t)t.lsh << 24) | (zc << 28));
 }
@@ -568,8 +571,10 @@ P265_HD uint16_t sat_s16(int v) { return (uint16_t)(pack_sat(v, 0) & 0xffff); }
 // Each lane copies its share (two columns' worth = 4N bytes) of its TB, 16 bytes at a
 // time, fully coalesced across the TB's lanes.  Asynchronous on the device: the caller
 // commits / waits the cp.async group and __syncwarp()s before anyone reads the tile.
+// `rows` (a multiple of 4, <= N): only the first `rows` rows of the TB are copied -- what a zero-extent code
+// leaves to read (iteration i of the loop moves rows 4i .. 4i+3 for both shared-memory sizes).
 template <int LOG2N>
-P265_HD void tile_issue(int lane, const int16_t *src, bool valid, unsigned char *in_base) {
+P265_HD void tile_issue(int lane, const int16_t *src, bool valid, unsigned char *in_base, int rows = 1 << LOG2N) {
     using L = Layout<LOG2N>;
     constexpr int N = L::N;
     const int tb = lane / L::TPB, tl = lane % L::TPB;
@@ -577,6 +582,7 @@ P265_HD void tile_issue(int lane, const int16_t *src, bool valid, unsigned char 
     unsigned char *in = in_base + tb * L::TB_BYTES;
     P265_UNROLL
     for (int i = 0; i < N / 4; i++) {
+        if (N >= 16 && 4 * i >= rows) break;
         const int chunk = tl + i * L::TPB;  // 16-byte chunk index inside the TB
         if (N >= 8) {
             copy16_async(in + chunk * 16, src + chunk * 8);

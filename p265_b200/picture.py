@@ -159,10 +159,10 @@ class ResidualBatch:
 
     def with_extents(self) -> "ResidualBatch":
         """The same batch with the zero-extent codes of its 16x16 / 32x32 TBs in the descriptors
-        (`extent_codes`); the order of the list stays (see size_kind_order)."""
+        (`extent_codes`) and the list re-ordered by the ordering rule (whole work items by code pair)."""
         tus = self.tus.copy()
         set_extents(tus, *extent_codes(tus, self.coeffs))
-        return ResidualBatch(self.geom, tus, self.coeffs, self.scaling_factor,
+        return ResidualBatch(self.geom, sort_by_size(tus, self.geom), self.coeffs, self.scaling_factor,
                              self.covers_all, self.sf_replicated, self.bins)
 
     def has_extents(self) -> bool:
@@ -230,11 +230,30 @@ def size_kind_order(tus: np.ndarray, geom=None) -> np.ndarray:
         left_shift = (tus["qp"].astype(np.int32) // 6 >= bd + tus["log2n"].astype(np.int32) - 5) & \
             ((tus["flags"] & (TU_PRESCALED | TU_BYPASS)) == 0)
         key = key + left_shift.astype(np.int32)
-    # The zero-extent codes of the big TBs are deliberately NOT part of the key: a work item (2 TBs of 32x32, 4
-    # of 16x16) stores the rows of its TBs together, and in decoding order those TBs are spatial neighbours
-    # (64 / 128 contiguous bytes per row); sorted by codes they are not, and the 16x16 bin ran 57 % slower
-    # (B200, round 2) -- far more than the shortened passes of uniform items win.
-    return np.argsort(key, kind="stable")
+    order = np.argsort(key, kind="stable")
+    # Second level, only when descriptors carry zero-extent codes: whole WORK ITEMS of the big bins (2
+    # consecutive 32x32 TBs, 4 consecutive 16x16 TBs, counted from the start of the bin -- P265_ITEM_TBS in the
+    # header) are ordered by the item's code pair, the weakest promise among its TBs.  Measured on B200 (round
+    # 2): (a) TBs sorted individually by code lose their spatial neighbours inside an item (an item stores the
+    # rows of its TBs together: 64 / 128 contiguous bytes per row in decoding order) and the 16x16 bin ran 57 %
+    # slower; (b) items left in decoding order run a different pair of passes every few items, all copies of
+    # the passes are hot at once and the instruction cache thrashes (32x32 bin 28 % slower than without codes).
+    # Items as units keep (a) and give every copy of the passes a long uninterrupted run.
+    if (tus["rsvd"] >> TU_ZR_SHIFT).any():
+        t = tus[order]
+        special = (t["flags"] & (TU_BYPASS | TU_SKIP)) != 0
+        zr = np.where(special, 0, (t["rsvd"] >> TU_ZR_SHIFT) & 3).astype(np.int32)
+        zc = np.where(special, 0, (t["rsvd"] >> TU_ZC_SHIFT) & 3).astype(np.int32)
+        for log2n, per in ((5, 2), (4, 4)):
+            idx = np.flatnonzero(t["log2n"] == log2n)
+            g = idx.size // per
+            if g < 2:
+                continue
+            lo = int(idx[0])
+            code = zr[lo:lo + g * per].reshape(g, per).min(axis=1) * 4 + zc[lo:lo + g * per].reshape(g, per).min(axis=1)
+            perm = np.argsort(code, kind="stable")
+            order[lo:lo + g * per] = order[lo:lo + g * per].reshape(g, per)[perm].reshape(-1)
+    return order
 
 
 def sort_by_size(tus: np.ndarray, geom=None) -> np.ndarray:

@@ -32,7 +32,12 @@ static void run_item_sf(const KernelArgs &a, int item) {
             zr = xd_zr(x) < zr ? xd_zr(x) : zr;
             zc = xd_zc(x) < zc ? xd_zc(x) : zc;
         }
-        tile_issue<LOG2N>(lane, t[lane].src, valid, in_buf);
+    }
+    // the kernel copies only the rows the item's row code leaves (the rest of the buffer keeps the 0xA5 fill:
+    // a pass that read beyond its extent would not match the oracle)
+    for (int lane = 0; lane < 32; lane++) {
+        if constexpr (LOG2N >= 4) tile_issue<LOG2N>(lane, t[lane].src, t[lane].valid, in_buf, N >> zr);
+        else tile_issue<LOG2N>(lane, t[lane].src, t[lane].valid, in_buf);
     }
     for (int lane = 0; lane < 32; lane++) phase_special<LOG2N>(lane, t[lane], in_buf);
     alignas(16) uint8_t sfc[512];

@@ -42,11 +42,32 @@ def test_extent_codes_of_hand_made_blocks():
     set_extents(tus, zr, zc)
     assert (tus["rsvd"] & TU_LEVELS_MASK).tolist() == [5, 5, 5, 5]
     assert codes(tus)[0].tolist() == [2, 0, 2, 0] and codes(tus)[1].tolist() == [1, 2, 0, 0]
-    # the ordering rule leaves the codes alone: neighbours in decoding order are neighbours in the picture,
-    # which matters more to the kernels than uniform codes (picture.size_kind_order)
     order = sort_by_size(tus)
     assert order["log2n"].tolist() == [5, 5, 4, 3]
-    assert codes(order)[0].tolist()[:2] == [2, 0]
+
+
+def test_ordering_rule_moves_whole_items():
+    """Items (4 consecutive 16x16 TBs, 2 consecutive 32x32 TBs) are ordered by their weakest promise and stay intact."""
+    n = 4 * 6 + 3                                  # six items of 16x16 TBs and a partial one
+    tus = np.zeros(n + 5, TU_DESC)
+    tus["log2n"][:5] = 5
+    tus["log2n"][5:] = 4
+    tus["x"] = np.arange(n + 5)                    # identity tag
+    zr = np.zeros(n + 5, int)
+    zc = np.zeros(n + 5, int)
+    zr[5:] = np.repeat([2, 0, 1, 2, 2, 0, 1], 4)[:n]
+    zc[5:] = np.repeat([2, 0, 1, 2, 1, 0, 2], 4)[:n]
+    zr[5 + 12] = 0                                 # one TB of the fourth item promises nothing -> item code (0, 2)
+    zr[:5], zc[:5] = [2, 2, 0, 1, 2], [2, 2, 0, 1, 2]
+    set_extents(tus, zr, zc)
+    out = sort_by_size(tus)
+    assert out["log2n"].tolist() == [5] * 5 + [4] * n
+    items16 = out["x"][5:5 + 24].reshape(6, 4)
+    assert all((row == row[0] + np.arange(4)).all() and (row[0] - 5) % 4 == 0 for row in items16)    # intact
+    first = ((items16[:, 0] - 5) // 4).tolist()
+    assert first == [1, 5, 3, 2, 4, 0]             # codes (0,0) (0,0) (0,2) (1,1) (2,1) (2,2)
+    assert out["x"][5 + 24:].tolist() == list(range(5 + 24, 5 + 27))                                   # the partial item stays last
+    assert out["x"][:5].tolist() == [2, 3, 0, 1, 4]  # 32x32: items (2,3) code (0,0), (0,1) code (2,2); the odd TB last
 
 
 def test_config3_model_leaves_nothing_to_skip():

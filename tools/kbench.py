@@ -36,11 +36,12 @@ def main():
         bins = batch.bin_counts()
         rep = bool(batch.sf_replicated) and not force_general
         dense = batch.dense_small_bins() and not os.environ.get("P265_KB_NO_DENSE")
+        zext = bool((batch.tus["rsvd"] >> 11).any())
 
         def run():
             eng.residual_dev(d_tus.data_ptr(), bins, d_co.data_ptr(), d_sf.data_ptr() if d_sf is not None else None,
                              batch.geom, d_out.data_ptr(), zero_fill=False, sf_replicated=rep, dense_arena=dense,
-                             zero_extents=bool((batch.tus["rsvd"] >> 11).any()))
+                             zero_extents=zext)
         for _ in range(3):
             run()
         torch.cuda.synchronize()
