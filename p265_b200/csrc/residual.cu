@@ -17,26 +17,43 @@
 
 namespace p265 {
 
-// Occupancy plan (per SM), 4 warps per CTA (one per scheduler; measured -1.8 % on the 32x32 bin
-// and -4 % on the 8x8 bin against 2-warp CTAs at the same warp counts):
-//   32x32  4 CTAs = 16 warps, 128 registers (lock-step two-column pass), 8.4 KB smem per warp
-//   16x16  8 CTAs = 32 warps,  64 registers
-//   8x8    6 CTAs = 24 warps,  80 registers
-//   4x4    8 CTAs = 32 warps,  64 registers
+// Occupancy plan (per SM) and CTA shape per bin.  The warps of a bin never talk to each other, so the CTA is
+// only a scheduling container -- but its shape matters at the seams between the bin kernels (programmatic
+// dependent launch: CTAs of the next bin start in the slots this bin frees) and for the order in which an SM
+// walks the item list (the warps of a CTA take consecutive items).  Measured on B200 (round 2,
+// profiles/r2_cta_shapes.txt): alone, the 32x32 bin is 6.6 % faster as ONE 16-warp CTA per SM and the 16x16
+// bin 3.8 % faster as one 32-warp CTA; in the chain of bins the best of 20 combinations is
+//   32x32  2 CTAs x  8 warps = 16 warps, 128 registers (lock-step two-column pass), 8.4 KB smem per warp
+//   16x16  2 CTAs x 16 warps = 32 warps,  64 registers
+//   8x8   12 CTAs x  2 warps = 24 warps,  80 registers (slower alone than 6 x 4, faster in the chain: small CTAs
+//                                         slip into the slots the draining 16x16 CTAs free)
+//   4x4    2 CTAs x 16 warps = 32 warps,  64 registers
+// = 0.2255 -> 0.2217 ms per 16 pictures against the round-1 shape (4 warps per CTA everywhere).
 #ifndef P265_WARPS_PER_CTA
 #define P265_WARPS_PER_CTA 4
 #endif
 #ifndef P265_CTAS_PER_SM
-#define P265_CTAS_PER_SM 6
+#define P265_CTAS_PER_SM 12   // 8x8 bin
 #endif
 #ifndef P265_CTAS_BIN0
-#define P265_CTAS_BIN0 4
+#define P265_CTAS_BIN0 2
+#endif
+#ifndef P265_WARPS_BIN0
+#define P265_WARPS_BIN0 8
+#endif
+#ifndef P265_WARPS_BIN1
+#define P265_WARPS_BIN1 16
+#endif
+#ifndef P265_WARPS_BIN2
+#define P265_WARPS_BIN2 2
+#endif
+#ifndef P265_WARPS_BIN3
+#define P265_WARPS_BIN3 16
 #endif
 constexpr int kWarpsPerCta = P265_WARPS_PER_CTA;
 constexpr int kCtasPerSm = P265_CTAS_PER_SM;
 constexpr int kDescRingBytes = 2 * 32 * 16;                          // 2 slots x 32 lanes x 16 B
 constexpr int kWarpBytes = 2 * kWarpSmemBytes + kDescRingBytes;      // in + g + ring = 9472
-constexpr int kCtaSmemBytes = kWarpsPerCta * kWarpBytes;
 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int KEEP>
@@ -610,27 +627,29 @@ __device__ __forceinline__ void stream_bin8(const KernelArgs &a, int item, int l
 // 5.25 KB per warp and fits 64 registers; 8x8 keeps 64 packed words live per lane; 4x4 is
 // register-only.
 #ifndef P265_CTAS_BIN1
-#define P265_CTAS_BIN1 8
+#define P265_CTAS_BIN1 2
 #endif
 #ifndef P265_CTAS_BIN3
-#define P265_CTAS_BIN3 8
+#define P265_CTAS_BIN3 2
 #endif
 constexpr int kSfcBytes = 640;  // compact ScalingFactor copy at the start of a CTA's shared memory (7 x 80 B)
 template <int BIN>
 struct BinCfg {
     static constexpr int ctas = BIN == 0 ? P265_CTAS_BIN0 : (BIN == 1 ? P265_CTAS_BIN1 : (BIN == 3 ? P265_CTAS_BIN3 : kCtasPerSm));
+    // warps per CTA (P265_WARPS_BIN0..3 override P265_WARPS_PER_CTA per bin; ctas x warps = resident warps per SM)
+    static constexpr int warps = BIN == 0 ? P265_WARPS_BIN0 : (BIN == 1 ? P265_WARPS_BIN1 : (BIN == 2 ? P265_WARPS_BIN2 : P265_WARPS_BIN3));
     // per warp: tile + g buffers + descriptor ring (2 slots x TBs per item x 16 B for the big sizes)
     static constexpr int smem =
-        BIN == 3 ? kSfcBytes + (SmallStream<3>::on ? 0 : kWarpsPerCta * kBin4WarpBytes)
-        : BIN == 0 ? kSfcBytes + kWarpsPerCta * (2 * Layout<5>::WARP_BYTES + 3 * Layout<5>::TBS * 16 + 32)
-        : BIN == 1 ? kSfcBytes + kWarpsPerCta * (2 * Layout<4>::WARP_BYTES + 3 * Layout<4>::TBS * 16)
-                   : kSfcBytes + (SmallStream<2>::on ? kWarpsPerCta * kWarpSmemBytes : kCtaSmemBytes);
+        BIN == 3 ? kSfcBytes + (SmallStream<3>::on ? 0 : P265_WARPS_BIN3 * kBin4WarpBytes)
+        : BIN == 0 ? kSfcBytes + P265_WARPS_BIN0 * (2 * Layout<5>::WARP_BYTES + 3 * Layout<5>::TBS * 16 + 32)
+        : BIN == 1 ? kSfcBytes + P265_WARPS_BIN1 * (2 * Layout<4>::WARP_BYTES + 3 * Layout<4>::TBS * 16)
+                   : kSfcBytes + P265_WARPS_BIN2 * (SmallStream<2>::on ? kWarpSmemBytes : kWarpBytes);
     // with zero-extent codes (run_bin_zext): a second tile buffer per warp of the big bins, behind the ring
     static constexpr int zext_extra = BIN == 0 ? Layout<5>::WARP_BYTES : (BIN == 1 ? Layout<4>::WARP_BYTES : 0);
 };
 
 template <int BIN, int SF>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, BinCfg<BIN>::ctas) residual_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(BinCfg<BIN>::warps * 32, BinCfg<BIN>::ctas) residual_kernel(const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     // The four bin kernels are independent (disjoint TBs): let the next one be scheduled
     // as soon as CTAs of this one retire (programmatic dependent launch) so the tail of a
@@ -641,9 +660,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, BinCfg<BIN>::ctas) residual
     if (a.wait_prev) asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int stride = gridDim.x * kWarpsPerCta;
-    const int gw = blockIdx.x * kWarpsPerCta + warp;
-    constexpr int warp_bytes0 = (BinCfg<BIN>::smem - kSfcBytes) / kWarpsPerCta;
+    constexpr int kWarps = BinCfg<BIN>::warps;
+    const int stride = gridDim.x * kWarps;
+    const int gw = blockIdx.x * kWarps + warp;
+    constexpr int warp_bytes0 = (BinCfg<BIN>::smem - kSfcBytes) / kWarps;
     const bool zext = P265_ZERO_EXTENT && BIN <= 1 && a.zext;
     const int warp_bytes = warp_bytes0 + (zext ? BinCfg<BIN>::zext_extra : 0);
     unsigned char *wbase = smem + kSfcBytes + warp * warp_bytes;
@@ -821,7 +841,8 @@ static int launch_bin(p265_ctx *ctx, KernelArgs a, bool first, cudaStream_t stre
     const int items = a.first_item[BIN + 1] - a.first_item[BIN];
     if (items == 0) return P265_OK;
     const bool zext = P265_ZERO_EXTENT && BIN <= 1 && a.zext;
-    const int smem = BinCfg<BIN>::smem + (zext ? kWarpsPerCta * BinCfg<BIN>::zext_extra : 0);
+    constexpr int kWarps = BinCfg<BIN>::warps;
+    const int smem = BinCfg<BIN>::smem + (zext ? kWarps * BinCfg<BIN>::zext_extra : 0);
     // CTAs per SM the kernel really gets; function attributes are per device, so the
     // carve-out hint is set once for every device this process uses
     static int occ_dev[2][64] = {{0}};
@@ -831,29 +852,37 @@ static int launch_bin(p265_ctx *ctx, KernelArgs a, bool first, cudaStream_t stre
         P265_CUDA(cudaFuncSetAttribute(residual_kernel<BIN, SF>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        cudaSharedmemCarveoutMaxShared));
         P265_CUDA(cudaFuncSetAttribute(residual_kernel<BIN, SF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       BinCfg<BIN>::smem + kWarpsPerCta * BinCfg<BIN>::zext_extra));
-        P265_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, residual_kernel<BIN, SF>, kWarpsPerCta * 32,
+                                       BinCfg<BIN>::smem + kWarps * BinCfg<BIN>::zext_extra));
+        P265_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, residual_kernel<BIN, SF>, kWarps * 32,
                                                                 smem));
         occ = o < 1 ? 1 : o;
     }
     // persistent grid, trimmed so that every warp gets the same number of items
-    static int pct = -1;  // tuning knob: P265_GRID_PCT limits the resident CTAs (kernels sharing the SMs)
+    // tuning knobs: P265_GRID_PCT (all bins) / P265_GRID_PCT_BINS="a,b,c,d" (per bin 32,16,8,4): size of the
+    // persistent grid in per cent of the CTAs that are resident at once.  < 100: kernels sharing the SMs;
+    // > 100: a short second wave, so that the CTAs of the NEXT bin (programmatic dependent launch) start one by
+    // one in the slots the first wave frees instead of all at once when an equal-work single wave ends
+    static int pct = -1, pct_bin[4] = {0, 0, 0, 0};
     if (pct < 0) {
         const char *e = getenv("P265_GRID_PCT");
         pct = e ? atoi(e) : 100;
-        if (pct < 1 || pct > 100) pct = 100;
+        if (pct < 1 || pct > 400) pct = 100;
+        const char *b = getenv("P265_GRID_PCT_BINS");
+        int v[4];
+        if (b && sscanf(b, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) == 4)
+            for (int i = 0; i < 4; i++) pct_bin[i] = (v[i] >= 1 && v[i] <= 400) ? v[i] : 0;
     }
-    const int pct_use = pct_limit > 0 ? pct_limit : pct;
+    const int pct_use = pct_limit > 0 ? pct_limit : (pct_bin[BIN] ? pct_bin[BIN] : pct);
     // CTAs over the whole device (not per SM): a 70 % grid of a 4-CTA kernel is 2.8 CTAs per SM on average
     int max_ctas = (int)((int64_t)ctx->sm_count * occ * pct_use / 100);
     if (max_ctas < 1) max_ctas = 1;
-    const int max_warps = max_ctas * kWarpsPerCta;
+    const int max_warps = max_ctas * kWarps;
     const int rounds = (items + max_warps - 1) / max_warps;
     const int warps = SmallStream<BIN>::on ? items : (items + rounds - 1) / rounds;  // streaming bins: one warp per item
-    const int grid = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int grid = (warps + kWarps - 1) / kWarps;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kWarpsPerCta * 32);
+    cfg.blockDim = dim3(kWarps * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream ? stream : ctx->stream;
     cudaLaunchAttribute attr[1];

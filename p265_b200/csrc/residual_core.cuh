@@ -488,7 +488,7 @@ P265_HD uint4 expand_desc(const KernelArgs &a, const uint4 d) {
     // extents only mean something where a transform runs: a bypass TB's "coefficients" are residual samples and
     // the element-wise path reads all of them -- such a TB promises nothing (and with it its work item)
     // (likewise a TB with the rare left-shift dequantisation: its item runs the one full-extent copy of that pass)
-    const bool elementwise = (t.flags & (P265_TU_SKIP | P265_TU_BYPASS)) != 0 || t.lsh != 0;
+    const bool elementwise = !a.zext || (t.flags & (P265_TU_SKIP | P265_TU_BYPASS)) != 0 || t.lsh != 0;
     const uint32_t zr = elementwise ? 0u : (uint32_t)desc_zr(d), zc = elementwise ? 0u : (uint32_t)desc_zc(d);
     return make_uint4(dst_off, flags | ((uint32_t)mid << 8) | ((uint32_t)t.sh2 << 11) | ((uint32_t)(t.stride >> 3) << 15),
                       d.z, (uint32_t)t.w | ((uint32_t)t.sh << 16) | (zr << 21) | ((uint32_t)t.lsh << 24) | (zc << 28));
