@@ -27,8 +27,9 @@ namespace p265 {
 //   16x16  2 CTAs x 16 warps = 32 warps,  64 registers
 //   8x8   12 CTAs x  2 warps = 24 warps,  80 registers (slower alone than 6 x 4, faster in the chain: small CTAs
 //                                         slip into the slots the draining 16x16 CTAs free)
-//   4x4    2 CTAs x 16 warps = 32 warps,  64 registers
-// = 0.2255 -> 0.2217 ms per 16 pictures against the round-1 shape (4 warps per CTA everywhere).
+//   4x4   16 CTAs x  2 warps = 32 warps,  64 registers (config 3 indifferent, BASELINE config 2 -1.7 %)
+// = 0.2255 -> 0.2220 ms per 16 4K pictures (config 3) and 0.2533 -> 0.2492 ms per 64 1080p pictures (config 2)
+// against the round-1 shape (4 warps per CTA everywhere).
 #ifndef P265_WARPS_PER_CTA
 #define P265_WARPS_PER_CTA 4
 #endif
@@ -48,7 +49,7 @@ namespace p265 {
 #define P265_WARPS_BIN2 2
 #endif
 #ifndef P265_WARPS_BIN3
-#define P265_WARPS_BIN3 16
+#define P265_WARPS_BIN3 2
 #endif
 constexpr int kWarpsPerCta = P265_WARPS_PER_CTA;
 constexpr int kCtasPerSm = P265_CTAS_PER_SM;
@@ -630,7 +631,7 @@ __device__ __forceinline__ void stream_bin8(const KernelArgs &a, int item, int l
 #define P265_CTAS_BIN1 2
 #endif
 #ifndef P265_CTAS_BIN3
-#define P265_CTAS_BIN3 2
+#define P265_CTAS_BIN3 16
 #endif
 constexpr int kSfcBytes = 640;  // compact ScalingFactor copy at the start of a CTA's shared memory (7 x 80 B)
 template <int BIN>

@@ -66,6 +66,14 @@ def main():
 
     if want("residual"):
         bench_residual(args, time_residual)
+    if "config2" in only:   # BASELINE config 2: 1080p 8-bit intra mix, flat lists (4x as many pictures: same working set)
+        c2 = synth.residual_batch("1080p8", n_pics=4 * args.pics, n_unique=2).densified()
+        time_residual(c2, "1080p8 mix, flat lists")
+        if not os.environ.get("P265_KB_MIX_ONLY"):
+            for l2 in (5, 4, 3, 2):
+                sel = c2.tus[c2.tus["log2n"] == l2]
+                time_residual(ResidualBatch(c2.geom, np.ascontiguousarray(sel), c2.coeffs, None, covers_all=True),
+                              "1080p8 only %2dx%-2d (%7d TBs)" % (1 << l2, 1 << l2, len(sel)))
     if want("lowfreq"):
         bench_lowfreq(args, time_residual)
     if "zprof" in only:   # ncu target: the 32x32 / 16x16 bins without codes and with every TB promising the first quarter
