@@ -51,7 +51,6 @@ namespace p265 {
 #ifndef P265_WARPS_BIN3
 #define P265_WARPS_BIN3 2
 #endif
-constexpr int kWarpsPerCta = P265_WARPS_PER_CTA;
 constexpr int kCtasPerSm = P265_CTAS_PER_SM;
 constexpr int kDescRingBytes = 2 * 32 * 16;                          // 2 slots x 32 lanes x 16 B
 constexpr int kWarpBytes = 2 * kWarpSmemBytes + kDescRingBytes;      // in + g + ring = 9472
