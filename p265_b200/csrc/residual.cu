@@ -27,9 +27,10 @@ namespace p265 {
 //   16x16  2 CTAs x 16 warps = 32 warps,  64 registers
 //   8x8   12 CTAs x  2 warps = 24 warps,  80 registers (slower alone than 6 x 4, faster in the chain: small CTAs
 //                                         slip into the slots the draining 16x16 CTAs free)
-//   4x4   16 CTAs x  2 warps = 32 warps,  64 registers (config 3 indifferent, BASELINE config 2 -1.7 %)
-// = 0.2255 -> 0.2220 ms per 16 4K pictures (config 3) and 0.2533 -> 0.2492 ms per 64 1080p pictures (config 2)
-// against the round-1 shape (4 warps per CTA everywhere).
+//   4x4    2 CTAs x 16 warps = 32 warps,  64 registers (16 x 2 warps: the same on config 3, BASELINE config 2 -1.7 %
+//                                         at 64 pictures per launch but +2 % at the benchmark's 32)
+// = 0.2246 -> 0.2193 ms per 16 4K pictures (config 3; with the launch order below 0.2255 -> 0.2193) against the
+// round-1 shape (4 warps per CTA everywhere); config 2 unchanged (0.1186 ms per 32 1080p pictures).
 #ifndef P265_WARPS_PER_CTA
 #define P265_WARPS_PER_CTA 4
 #endif
@@ -49,7 +50,7 @@ namespace p265 {
 #define P265_WARPS_BIN2 2
 #endif
 #ifndef P265_WARPS_BIN3
-#define P265_WARPS_BIN3 2
+#define P265_WARPS_BIN3 16
 #endif
 constexpr int kCtasPerSm = P265_CTAS_PER_SM;
 constexpr int kDescRingBytes = 2 * 32 * 16;                          // 2 slots x 32 lanes x 16 B
@@ -630,7 +631,7 @@ __device__ __forceinline__ void stream_bin8(const KernelArgs &a, int item, int l
 #define P265_CTAS_BIN1 2
 #endif
 #ifndef P265_CTAS_BIN3
-#define P265_CTAS_BIN3 16
+#define P265_CTAS_BIN3 2
 #endif
 constexpr int kSfcBytes = 640;  // compact ScalingFactor copy at the start of a CTA's shared memory (7 x 80 B)
 template <int BIN>
@@ -900,16 +901,36 @@ static int launch_residual_sf(p265_ctx *ctx, const KernelArgs &a) {
     // the first kernel of the batch is ordered normally behind whatever precedes it on the
     // stream (zero fill, copies); the following bins may overlap their predecessor
     // the bins are independent, so their launch order is free (tuning knob P265_BIN_ORDER, e.g. "0312")
-    static int order[4] = {-1, 0, 0, 0};
-    if (order[0] < 0) {
+    // Default: the bin with the least work first, the others by size (32, 16, 8, 4).  Measured on B200 with the
+    // round-2 CTA shapes, 20 of the 24 orders (profiles/r2_cta_shapes.txt): the 4K 10-bit mix,
+    // whose lightest bin is 4x4, runs 1.3 % faster as 4,32,16,8 (1.7 % on the benchmark's residual + SAO step) and
+    // 9 % SLOWER with the 1080p 8-bit mix, whose lightest bin is 32x32 and whose best orders start with it.
+    // Work per TB in ns (per-bin times of both mixes alone): 1.2 / 0.28 / 0.095 / 0.035.
+    static int env_order[4] = {-1, 0, 0, 0};
+    if (env_order[0] < 0) {
         const char *e = getenv("P265_BIN_ORDER");
-        int o[4] = {0, 1, 2, 3};
+        int o[4] = {4, 4, 4, 4};   // 4 = not given
         if (e && strlen(e) == 4) {
             int seen = 0;
             for (int i = 0; i < 4; i++) { o[i] = e[i] - '0'; if (o[i] >= 0 && o[i] < 4) seen |= 1 << o[i]; }
-            if (seen != 15) { o[0] = 0; o[1] = 1; o[2] = 2; o[3] = 3; }
+            if (seen != 15) o[0] = o[1] = o[2] = o[3] = 4;
         }
-        order[1] = o[1]; order[2] = o[2]; order[3] = o[3]; order[0] = o[0];
+        env_order[1] = o[1]; env_order[2] = o[2]; env_order[3] = o[3]; env_order[0] = o[0];
+    }
+    int order[4] = {env_order[0], env_order[1], env_order[2], env_order[3]};
+    if (order[0] > 3) {
+        const double ns_per_tb[4] = {1.2, 0.28, 0.095, 0.035};
+        int first = -1;
+        double least = 0;
+        for (int b = 0; b < 4; b++) {
+            if (!a.n_tb[b]) continue;
+            const double w = ns_per_tb[b] * a.n_tb[b];
+            if (first < 0 || w < least) { first = b; least = w; }
+        }
+        if (first < 0) first = 0;
+        int n = 0;
+        order[n++] = first;
+        for (int b = 0; b < 4; b++) if (b != first) order[n++] = b;
     }
     int rc = P265_OK;
     // Two chains sharing the SMs (tuning knob P265_SPLIT, e.g. "03|12": bins 32x32 + 4x4 on the context's
