@@ -22,20 +22,20 @@ namespace p265 {
 // dependent launch: CTAs of the next bin start in the slots this bin frees) and for the order in which an SM
 // walks the item list (the warps of a CTA take consecutive items).  Measured on B200 (round 2,
 // profiles/r2_cta_shapes.txt): alone, the 32x32 bin is 6.6 % faster as ONE 16-warp CTA per SM and the 16x16
-// bin 3.8 % faster as one 32-warp CTA; in the chain of bins the best of 20 combinations is
+// bin 3.8 % faster as one 32-warp CTA, but a single large CTA holds its slots until its last warp is done and
+// the next bin starts late; in the chain of bins, with the launch order of launch_residual_sf, the best of
+// some 40 combinations over three sweeps is
 //   32x32  2 CTAs x  8 warps = 16 warps, 128 registers (lock-step two-column pass), 8.4 KB smem per warp
-//   16x16  2 CTAs x 16 warps = 32 warps,  64 registers
-//   8x8   12 CTAs x  2 warps = 24 warps,  80 registers (slower alone than 6 x 4, faster in the chain: small CTAs
-//                                         slip into the slots the draining 16x16 CTAs free)
-//   4x4    2 CTAs x 16 warps = 32 warps,  64 registers (16 x 2 warps: the same on config 3, BASELINE config 2 -1.7 %
-//                                         at 64 pictures per launch but +2 % at the benchmark's 32)
-// = 0.2246 -> 0.2193 ms per 16 4K pictures (config 3; with the launch order below 0.2255 -> 0.2193) against the
-// round-1 shape (4 warps per CTA everywhere); config 2 unchanged (0.1186 ms per 32 1080p pictures).
+//   16x16  4 CTAs x  8 warps = 32 warps,  64 registers
+//   8x8    3 CTAs x  8 warps = 24 warps,  80 registers
+//   4x4    2 CTAs x 16 warps = 32 warps,  64 registers
+// = 0.2246 -> 0.2172 ms per 16 4K pictures (config 3) against the round-1 shape (4 warps per CTA everywhere,
+// bins launched by size); config 2 0.1186 -> 0.1193 ms per 32 1080p pictures (unchanged within the noise).
 #ifndef P265_WARPS_PER_CTA
 #define P265_WARPS_PER_CTA 4
 #endif
 #ifndef P265_CTAS_PER_SM
-#define P265_CTAS_PER_SM 12   // 8x8 bin
+#define P265_CTAS_PER_SM 3   // 8x8 bin
 #endif
 #ifndef P265_CTAS_BIN0
 #define P265_CTAS_BIN0 2
@@ -44,10 +44,10 @@ namespace p265 {
 #define P265_WARPS_BIN0 8
 #endif
 #ifndef P265_WARPS_BIN1
-#define P265_WARPS_BIN1 16
+#define P265_WARPS_BIN1 8
 #endif
 #ifndef P265_WARPS_BIN2
-#define P265_WARPS_BIN2 2
+#define P265_WARPS_BIN2 8
 #endif
 #ifndef P265_WARPS_BIN3
 #define P265_WARPS_BIN3 16
@@ -628,7 +628,7 @@ __device__ __forceinline__ void stream_bin8(const KernelArgs &a, int item, int l
 // 5.25 KB per warp and fits 64 registers; 8x8 keeps 64 packed words live per lane; 4x4 is
 // register-only.
 #ifndef P265_CTAS_BIN1
-#define P265_CTAS_BIN1 2
+#define P265_CTAS_BIN1 4
 #endif
 #ifndef P265_CTAS_BIN3
 #define P265_CTAS_BIN3 2
