@@ -97,7 +97,7 @@ def decode(data: bytes, skip_loop_filter: bool):
         while avcodec.avcodec_receive_frame(ctx, frm) >= 0:
             h = _FrameHead.from_address(frm)
             name = avutil.av_get_pix_fmt_name(h.format).decode()
-            if name not in ("yuv420p", "yuv420p10le", "yuv420p12le"):
+            if name not in ("yuv420p", "yuv420p9le", "yuv420p10le", "yuv420p12le"):
                 raise RuntimeError("unexpected pixel format %s" % name)
             dt = np.uint8 if name == "yuv420p" else np.dtype("<u2")
             planes = []

@@ -503,6 +503,9 @@ STREAMS = [
                                           dense=True, seed=18, qps=(26, 34, 41), tc_offset_div2=2)),
     ("main10_tiles_3x2_lf_across", dict(tiles=(3, 2), lf_across_tiles=1, slices=6, ctb_log2=4, width=96, height=64,
                                         bit_depth=10, profile=2, dense=False, seed=19, qps=(24, 36), pictures=1)),
+    # 9 bit (round 2): the odd depth libavcodec can decode (9-bit packed arithmetic of deblocking and SAO, bdShift 11 / 6)
+    ("rext9_sparse_ctb32", dict(bit_depth=9, profile=4, ctb_log2=5, dense=False, seed=21, qps=(20, 31, 42), width=96,
+                                height=64, cb_qp_offset=-2, cr_qp_offset=3, beta_offset_div2=1, tc_offset_div2=-1)),
 ]
 BASE = dict(width=128, height=96, bit_depth=8, profile=1, ctb_log2=6, tu_depth=2, scaling_lists="off",
             strong_smoothing=1, sdh=1, transform_skip=1, bypass=0, cb_qp_offset=0, cr_qp_offset=0,

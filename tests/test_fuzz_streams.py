@@ -24,7 +24,7 @@ def test_oracle_chain_equals_libavcodec(name, cfg, c_oracle):
 
 def test_the_streams_cover_what_sanity_bin_does_not():
     m = fz.manifest()
-    assert {c["bit_depth"] for c in m.values()} == {8, 10, 12}
+    assert {c["bit_depth"] for c in m.values()} == {8, 9, 10, 12}
     assert {c["ctb_log2"] for c in m.values()} == {4, 5, 6}
     assert {c["scaling_lists"] for c in m.values()} == {"off", "default", "pps"}
     assert any(c["bypass"] for c in m.values()) and any(c["slices"] > 1 for c in m.values())
