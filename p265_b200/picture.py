@@ -230,7 +230,16 @@ def size_kind_order(tus: np.ndarray, geom=None) -> np.ndarray:
         left_shift = (tus["qp"].astype(np.int32) // 6 >= bd + tus["log2n"].astype(np.int32) - 5) & \
             ((tus["flags"] & (TU_PRESCALED | TU_BYPASS)) == 0)
         key = key + left_shift.astype(np.int32)
-    order = np.argsort(key, kind="stable")
+    # Inside a cluster: big TBs stay in decoding order (a work item = 2 / 4 neighbours of one quadrant); the 8x8 and
+    # 4x4 TBs go in RASTER order of their plane (picture, component, y, x).  A work item of the small bins is 32 TBs,
+    # one per lane, and every store instruction writes one row of each: in decoding (z-scan) order those 32 rows lie
+    # in 8-16 different plane rows, in raster order they are pieces of the same few rows -- fewer, longer runs for
+    # the L2 to merge and for DRAM to write.  Measured on B200 (round 2, profiles/r2_small_bins.txt): BASELINE
+    # config 2 -3.7 % (8x8 bin -6.7 %, 4x4 bin -5.8 %), config 3 -0.9 %; the 16x16 bin does not care.
+    small = tus["log2n"] <= 3
+    pos = (((tus["pic"].astype(np.int64) << 2) | tus["c_idx"].astype(np.int64)) << 32) | \
+        (tus["y"].astype(np.int64) << 16) | tus["x"].astype(np.int64)
+    order = np.lexsort((np.where(small, pos, np.arange(len(tus), dtype=np.int64)), key))
     # Second level, only when descriptors carry zero-extent codes: whole WORK ITEMS of the big bins (2
     # consecutive 32x32 TBs, 4 consecutive 16x16 TBs, counted from the start of the bin -- P265_ITEM_TBS in the
     # header) are ordered by the item's code pair, the weakest promise among its TBs.  Measured on B200 (round

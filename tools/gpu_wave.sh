@@ -1,16 +1,9 @@
 #!/bin/bash
-# Persistent grid size per bin (P265_GRID_PCT_BINS, per cent of the resident capacity; bins 32,16,8,4) under the
-# least-work-first launch order
-TAG=${1:-wave2}
+# Diagnostic: small-bin TBs in raster order inside a plane (P265_KB_RASTER=1) against decoding order
+TAG=${1:-raster}
 OUT=gpurun_out; mkdir -p $OUT
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-run() { echo "== $1" | tee -a $OUT/kbench_$TAG.log; env $1 P265_KB_MIX_ONLY=1 python tools/kbench.py --pics 16 --reps 30 --only residual --quick 2>&1 | tee -a $OUT/kbench_$TAG.log; }
-run A=1
-run P265_GRID_PCT_BINS=100,100,100,50
-run P265_GRID_PCT_BINS=100,100,100,75
-run P265_GRID_PCT_BINS=100,100,100,90
-run P265_GRID_PCT_BINS=90,100,100,100
-run P265_GRID_PCT_BINS=100,90,100,100
-run P265_GRID_PCT_BINS=100,100,90,100
-run P265_GRID_PCT_BINS=95,95,95,95
-run A=2
+for rep in 1 2; do for r in 1 2; do
+  echo "== raster=$r" | tee -a $OUT/kbench_${TAG}b.log
+  P265_KB_RASTER=$r python tools/kbench.py --pics 16 --reps 30 --only residual --quick 2>&1 | tee -a $OUT/kbench_${TAG}b.log
+  P265_KB_RASTER=$r python tools/kbench.py --pics 8 --reps 30 --only config2 2>&1 | tee -a $OUT/kbench_${TAG}b.log
+done; done

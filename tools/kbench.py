@@ -67,7 +67,10 @@ def main():
     if want("residual"):
         bench_residual(args, time_residual)
     if "config2" in only:   # BASELINE config 2: 1080p 8-bit intra mix, flat lists (4x as many pictures: same working set)
-        c2 = synth.residual_batch("1080p8", n_pics=4 * args.pics, n_unique=2).densified()
+        c2 = synth.residual_batch("1080p8", n_pics=4 * args.pics, n_unique=2)
+        if os.environ.get("P265_KB_RASTER"):
+            c2 = raster_small_bins(c2)
+        c2 = c2.densified()
         time_residual(c2, "1080p8 mix, flat lists")
         if not os.environ.get("P265_KB_MIX_ONLY"):
             for l2 in (5, 4, 3, 2):
@@ -171,8 +174,22 @@ def bench_overlap(args, eng, dev, stream, to_dev):
             print("overlap residual || SAO (%s, sao prio %d)   %8.4f ms per pair" % (order, prio, ms), flush=True)
 
 
+def raster_small_bins(batch):
+    """Diagnostic (P265_KB_RASTER=1): the 8x8 / 4x4 TBs of a batch re-ordered by (picture, plane, y, x) -- raster order
+    inside a plane instead of decoding order -- so that the 32 TBs of a work item lie side by side in a few plane rows."""
+    t = batch.tus
+    lim = 5 if os.environ.get("P265_KB_RASTER") == "2" else 4      # "2": the 16x16 bin as well
+    key = np.where(t["log2n"] >= lim, 0, 1).astype(np.int64)
+    sub = ((t["pic"].astype(np.int64) * 4 + t["c_idx"]) << 32) | (t["y"].astype(np.int64) << 16) | t["x"].astype(np.int64)
+    order = np.lexsort((np.where(key == 1, sub, np.arange(len(t))), (t["flags"] & 7).astype(np.int64) * key, -t["log2n"].astype(np.int64)))
+    return ResidualBatch(batch.geom, np.ascontiguousarray(t[order]), batch.coeffs, batch.scaling_factor, batch.covers_all,
+                         batch.sf_replicated)
+
+
 def bench_residual(args, time_residual):
     full = synth.residual_batch("4k10", n_pics=args.pics, n_unique=min(2, args.pics))
+    if os.environ.get("P265_KB_RASTER"):
+        full = raster_small_bins(full)
     if not os.environ.get("P265_KB_NO_DENSE"):
         full = full.densified()   # arena in descriptor order: P265_RES_DENSE_ARENA applies
     time_residual(full, "4k10 mix, SF replicated")
