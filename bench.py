@@ -350,7 +350,8 @@ def run_gpu(args):
         del t_pix, t_work, t_res
         # BASELINE config 2: residual of the synthetic 1080p 8-bit intra mix, flat lists,
         # DST 4x4 -- outside the metric; 4x as many pictures as the 4K batch (same working set, > L2)
-        c2 = synth.residual_batch("1080p8", n_pics=4 * n_o, n_unique=2)
+        # (arena in descriptor order, like the main workload: the layout unpack_kernel and a sorting packer produce)
+        c2 = synth.residual_batch("1080p8", n_pics=4 * n_o, n_unique=2).densified()
         c_tus, c_co = to_dev(c2.tus), to_dev(c2.coeffs)
         c_out = torch.empty(c2.geom.total_elems() * 2, dtype=torch.uint8, device=dev)
         c_bins = c2.bin_counts()
