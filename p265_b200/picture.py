@@ -215,16 +215,26 @@ def set_extents(tus: np.ndarray, zr: np.ndarray, zc: np.ndarray) -> None:
 
 
 def size_kind_order(tus: np.ndarray, geom=None) -> np.ndarray:
-    """Permutation that sorts descriptors largest TBs first -- the order `p265_residual_*`
-    requires -- and, inside a size, clusters TBs that take the same path through the kernels so
-    that a warp's 32 lanes (32 small TBs) agree: the kinds (normal, DST, transform-skip, bypass)
-    and, when the bit depths are known (`geom`), whether the TB's dequantisation is the
-    left-shift form of 8.6.3 (qP / 6 >= bdShift: `clip16(level * m) << n` instead of
-    `(level * m + round) >> n`) -- the kernels pick that slower form per warp, and unsorted almost
-    every warp of the 8x8 / 4x4 bins holds one such TB.  Stable otherwise (picture / decoding order
-    kept).  The one ordering rule of the packed format: the packer, the parser-side emitter and the
-    synthetic workloads share it; any order inside a size is CORRECT, this one is fast."""
-    key = (-(tus["log2n"].astype(np.int32)) * 32 + (tus["flags"] & (TU_DST | TU_SKIP | TU_BYPASS)).astype(np.int32) * 2)
+    """Permutation that sorts descriptors largest TBs first -- the order `p265_residual_*` requires -- and,
+    inside a size, arranges TBs for the kernels.  The one ordering rule of the packed format: the packer, the
+    parser-side emitter and the synthetic workloads share it; any order inside a size is CORRECT, this one is
+    fast.  Inside a size:
+      * kinds (normal, DST, transform-skip, bypass) are clustered so that a warp's 32 lanes (32 small TBs) agree
+        (transform-skip only while rare, see below);
+      * 16x16 / 32x32 TBs: when the bit depths are known (`geom`), TBs whose dequantisation is the left-shift form
+        of 8.6.3 (qP / 6 >= bdShift) are clustered as well (the kernels pick that slower form per work item);
+        otherwise the order they came in (decoding order: the 2 / 4 TBs of a work item are neighbours), whole
+        work items ordered by zero-extent code pair when descriptors carry codes;
+      * 8x8 / 4x4 TBs: raster order of their plane (picture, component, y, x)."""
+    # Transform-skip TBs (4x4 only) get their own cluster only while they are rare: pulled out of the list they
+    # break the raster runs of the 4x4 bin (below), left in they make the warps that hold one run both paths.
+    # Measured on B200 (round 2): 10 % of the 4x4 TBs (config 3) -> unclustered, the 4x4 bin 12 % faster and the
+    # chain 3.6 %; 1 % (config 2) -> clustered, 1.2 % faster than unclustered.
+    kinds = TU_DST | TU_SKIP | TU_BYPASS
+    n4 = int((tus["log2n"] == 2).sum())
+    if n4 and int(((tus["flags"] & TU_SKIP) != 0).sum()) > 0.03 * n4:
+        kinds = TU_DST | TU_BYPASS
+    key = (-(tus["log2n"].astype(np.int32)) * 32 + (tus["flags"] & kinds).astype(np.int32) * 2)
     if geom is not None:
         bd = np.where(tus["c_idx"] == 0, geom.bit_depth_y, geom.bit_depth_c).astype(np.int32)
         left_shift = (tus["qp"].astype(np.int32) // 6 >= bd + tus["log2n"].astype(np.int32) - 5) & \

@@ -8,9 +8,15 @@ from p265_b200.picture import TU_BYPASS, TU_DESC, TU_DST, TU_SKIP, PicGeom, size
 from conftest import small_cfg
 
 
-def test_sizes_kinds_and_raster_order_of_small_tbs():
+import pytest
+
+
+@pytest.mark.parametrize("skip_share", [0.25, 0.02])
+def test_sizes_kinds_and_raster_order_of_small_tbs(skip_share):
+    """Transform-skip TBs are a cluster of their own only while they are rare (<= 3 % of the 4x4 TBs): pulled out
+    of the list they break the raster runs, left in they make their warps run both paths."""
     rng = np.random.default_rng(1)
-    n = 400
+    n = 4000
     t = np.zeros(n, TU_DESC)
     t["log2n"] = rng.integers(2, 6, n)
     t["c_idx"] = rng.integers(0, 3, n)
@@ -18,14 +24,17 @@ def test_sizes_kinds_and_raster_order_of_small_tbs():
     t["x"] = rng.integers(0, 64, n) * 8
     t["y"] = rng.integers(0, 32, n) * 8
     t["qp"] = 30
-    t["flags"] = np.where(t["log2n"] == 2, rng.choice([0, TU_DST, TU_SKIP, TU_BYPASS], n), rng.choice([0, TU_BYPASS], n))
+    rest = (1 - skip_share) / 3
+    t["flags"] = np.where(t["log2n"] == 2, rng.choice([0, TU_DST, TU_SKIP, TU_BYPASS], n, p=[rest, rest, skip_share, rest]),
+                          rng.choice([0, TU_BYPASS], n))
+    clustered = TU_DST | TU_BYPASS | (TU_SKIP if skip_share < 0.03 else 0)
     t["coeff_off"] = np.arange(n)                     # identity tag
     out = sort_by_size(t, PicGeom(512, 256, 3, 8, 8))
     assert sorted(out["coeff_off"].tolist()) == list(range(n))                      # a permutation
     assert (np.diff(out["log2n"].astype(int)) <= 0).all()                           # 32, 16, 8, 4
     for l2 in (2, 3, 4, 5):
         b = out[out["log2n"] == l2]
-        kind = (b["flags"] & (TU_DST | TU_SKIP | TU_BYPASS)).astype(int)
+        kind = (b["flags"] & clustered).astype(int)
         assert (np.diff(kind) >= 0).all()                                           # kinds clustered
         for k in np.unique(kind):
             c = b[kind == k]
