@@ -232,3 +232,46 @@ def enable_transquant_bypass(ns) -> None:
         return bit
 
     cls.parse__cu_transquant_bypass_flag = parse__cu_transquant_bypass_flag
+
+
+def enable_pcm(ns) -> None:
+    """Test-harness patch: the reference's pcm branch cannot run.  cu.py:139-151 reads
+    `sps.log2_min_pcm_luma_coding_block_size` / `log2_max_...` (sps.py:95-101 stores only the
+    `_minus3` / `_diff_` syntax elements) and calls `parse__pcm_flag`, `parse__pcm_sample` and
+    (cu.py:484-485) `decode_pcm`, none of which exist.  Added here, for the pcm fuzz streams only:
+
+      * the two derived SPS variables (7.4.3.2.1: Log2MinIpcmCbSizeY, Log2MaxIpcmCbSizeY);
+      * pcm_flag: one terminate bin (9.3.4.3.5);
+      * pcm_sample(): 7.3.8.7 -- (1 << (log2CbSize << 1)) luma samples of PcmBitDepthY bits, then
+        Cb and Cr of PcmBitDepthC bits each, raster order inside the coding block; kept on the CU as
+        `pcm_sample_luma` (N, N) and `pcm_sample_chroma` (2, N/2, N/2), [row][col]; afterwards the
+        arithmetic decoding engine is initialised again (9.3.2.5);
+      * decode_pcm: only the CU's QpY (8.6.1; the in-loop filters read it), like every other CU."""
+    cls = sys.modules["cu"].Cu
+    if hasattr(cls, "parse__pcm_sample"):
+        return
+    import numpy as np
+    sps_cls = sys.modules["sps"].Sps
+    sps_cls.log2_min_pcm_luma_coding_block_size = property(
+        lambda self: self.log2_min_pcm_luma_coding_block_size_minus3 + 3)
+    sps_cls.log2_max_pcm_luma_coding_block_size = property(
+        lambda self: self.log2_min_pcm_luma_coding_block_size_minus3 + 3 + self.log2_diff_max_min_pcm_luma_coding_block_size)
+
+    def parse__pcm_flag(self):
+        bit = self.ctx.cabac.decode_terminate()
+        sys.modules["log"].syntax.info("pcm_flag = %d" % bit)
+        return bit
+
+    def parse__pcm_sample(self):
+        bs, sps = self.ctx.bs, self.ctx.sps
+        n = 1 << self.log2size
+        dy, dc = sps.pcm_sample_bit_depth_luma_minus1 + 1, sps.pcm_sample_bit_depth_chroma_minus1 + 1
+        self.pcm_sample_luma = np.array([bs.read_bits(dy) for _ in range(n * n)], np.int64).reshape(n, n)
+        h = n // 2
+        self.pcm_sample_chroma = np.array([bs.read_bits(dc) for _ in range(2 * h * h)], np.int64).reshape(2, h, h)
+        self.ctx.cabac.initialization_process_arithmetic_decoding_engine()
+
+    def decode_pcm(self):
+        self.decode_qp()
+
+    cls.parse__pcm_flag, cls.parse__pcm_sample, cls.decode_pcm = parse__pcm_flag, parse__pcm_sample, decode_pcm

@@ -164,6 +164,9 @@ class IntraReconstructor:
         self.avail = _Avail(img, sps, pps)
         self.bd = (int(sps.bit_depth_y), int(sps.bit_depth_c), int(sps.bit_depth_c))
         self.strong = bool(getattr(sps, "strong_intra_smoothing_enabled_flag", 0))
+        #: PcmBitDepthY, PcmBitDepthC (sps.py:97-98)
+        self.pcm_bd = (int(getattr(sps, "pcm_sample_bit_depth_luma_minus1", self.bd[0] - 1)) + 1,
+                       int(getattr(sps, "pcm_sample_bit_depth_chroma_minus1", self.bd[1] - 1)) + 1)
         w, h = self.avail.w, self.avail.h
         dt = np.uint8 if max(self.bd) <= 8 else np.uint16
         self.planes = [np.zeros((h, w), dt), np.zeros((h // 2, w // 2), dt), np.zeros((h // 2, w // 2), dt)]
@@ -240,6 +243,20 @@ class IntraReconstructor:
             for c in (1, 2):
                 self._tb(c, first.x >> 1, first.y >> 1, 2, int(cu.intra_pred_mode_c), residual)
 
+    def _pcm(self, cu):
+        """8.4.4.1 step for a pcm CU (cu.py:146-151): its samples are the pcm_sample_luma / pcm_sample_chroma
+        values shifted up to the picture's bit depth, no prediction, no residual.  The parser has to have kept
+        them ([row][col] arrays `pcm_sample_luma` (N, N), `pcm_sample_chroma` (2, N/2, N/2)); the reference
+        has no pcm_sample() at all (oracle/refshim.enable_pcm supplies it for the tests)."""
+        if not hasattr(cu, "pcm_sample_luma"):
+            raise ValueError("pcm CU at (%d,%d) carries no pcm_sample_luma / pcm_sample_chroma" % (cu.x, cu.y))
+        n = cu.size
+        self.planes[0][cu.y:cu.y + n, cu.x:cu.x + n] = np.asarray(cu.pcm_sample_luma) << (self.bd[0] - self.pcm_bd[0])
+        h = n >> 1
+        for c in (1, 2):
+            self.planes[c][cu.y >> 1:(cu.y >> 1) + h, cu.x >> 1:(cu.x >> 1) + h] = \
+                np.asarray(cu.pcm_sample_chroma[c - 1]) << (self.bd[c] - self.pcm_bd[1])
+
     def run(self, residual):
         """residual: (Y, Cb, Cr) int16 [row][col] planes (zero where no TB is coded)."""
         for addr in sorted(self.img.ctus, key=lambda a: self.avail.rs2ts[a]):
@@ -249,9 +266,10 @@ class IntraReconstructor:
                 if cu.pred_mode != MODE_INTRA:
                     raise NotImplementedError("inter prediction is outside this decoder's scope "
                                               "(the reference parses no motion compensation)")
-                if getattr(cu, "pcm_flag", 0):
-                    raise NotImplementedError("pcm samples (cu.py:146-151 parses them without storing)")
                 self.intra_map[cu.y >> 2:(cu.y + cu.size) >> 2, cu.x >> 2:(cu.x + cu.size) >> 2] = True
+                if getattr(cu, "pcm_flag", 0):
+                    self._pcm(cu)
+                    continue
                 self._tu(cu, cu.tu, residual)
         return tuple(self.planes)
 

@@ -129,7 +129,12 @@ def sps_rbsp(cfg) -> bytes:
         w.u(1, 0)                                              # sps_scaling_list_data_present_flag
     w.u(1, 0)                                                  # amp
     w.u(1, 1)                                                  # sample_adaptive_offset_enabled_flag
-    w.u(1, 0)                                                  # pcm
+    pcm = cfg.get("pcm")
+    w.u(1, 1 if pcm else 0)                                    # pcm_enabled_flag
+    if pcm:
+        w.u(4, pcm["bits_y"] - 1); w.u(4, pcm["bits_c"] - 1)   # pcm_sample_bit_depth_{luma,chroma}_minus1
+        w.ue(pcm["log2_min"] - 3); w.ue(pcm["log2_max"] - pcm["log2_min"])
+        w.u(1, pcm["lf_disabled"])                             # pcm_loop_filter_disabled_flag
     w.ue(0)                                                    # num_short_term_ref_pic_sets
     w.u(1, 0); w.u(1, 0)                                       # long-term refs, temporal mvp
     w.u(1, cfg["strong_smoothing"])
@@ -279,6 +284,16 @@ class CabacEncoder:
         else:
             self._renorm()
 
+    def pcm_samples(self, values, n_bits):
+        """After terminate(1) for pcm_flag: pcm_alignment_zero_bits, the raw samples (7.3.8.7), and the
+        arithmetic encoder starts again (9.3.2.5) -- the bits written so far stay."""
+        while len(self.bits) % 8:
+            self.bits.append(0)
+        for v, n in zip(values, n_bits):
+            self.bits += [(v >> (n - 1 - i)) & 1 for i in range(n)]
+        assert len(self.bits) % 8 == 0
+        self.low, self.range, self.first, self.outstanding = 0, 510, True, 0
+
     def payload(self) -> bytes:
         bits = list(self.bits)
         while len(bits) % 8:
@@ -300,7 +315,7 @@ class Policy:
                   "coded_sub_block_flag": 0.5 if d else 0.3, "sig_coeff_flag": 0.45 if d else 0.25,
                   "coeff_abs_level_greater1_flag": 0.4 if d else 0.15,
                   "coeff_abs_level_greater2_flag": 0.4 if d else 0.15,
-                  "sao_merge_leftup_flag": 0.3, "sao_type_idx_lumachroma_flag": 0.75}
+                  "sao_merge_leftup_flag": 0.3, "sao_type_idx_lumachroma_flag": 0.75, "pcm_flag": 0.35}
         self.p_bypass = 0.62 if big else (0.4 if d else 0.3)    # big: long remaining-level prefixes
         self.ones = 0
 
@@ -410,9 +425,41 @@ def make_stream(ns, cfg):
                     state["pic"], state["slice"] = state["pic"] + 1, 0
             return b
         cab.decode_decision, cab.decode_bypass, cab.decode_terminate = decision, bypass, terminate
+        state["enc"] = enc
 
     prepare(ns, cfg)
-    imgs, sps, pps = run_parser(ns, tmp.name, hook)
+    cu_cls, saved = sys.modules["cu"].Cu, None
+    if cfg.get("pcm"):
+        # pcm_flag is a terminate bin of its own (not the end of the slice segment) and pcm_sample() is raw
+        # bits between two arithmetic codewords: the hooked run draws both from the policy
+        saved = (cu_cls.parse__pcm_flag, cu_cls.parse__pcm_sample)
+        pcm = cfg["pcm"]
+
+        def parse__pcm_flag(self):
+            b = policy.decision("pcm_flag")
+            state["enc"].terminate(b)
+            return b
+
+        def parse__pcm_sample(self):
+            n = 1 << self.log2size
+            h = n // 2
+            # smooth-ish content: a random level per CU plus noise, so that the loop filters have decisions to make
+            def block(count, bits):
+                base = int(policy.rng.integers(0, 1 << bits))
+                amp = int(policy.rng.choice([1, 3, 1 << max(bits - 2, 1)]))
+                return np.clip(base + policy.rng.integers(-amp, amp + 1, count), 0, (1 << bits) - 1).astype(np.int64)
+            y = block(n * n, pcm["bits_y"])
+            c = np.concatenate([block(h * h, pcm["bits_c"]), block(h * h, pcm["bits_c"])])
+            self.pcm_sample_luma = y.reshape(n, n)
+            self.pcm_sample_chroma = c.reshape(2, h, h)
+            state["enc"].pcm_samples([int(v) for v in y] + [int(v) for v in c],
+                                     [pcm["bits_y"]] * (n * n) + [pcm["bits_c"]] * (2 * h * h))
+        cu_cls.parse__pcm_flag, cu_cls.parse__pcm_sample = parse__pcm_flag, parse__pcm_sample
+    try:
+        imgs, sps, pps = run_parser(ns, tmp.name, hook)
+    finally:
+        if saved:
+            cu_cls.parse__pcm_flag, cu_cls.parse__pcm_sample = saved
     os.unlink(tmp.name)
     assert len(imgs) == cfg["pictures"] and len(payloads) == sum(len(p) for p in pictures)
     k, body = 0, b""
@@ -468,6 +515,10 @@ def summarize(imgs, sps):
         modes = []
         for a in sorted(img.ctus):
             for cu in packer._leaf_cus(img.ctus[a]):
+                if getattr(cu, "pcm_flag", 0):
+                    modes.append((cu.x, cu.y, cu.log2size, "pcm", int(cu.qp_y), cu.pcm_sample_luma.tobytes(),
+                                  cu.pcm_sample_chroma.tobytes()))
+                    continue
                 modes.append((cu.x, cu.y, cu.log2size, cu.part_mode, cu.intra_pred_mode_c,
                               tuple(sorted((x, y, int(v)) for x, col in cu.intra_pred_mode_y.items()
                                            for y, v in col.items())), int(cu.cu_transquant_bypass_flag)))
@@ -506,11 +557,18 @@ STREAMS = [
     # 9 bit (round 2): the odd depth libavcodec can decode (9-bit packed arithmetic of deblocking and SAO, bdShift 11 / 6)
     ("rext9_sparse_ctb32", dict(bit_depth=9, profile=4, ctb_log2=5, dense=False, seed=21, qps=(20, 31, 42), width=96,
                                 height=64, cb_qp_offset=-2, cr_qp_offset=3, beta_offset_div2=1, tc_offset_div2=-1)),
+    # pcm coding units (round 2): raw samples at a lower PcmBitDepth between two arithmetic codewords, 8x8 .. 32x32;
+    # pcm_loop_filter_disabled_flag = 1 (deblocking and SAO leave them alone) / 0 (filtered like any intra CU)
+    ("main8_pcm_lf_disabled", dict(pcm=dict(bits_y=7, bits_c=5, log2_min=3, log2_max=5, lf_disabled=1), ctb_log2=5,
+                                   width=96, height=64, dense=True, seed=22, qps=(25, 33, 39))),
+    ("main10_pcm_filtered", dict(pcm=dict(bits_y=8, bits_c=10, log2_min=3, log2_max=4, lf_disabled=0), ctb_log2=4,
+                                 bit_depth=10, profile=2, width=64, height=48, dense=False, seed=23, qps=(22, 30, 38),
+                                 tu_depth=1, sao_chroma=0)),
 ]
 BASE = dict(width=128, height=96, bit_depth=8, profile=1, ctb_log2=6, tu_depth=2, scaling_lists="off",
             strong_smoothing=1, sdh=1, transform_skip=1, bypass=0, cb_qp_offset=0, cr_qp_offset=0,
             dbk_disable=0, beta_offset_div2=0, tc_offset_div2=0, sao_chroma=1, pictures=2, slices=1,
-            qps=(24, 32), dense=True, big=False, seed=10, tiles=None, lf_across_tiles=1)
+            qps=(24, 32), dense=True, big=False, seed=10, tiles=None, lf_across_tiles=1, pcm=None)
 
 
 def prepare(ns, cfg):
@@ -522,6 +580,8 @@ def prepare(ns, cfg):
         refshim.enable_multi_slice(ns)
     if cfg["bypass"]:
         refshim.enable_transquant_bypass(ns)
+    if cfg.get("pcm"):
+        refshim.enable_pcm(ns)
 
 
 def main():

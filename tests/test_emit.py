@@ -56,3 +56,35 @@ def test_sink_rejects_bad_blocks():
         s.add_tb(0, 0, 0, 2, 30, 0, np.full((4, 4), 40000))
     s.add_tb(0, 0, 0, 2, 30, 0, np.zeros((4, 4), np.int64))
     assert len(s.stream) == 4 and s.recs[0][5] & TU_LEVELS8
+
+
+def _fuzz_streams():
+    import fuzz_common as fz
+    return sorted(fz.manifest().items())
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("name,cfg", _fuzz_streams(), ids=[n for n, _ in _fuzz_streams()])
+def test_emission_on_the_fuzz_streams(name, cfg, c_oracle):
+    """The same equality on the libavcodec-pinned fuzz streams: bypass CUs, several slices, tiles (CUs arrive in
+    tile-scan order), PPS scaling lists, 9 .. 12 bit, and pcm CUs (a leaf CU without any TB)."""
+    import sys
+    import fuzz_common as fz
+    from p265_b200 import scaling_list
+    from oracle import refshim
+    if not refshim.shim_available() and not refshim.reference_available():
+        pytest.skip("baseline/_ref shim not present")
+    refshim.load()
+    emit.hook_parser(sys.modules["cu"])
+    imgs, sps, pps = fz.parse(name, cfg)
+    for img in imgs:
+        sf = scaling_list.active_table(sps, pps)
+        dense = packer.pack_pictures([img], sps, sf)
+        packed = emit.take(img, sps, sf)
+        assert packed is not None and len(packed.tus) == len(dense.tus)
+        tus, arena = spec_oracle.unpack_stream(packed.tus, packed.stream)
+        assert _tb_set(tus, arena) == _tb_set(dense.tus, dense.coeffs)
+        assert packed.bin_counts() == dense.bin_counts()
+        assert np.array_equal(c_oracle.residual_batch(packed.unpacked()), c_oracle.residual_batch(dense))
