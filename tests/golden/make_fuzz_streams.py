@@ -173,7 +173,7 @@ def pps_rbsp(cfg, sl=None) -> bytes:
     w.u(1, cfg["transform_skip"])
     w.u(1, 0)                                                  # cu_qp_delta_enabled_flag
     w.se(cfg["cb_qp_offset"]); w.se(cfg["cr_qp_offset"])
-    w.u(1, 0)                                                  # slice chroma qp offsets present
+    w.u(1, 1 if cfg.get("slice_chroma_offsets") else 0)        # pps_slice_chroma_qp_offsets_present_flag
     w.u(1, 0); w.u(1, 0)                                       # weighted pred / bipred
     w.u(1, cfg["bypass"])                                      # transquant_bypass_enabled_flag
     tiles = cfg.get("tiles")
@@ -200,7 +200,7 @@ def pps_rbsp(cfg, sl=None) -> bytes:
     return w.to_bytes()
 
 
-def slice_header_bits(cfg, first: bool, address: int, qp: int, across: int) -> BitWriter:
+def slice_header_bits(cfg, first: bool, address: int, qp: int, across: int, index: int = 0) -> BitWriter:
     w = BitWriter()
     w.u(1, 1 if first else 0)
     w.u(1, 0)                                                  # no_output_of_prior_pics_flag (IDR)
@@ -211,6 +211,9 @@ def slice_header_bits(cfg, first: bool, address: int, qp: int, across: int) -> B
     w.ue(2)                                                    # slice_type I
     w.u(1, 1); w.u(1, cfg["sao_chroma"])                       # slice_sao_luma_flag, slice_sao_chroma_flag
     w.se(qp - 26)                                              # slice_qp_delta (init_qp_minus26 = 0)
+    if cfg.get("slice_chroma_offsets"):                        # slice_cb_qp_offset, slice_cr_qp_offset: dequantisation
+        cb, cr = cfg["slice_chroma_offsets"][index % len(cfg["slice_chroma_offsets"])]   # only (8.6.1); deblocking's
+        w.se(cb); w.se(cr)                                     # cQpPicOffset is the PPS offset alone (8.7.2.5.5)
     w.u(1, across)                                             # slice_loop_filter_across_slices_enabled_flag
     if cfg.get("tiles"):
         w.ue(0)                                                # num_entry_point_offsets: one tile per slice
@@ -384,7 +387,8 @@ def make_stream(ns, cfg):
                                          replace=False).tolist()) if cfg["slices"] > 1 else [0]
         # slice_loop_filter_across_slices_enabled_flag: 1, 0, 1, ... (the first slice has no left / upper slice)
         pictures.append([(a, int(rng.choice(cfg["qps"])), 1 - (i & 1)) for i, a in enumerate(starts)])
-    headers = [[slice_header_bits(cfg, a == 0, a, qp, across).to_bytes() for a, qp, across in pic] for pic in pictures]
+    headers = [[slice_header_bits(cfg, a == 0, a, qp, across, i).to_bytes() for i, (a, qp, across) in enumerate(pic)]
+               for pic in pictures]
     # pass 1: headers only; the hooked parser writes the slice data
     skeleton = head + b"".join(nal_unit(19, h) for pic in headers for h in pic) + b"\x00" * 16
     tmp = tempfile.NamedTemporaryFile(suffix=".bin", delete=False)
@@ -557,6 +561,10 @@ STREAMS = [
     # 9 bit (round 2): the odd depth libavcodec can decode (9-bit packed arithmetic of deblocking and SAO, bdShift 11 / 6)
     ("rext9_sparse_ctb32", dict(bit_depth=9, profile=4, ctb_log2=5, dense=False, seed=21, qps=(20, 31, 42), width=96,
                                 height=64, cb_qp_offset=-2, cr_qp_offset=3, beta_offset_div2=1, tc_offset_div2=-1)),
+    # slice-level chroma QP offsets (round 2): they move the chroma qP of dequantisation, not deblocking's QpC
+    ("main8_slice_chroma_offsets", dict(slices=3, slice_chroma_offsets=((5, -6), (-7, 4), (0, 8)), cb_qp_offset=4,
+                                        cr_qp_offset=-3, ctb_log2=5, width=128, height=64, dense=True, seed=24,
+                                        qps=(23, 31, 38), tc_offset_div2=1)),
     # pcm coding units (round 2): raw samples at a lower PcmBitDepth between two arithmetic codewords, 8x8 .. 32x32;
     # pcm_loop_filter_disabled_flag = 1 (deblocking and SAO leave them alone) / 0 (filtered like any intra CU)
     ("main8_pcm_lf_disabled", dict(pcm=dict(bits_y=7, bits_c=5, log2_min=3, log2_max=5, lf_disabled=1), ctb_log2=5,
@@ -568,7 +576,7 @@ STREAMS = [
 BASE = dict(width=128, height=96, bit_depth=8, profile=1, ctb_log2=6, tu_depth=2, scaling_lists="off",
             strong_smoothing=1, sdh=1, transform_skip=1, bypass=0, cb_qp_offset=0, cr_qp_offset=0,
             dbk_disable=0, beta_offset_div2=0, tc_offset_div2=0, sao_chroma=1, pictures=2, slices=1,
-            qps=(24, 32), dense=True, big=False, seed=10, tiles=None, lf_across_tiles=1, pcm=None)
+            qps=(24, 32), dense=True, big=False, seed=10, tiles=None, lf_across_tiles=1, pcm=None, slice_chroma_offsets=None)
 
 
 def prepare(ns, cfg):
