@@ -13,6 +13,7 @@ Transform, nothing else is touched:
   4. stub `matplotlib`, `matplotlib.pyplot`, `matplotlib.patches` (imported at
      image.py:1-2, tree.py:2-3, slice.py:1; never used while decoding)
   5. pps.py:64-65: the misspelt `num_tile_colums_minus1` (tile branch only; see transform_source)
+  6. slice.py:174-175: the unimplemented deblocking_filter_override branch (see transform_source)
 
 Only tests/, bench.py's cpu_baseline / --impl reference leg and
 __graft_entry__ may import this module; the product package never does.
@@ -61,7 +62,7 @@ def _fix_division(src: str) -> str:
 
 
 #: bump when the transform changes: build() regenerates a shim directory with another stamp
-SHIM_VERSION = "5"
+SHIM_VERSION = "6"
 
 
 def transform_source(src: str, name: str) -> str:
@@ -89,6 +90,19 @@ def transform_source(src: str, name: str) -> str:
         #    ... and slice.py:182 calls `self.ue(...)` (no such method) for num_entry_point_offsets, a syntax
         #    element that only exists when tiles or wavefronts are enabled
         src = src.replace('self.ue("num_entry_point_offsets")', 'bs.ue("num_entry_point_offsets")')
+        # 6. harness patch for the deblocking-override fuzz stream: slice.py:174-175 raises "Unimplemented yet" when
+        #    deblocking_filter_override_flag = 1 (and :178 reads slice_deblocking_filter_disabled_flag, which nothing
+        #    assigns).  7.3.6.1: the flag, then the two offsets unless the slice disables deblocking.
+        old = ('            if self.deblocking_filter_override_flag:\n'
+               '                raise "Unimplemented yet"\n')
+        new = ('            self.slice_deblocking_filter_disabled_flag = getattr(self.pps, "pps_deblocking_filter_disabled_flag", 0)\n'
+               '            if self.deblocking_filter_override_flag:\n'
+               '                self.slice_deblocking_filter_disabled_flag = bs.u(1, "slice_deblocking_filter_disabled_flag")\n'
+               '                if not self.slice_deblocking_filter_disabled_flag:\n'
+               '                    self.slice_beta_offset_div2 = bs.se("slice_beta_offset_div2")\n'
+               '                    self.slice_tc_offset_div2 = bs.se("slice_tc_offset_div2")\n')
+        assert old in src, "slice.py: deblocking override branch not found"
+        src = src.replace(old, new)
     return src
 
 

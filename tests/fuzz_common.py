@@ -18,6 +18,10 @@ comparison stays bit-exact everywhere and the deviations are characterised exact
     CUs only in the top-left (CtbSize/2)^2 luma area of a CTB for the chroma planes (the
     restore loop takes the chroma width / height as luma extents).
 
+  * per-slice deblocking override, chroma only: the tc offset of an edge segment is the current or the left CTB's by
+    loop position, not that of the slice holding the q0 sample (`lav_chroma_tc_mask`; one stream, differences
+    confined to the mask, luma exact).
+
 `out_spec` (the standard's rules, what the product implements) is returned next to `out_lav`
 (libavcodec's rules) so the tests can also state where the two differ.
 """
@@ -145,11 +149,44 @@ def check_stream(name, cfg, backend, want):
     diffs = []
     for p, img in enumerate(imgs):
         rec, out_spec, out_lav = decode_picture(img, sps, pps, backend)
+        tc_dev = [0, 0, 0]
         for c, n in enumerate(COMPS):
             assert np.array_equal(rec[c], want["%s/rec%d_%s" % (name, p, n)]), (name, "rec", p, n)
+            if c and cfg.get("lav_chroma_tc_dev"):
+                d = out_lav[c] != want["%s/out%d_%s" % (name, p, n)]
+                assert not (d & ~lav_chroma_tc_mask(img, sps, pps)).any(), (name, "out", p, n)
+                tc_dev[c] = int(d.sum())
+                continue
             assert np.array_equal(out_lav[c], want["%s/out%d_%s" % (name, p, n)]), (name, "out", p, n)
-        diffs.append([int((out_spec[c] != out_lav[c]).sum()) for c in range(3)])
+        diffs.append([int((out_spec[c] != out_lav[c]).sum()) + tc_dev[c] for c in range(3)])
     return diffs
+
+
+def lav_chroma_tc_mask(img, sps, pps):
+    """Third libavcodec deviation (per-slice deblocking override with different slice_tc_offset_div2 in neighbouring
+    CTBs): for chroma it takes the tc offset of an edge segment from the current or the left CTB by loop position
+    instead of from the slice of the q0 sample.  Where it can matter: the p0 / q0 samples of the 8x8 chroma edge grid
+    inside CTBs whose 3x3 CTB neighbourhood does not share one tc offset."""
+    from p265_b200 import deblock_api
+    wc, hc = int(sps.pic_width_in_ctbs_y), int(sps.pic_height_in_ctbs_y)
+    w, h = int(sps.pic_width_in_luma_samples) // 2, int(sps.pic_height_in_luma_samples) // 2
+    cs = 1 << (int(sps.ctb_log2_size_y) - 1)
+    slices = deblock_api._slice_params(img, pps)
+    tc = np.zeros((hc + 2, wc + 2), np.int64)
+    for a, ctu in img.ctus.items():
+        tc[a // wc + 1, a % wc + 1] = slices[int(ctu.slice_addr)][2]
+    tc[0], tc[-1], tc[:, 0], tc[:, -1] = tc[1], tc[-2], tc[:, 1], tc[:, -2]
+    tc[0, 0], tc[0, -1], tc[-1, 0], tc[-1, -1] = tc[1, 1], tc[1, -2], tc[-2, 1], tc[-2, -2]
+    mixed = np.zeros((hc, wc), bool)
+    for dy in range(3):
+        for dx in range(3):
+            mixed |= tc[dy:dy + hc, dx:dx + wc] != tc[1:-1, 1:-1]
+    m = np.kron(mixed, np.ones((cs, cs), bool))[:h, :w]
+    grown = m.copy()                                         # the p0 sample lies in the neighbouring CTB
+    grown[1:] |= m[:-1]; grown[:-1] |= m[1:]; grown[:, 1:] |= m[:, :-1]; grown[:, :-1] |= m[:, 1:]
+    y, x = np.mgrid[0:h, 0:w]
+    on_edge = (x % 8 == 0) | (x % 8 == 7) | (y % 8 == 0) | (y % 8 == 7)
+    return grown & on_edge
 
 
 class OracleBackend:

@@ -183,10 +183,10 @@ def pps_rbsp(cfg, sl=None) -> bytes:
         w.u(1, 1)                                              # uniform_spacing_flag
         w.u(1, cfg["lf_across_tiles"])                         # loop_filter_across_tiles_enabled_flag
     w.u(1, 1)                                                  # pps_loop_filter_across_slices_enabled_flag
-    ctl = cfg["dbk_disable"] or cfg["beta_offset_div2"] or cfg["tc_offset_div2"]
+    ctl = cfg["dbk_disable"] or cfg["beta_offset_div2"] or cfg["tc_offset_div2"] or cfg.get("dbk_override")
     w.u(1, 1 if ctl else 0)                                    # deblocking_filter_control_present_flag
     if ctl:
-        w.u(1, 0)                                              # override enabled
+        w.u(1, 1 if cfg.get("dbk_override") else 0)            # deblocking_filter_override_enabled_flag
         w.u(1, cfg["dbk_disable"])
         if not cfg["dbk_disable"]:
             w.se(cfg["beta_offset_div2"]); w.se(cfg["tc_offset_div2"])
@@ -214,6 +214,13 @@ def slice_header_bits(cfg, first: bool, address: int, qp: int, across: int, inde
     if cfg.get("slice_chroma_offsets"):                        # slice_cb_qp_offset, slice_cr_qp_offset: dequantisation
         cb, cr = cfg["slice_chroma_offsets"][index % len(cfg["slice_chroma_offsets"])]   # only (8.6.1); deblocking's
         w.se(cb); w.se(cr)                                     # cQpPicOffset is the PPS offset alone (8.7.2.5.5)
+    if cfg.get("dbk_override"):                                # None: PPS values | "off" | (beta_offset_div2, tc_offset_div2)
+        o = cfg["dbk_override"][index % len(cfg["dbk_override"])]
+        w.u(1, 0 if o is None else 1)                          # deblocking_filter_override_flag
+        if o is not None:
+            w.u(1, 1 if o == "off" else 0)                     # slice_deblocking_filter_disabled_flag
+            if o != "off":
+                w.se(o[0]); w.se(o[1])                         # slice_beta_offset_div2, slice_tc_offset_div2
     w.u(1, across)                                             # slice_loop_filter_across_slices_enabled_flag
     if cfg.get("tiles"):
         w.ue(0)                                                # num_entry_point_offsets: one tile per slice
@@ -565,6 +572,20 @@ STREAMS = [
     ("main8_slice_chroma_offsets", dict(slices=3, slice_chroma_offsets=((5, -6), (-7, 4), (0, 8)), cb_qp_offset=4,
                                         cr_qp_offset=-3, ctb_log2=5, width=128, height=64, dense=True, seed=24,
                                         qps=(23, 31, 38), tc_offset_div2=1)),
+    # per-slice deblocking override (round 2): PPS offsets, own offsets, deblocking off, in neighbouring slices; the
+    # parameters of an edge are those of the slice that holds its q0 sample (8.7.2.5.3), an edge belongs to the CU on
+    # its right / lower side (8.7.2.3) -- slices 2 and 4 filter across their upper / left boundaries INTO slices with
+    # deblocking off (slice_loop_filter_across_slices_enabled_flag: 1, 0, 1, 0, 1)
+    ("main8_dbk_override_slices", dict(slices=5, dbk_override=("off", (3, 2), None, "off", (-4, 2)), beta_offset_div2=-1,
+                                       tc_offset_div2=2, ctb_log2=4, width=96, height=64, dense=True, seed=25,
+                                       qps=(28, 35, 42), sao_chroma=0)),
+    # ... the same with slice_tc_offset_div2 differing between slices as well.  Luma is bit-exact; for CHROMA libavcodec
+    # picks the tc offset of an edge segment from the current or the left CTB by loop position, not from the slice
+    # of the q0 sample (observed; 8.7.2.5.5 says the latter): the test confines the chroma differences to the edge
+    # samples next to CTBs whose neighbours carry another tc offset (lav_chroma_tc_dev)
+    ("main8_dbk_override_tc", dict(slices=5, dbk_override=("off", (3, -2), None, "off", (-4, 5)), beta_offset_div2=-1,
+                                   tc_offset_div2=2, ctb_log2=4, width=96, height=64, dense=True, seed=25,
+                                   qps=(28, 35, 42), sao_chroma=0, lav_chroma_tc_dev=1)),
     # pcm coding units (round 2): raw samples at a lower PcmBitDepth between two arithmetic codewords, 8x8 .. 32x32;
     # pcm_loop_filter_disabled_flag = 1 (deblocking and SAO leave them alone) / 0 (filtered like any intra CU)
     ("main8_pcm_lf_disabled", dict(pcm=dict(bits_y=7, bits_c=5, log2_min=3, log2_max=5, lf_disabled=1), ctb_log2=5,
@@ -576,7 +597,7 @@ STREAMS = [
 BASE = dict(width=128, height=96, bit_depth=8, profile=1, ctb_log2=6, tu_depth=2, scaling_lists="off",
             strong_smoothing=1, sdh=1, transform_skip=1, bypass=0, cb_qp_offset=0, cr_qp_offset=0,
             dbk_disable=0, beta_offset_div2=0, tc_offset_div2=0, sao_chroma=1, pictures=2, slices=1,
-            qps=(24, 32), dense=True, big=False, seed=10, tiles=None, lf_across_tiles=1, pcm=None, slice_chroma_offsets=None)
+            qps=(24, 32), dense=True, big=False, seed=10, tiles=None, lf_across_tiles=1, pcm=None, slice_chroma_offsets=None, dbk_override=None, lav_chroma_tc_dev=0)
 
 
 def prepare(ns, cfg):

@@ -15,6 +15,9 @@ def test_oracle_chain_equals_libavcodec(name, cfg, c_oracle):
     diffs = fz.check_stream(name, cfg, fz.OracleBackend(c_oracle), fz.answers())
     total = [sum(d[c] for d in diffs) for c in range(3)]
     restore = cfg["bypass"] or bool(cfg.get("pcm") and cfg["pcm"]["lf_disabled"])
+    if cfg.get("lav_chroma_tc_dev"):
+        assert total[1] > 0 and total[2] > 0      # the deviation is there (chroma SAO is off in that stream; luma is
+        #                                           compared exactly inside check_stream)
     if cfg["slices"] == 1 and not restore:
         assert total == [0, 0, 0]            # no rule on which the standard and libavcodec differ is in play
     if restore:
