@@ -14,6 +14,7 @@ Transform, nothing else is touched:
      image.py:1-2, tree.py:2-3, slice.py:1; never used while decoding)
   5. pps.py:64-65: the misspelt `num_tile_colums_minus1` (tile branch only; see transform_source)
   6. slice.py:174-175: the unimplemented deblocking_filter_override branch (see transform_source)
+  7. cu.py:557 / tu.py:100: two one-token fixes on the cu_qp_delta path (see transform_source)
 
 Only tests/, bench.py's cpu_baseline / --impl reference leg and
 __graft_entry__ may import this module; the product package never does.
@@ -62,7 +63,7 @@ def _fix_division(src: str) -> str:
 
 
 #: bump when the transform changes: build() regenerates a shim directory with another stamp
-SHIM_VERSION = "6"
+SHIM_VERSION = "7"
 
 
 def transform_source(src: str, name: str) -> str:
@@ -86,6 +87,16 @@ def transform_source(src: str, name: str) -> str:
     if name == "cu.py":
         #    ... and cu.py:518 (tile branch of decode_qp) reads the misspelt `sps.ctb_log2size_y`
         src = src.replace("self.ctx.sps.ctb_log2size_y", "self.ctx.sps.ctb_log2_size_y")
+        # 7. harness patches for the cu_qp_delta fuzz stream (only reached when cu_qp_delta_enabled_flag = 1;
+        #    sanity.bin: 0).  cu.py:557: qPY_B falls back to qPY_PREV when the upper neighbour is unavailable OR lies in
+        #    another CTB (8.6.1, as cu.py:545 has it for qPY_A); the reference wrote `and`
+        old = "if available_b == False and self.get_root().addr_ts != derived_ctb_addr_b:"
+        assert old in src, "cu.py: qPY_B condition not found"
+        src = src.replace(old, old.replace(" and ", " or "))
+    if name == "tu.py":
+        #    ... and tu.py:100 reads the misspelt `self.cu_qp_data_abs`
+        assert "self.cu_qp_data_abs" in src
+        src = src.replace("self.cu_qp_data_abs", "self.cu_qp_delta_abs")
     if name == "slice.py":
         #    ... and slice.py:182 calls `self.ue(...)` (no such method) for num_entry_point_offsets, a syntax
         #    element that only exists when tiles or wavefronts are enabled
@@ -289,3 +300,37 @@ def enable_pcm(ns) -> None:
         self.decode_qp()
 
     cls.parse__pcm_flag, cls.parse__pcm_sample, cls.decode_pcm = parse__pcm_flag, parse__pcm_sample, decode_pcm
+
+
+def enable_cu_qp_delta(ns) -> None:
+    """Test-harness patch: tu.py:94,96 call `parse__cu_qp_delta_abs` / `parse__cu_qp_delta_sign_flag`, which the
+    reference never defines.  9.3.3.10 / Table 9-4x: cu_qp_delta_abs = prefix TR(cMax 5) with context-coded bins
+    (ctxInc 0 for the first, 1 for the others; two contexts per initType, cabac.py:32) + suffix EG0 in bypass bins
+    when the prefix is 5; the sign is one bypass bin."""
+    cls = sys.modules["tu"].Tu
+    if hasattr(cls, "parse__cu_qp_delta_abs"):
+        return
+
+    def parse__cu_qp_delta_abs(self):
+        cab = self.ctx.cabac
+        base = 2 * int(getattr(self.ctx.img.slice_hdr, "init_type", 0) or 0)
+        prefix = 0
+        while prefix < 5 and cab.decode_decision("cu_qp_delta_abs", base + (1 if prefix else 0)):
+            prefix += 1
+        value = prefix
+        if prefix == 5:
+            k = 0
+            while cab.decode_bypass():
+                value += 1 << k
+                k += 1
+            for i in range(k - 1, -1, -1):
+                value += cab.decode_bypass() << i
+        sys.modules["log"].syntax.info("cu_qp_delta_abs = %d" % value)
+        return value
+
+    def parse__cu_qp_delta_sign_flag(self):
+        bit = self.ctx.cabac.decode_bypass()
+        sys.modules["log"].syntax.info("cu_qp_delta_sign_flag = %d" % bit)
+        return bit
+
+    cls.parse__cu_qp_delta_abs, cls.parse__cu_qp_delta_sign_flag = parse__cu_qp_delta_abs, parse__cu_qp_delta_sign_flag

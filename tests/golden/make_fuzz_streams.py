@@ -171,7 +171,9 @@ def pps_rbsp(cfg, sl=None) -> bytes:
     w.se(0)                                                    # init_qp_minus26
     w.u(1, 0)                                                  # constrained_intra_pred_flag
     w.u(1, cfg["transform_skip"])
-    w.u(1, 0)                                                  # cu_qp_delta_enabled_flag
+    w.u(1, 1 if cfg.get("cu_qp_delta") is not None else 0)     # cu_qp_delta_enabled_flag
+    if cfg.get("cu_qp_delta") is not None:
+        w.ue(cfg["cu_qp_delta"])                               # diff_cu_qp_delta_depth
     w.se(cfg["cb_qp_offset"]); w.se(cfg["cr_qp_offset"])
     w.u(1, 1 if cfg.get("slice_chroma_offsets") else 0)        # pps_slice_chroma_qp_offsets_present_flag
     w.u(1, 0); w.u(1, 0)                                       # weighted pred / bipred
@@ -328,9 +330,17 @@ class Policy:
                   "sao_merge_leftup_flag": 0.3, "sao_type_idx_lumachroma_flag": 0.75, "pcm_flag": 0.35}
         self.p_bypass = 0.62 if big else (0.4 if d else 0.3)    # big: long remaining-level prefixes
         self.ones = 0
+        self.qpd = 0
 
     def decision(self, name):
-        return int(self.rng.random() < self.p.get(name, 0.5))
+        b = int(self.rng.random() < self.p.get(name, 0.5))
+        if name == "cu_qp_delta_abs":                      # prefix of at most 4 ones: |CuQpDeltaVal| <= 4, no suffix
+            if self.qpd >= 4:
+                b = 0
+            self.qpd = self.qpd + 1 if b else 0
+        else:
+            self.qpd = 0
+        return b
 
     def bypass(self):
         b = int(self.rng.random() < self.p_bypass)
@@ -586,6 +596,10 @@ STREAMS = [
     ("main8_dbk_override_tc", dict(slices=5, dbk_override=("off", (3, -2), None, "off", (-4, 5)), beta_offset_div2=-1,
                                    tc_offset_div2=2, ctb_log2=4, width=96, height=64, dense=True, seed=25,
                                    qps=(28, 35, 42), sao_chroma=0, lav_chroma_tc_dev=1)),
+    # cu_qp_delta (round 2): quantisation groups of 8x8, a QP of its own for every CU with a coded block -- qP differs
+    # from TB to TB inside a warp's 32 TBs, deblocking averages QpP / QpQ across every CU edge, QpC over its whole table
+    ("main10_cu_qp_delta", dict(cu_qp_delta=2, bit_depth=10, profile=2, ctb_log2=5, width=128, height=64, dense=True,
+                                seed=26, qps=(24, 37), slices=2, cb_qp_offset=5, cr_qp_offset=-4, tc_offset_div2=1)),
     # pcm coding units (round 2): raw samples at a lower PcmBitDepth between two arithmetic codewords, 8x8 .. 32x32;
     # pcm_loop_filter_disabled_flag = 1 (deblocking and SAO leave them alone) / 0 (filtered like any intra CU)
     ("main8_pcm_lf_disabled", dict(pcm=dict(bits_y=7, bits_c=5, log2_min=3, log2_max=5, lf_disabled=1), ctb_log2=5,
@@ -597,7 +611,7 @@ STREAMS = [
 BASE = dict(width=128, height=96, bit_depth=8, profile=1, ctb_log2=6, tu_depth=2, scaling_lists="off",
             strong_smoothing=1, sdh=1, transform_skip=1, bypass=0, cb_qp_offset=0, cr_qp_offset=0,
             dbk_disable=0, beta_offset_div2=0, tc_offset_div2=0, sao_chroma=1, pictures=2, slices=1,
-            qps=(24, 32), dense=True, big=False, seed=10, tiles=None, lf_across_tiles=1, pcm=None, slice_chroma_offsets=None, dbk_override=None, lav_chroma_tc_dev=0)
+            qps=(24, 32), dense=True, big=False, seed=10, tiles=None, lf_across_tiles=1, pcm=None, slice_chroma_offsets=None, dbk_override=None, lav_chroma_tc_dev=0, cu_qp_delta=None)
 
 
 def prepare(ns, cfg):
@@ -611,6 +625,8 @@ def prepare(ns, cfg):
         refshim.enable_transquant_bypass(ns)
     if cfg.get("pcm"):
         refshim.enable_pcm(ns)
+    if cfg.get("cu_qp_delta") is not None:
+        refshim.enable_cu_qp_delta(ns)
 
 
 def main():
