@@ -15,6 +15,7 @@ Transform, nothing else is touched:
   5. pps.py:64-65: the misspelt `num_tile_colums_minus1` (tile branch only; see transform_source)
   6. slice.py:174-175: the unimplemented deblocking_filter_override branch (see transform_source)
   7. cu.py:557 / tu.py:100: two one-token fixes on the cu_qp_delta path (see transform_source)
+  8. sps.py:90: `scaling_list_data.decode()` -> `self.scaling_list_data.decode()` (see transform_source)
 
 Only tests/, bench.py's cpu_baseline / --impl reference leg and
 __graft_entry__ may import this module; the product package never does.
@@ -63,7 +64,7 @@ def _fix_division(src: str) -> str:
 
 
 #: bump when the transform changes: build() regenerates a shim directory with another stamp
-SHIM_VERSION = "7"
+SHIM_VERSION = "8"
 
 
 def transform_source(src: str, name: str) -> str:
@@ -93,6 +94,12 @@ def transform_source(src: str, name: str) -> str:
         old = "if available_b == False and self.get_root().addr_ts != derived_ctb_addr_b:"
         assert old in src, "cu.py: qPY_B condition not found"
         src = src.replace(old, old.replace(" and ", " or "))
+    if name == "sps.py":
+        # 8. harness patch for the SPS scaling-list fuzz streams: sps.py:90 calls `scaling_list_data.decode()` on an
+        #    undefined local name (the object is `self.scaling_list_data`, sps.py:18)
+        old = "                scaling_list_data.decode()"
+        assert old in src, "sps.py: scaling_list_data.decode() not found"
+        src = src.replace(old, "                self.scaling_list_data.decode()")
     if name == "tu.py":
         #    ... and tu.py:100 reads the misspelt `self.cu_qp_data_abs`
         assert "self.cu_qp_data_abs" in src

@@ -111,7 +111,7 @@ def vps_rbsp(cfg) -> bytes:
     return w.to_bytes()
 
 
-def sps_rbsp(cfg) -> bytes:
+def sps_rbsp(cfg, sl=None) -> bytes:
     w = BitWriter()
     w.u(4, 0); w.u(3, 0); w.u(1, 1)
     profile_tier_level(w, cfg["profile"])
@@ -126,7 +126,9 @@ def sps_rbsp(cfg) -> bytes:
     w.ue(cfg["tu_depth"]); w.ue(cfg["tu_depth"])
     w.u(1, cfg["scaling_lists"] != "off")
     if cfg["scaling_lists"] != "off":
-        w.u(1, 0)                                              # sps_scaling_list_data_present_flag
+        w.u(1, 1 if sl else 0)                                 # sps_scaling_list_data_present_flag
+        if sl:
+            write_scaling_list_data(w, *sl)
     w.u(1, 0)                                                  # amp
     w.u(1, 1)                                                  # sample_adaptive_offset_enabled_flag
     pcm = cfg.get("pcm")
@@ -378,10 +380,12 @@ def make_stream(ns, cfg):
     ctb = 1 << cfg["ctb_log2"]
     cfg["ctbs_w"], cfg["ctbs_h"] = -(-cfg["width"] // ctb), -(-cfg["height"] // ctb)
     n_ctb = cfg["ctbs_w"] * cfg["ctbs_h"]
-    sl = None
-    if cfg["scaling_lists"] == "pps":
+    sl = sl_sps = None
+    if "pps" in cfg["scaling_lists"]:
         sl = random_scaling_lists(cfg["seed"])
-    head = nal_unit(32, vps_rbsp(cfg)) + nal_unit(33, sps_rbsp(cfg)) + nal_unit(34, pps_rbsp(cfg, sl))
+    if "sps" in cfg["scaling_lists"]:
+        sl_sps = random_scaling_lists(cfg["seed"] + 100)
+    head = nal_unit(32, vps_rbsp(cfg)) + nal_unit(33, sps_rbsp(cfg, sl_sps)) + nal_unit(34, pps_rbsp(cfg, sl))
     # slices of every picture: list of (first CTB address, qp, across flag)
     rng = np.random.default_rng(cfg["seed"] + 1)
     pictures = []
@@ -600,6 +604,11 @@ STREAMS = [
     # from TB to TB inside a warp's 32 TBs, deblocking averages QpP / QpQ across every CU edge, QpC over its whole table
     ("main10_cu_qp_delta", dict(cu_qp_delta=2, bit_depth=10, profile=2, ctb_log2=5, width=128, height=64, dense=True,
                                 seed=26, qps=(24, 37), slices=2, cb_qp_offset=5, cr_qp_offset=-4, tc_offset_div2=1)),
+    # scaling lists in the SPS (round 2), and in both parameter sets: the PPS lists win (7.4.3.3.1)
+    ("main8_sps_lists", dict(scaling_lists="sps", ctb_log2=5, dense=True, seed=27, qps=(21, 29, 36), width=96, height=64,
+                             sdh=0)),
+    ("main10_sps_and_pps_lists", dict(scaling_lists="sps+pps", bit_depth=10, profile=2, ctb_log2=5, dense=True, seed=28,
+                                      qps=(25, 33), width=64, height=64, pictures=1)),
     # pcm coding units (round 2): raw samples at a lower PcmBitDepth between two arithmetic codewords, 8x8 .. 32x32;
     # pcm_loop_filter_disabled_flag = 1 (deblocking and SAO leave them alone) / 0 (filtered like any intra CU)
     ("main8_pcm_lf_disabled", dict(pcm=dict(bits_y=7, bits_c=5, log2_min=3, log2_max=5, lf_disabled=1), ctb_log2=5,
@@ -617,7 +626,7 @@ BASE = dict(width=128, height=96, bit_depth=8, profile=1, ctb_log2=6, tu_depth=2
 def prepare(ns, cfg):
     """Harness patches a stream needs before the reference's parser can read it (also used by
     the tests): see oracle/refshim.py for what each one works around."""
-    if cfg["scaling_lists"] == "pps":
+    if cfg["scaling_lists"] in ("pps", "sps", "sps+pps"):
         use_sld_dropin(ns)
     if cfg["slices"] > 1:
         refshim.enable_multi_slice(ns)

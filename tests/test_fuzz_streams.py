@@ -30,7 +30,7 @@ def test_the_streams_cover_what_sanity_bin_does_not():
     m = fz.manifest()
     assert {c["bit_depth"] for c in m.values()} == {8, 9, 10, 12}
     assert {c["ctb_log2"] for c in m.values()} == {4, 5, 6}
-    assert {c["scaling_lists"] for c in m.values()} == {"off", "default", "pps"}
+    assert {c["scaling_lists"] for c in m.values()} == {"off", "default", "pps", "sps", "sps+pps"}
     assert any(c["bypass"] for c in m.values()) and any(c["slices"] > 1 for c in m.values())
     assert any(c["dbk_disable"] for c in m.values()) and any(c["tc_offset_div2"] for c in m.values())
     assert any(c["cb_qp_offset"] for c in m.values()) and sum(c["tbs"] for c in m.values()) > 3000
